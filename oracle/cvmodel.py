@@ -1,0 +1,257 @@
+"""Closed-form numpy models of the OpenCV primitives on the hot path.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  No cv2 import here: these
+are the specifications the CUDA kernels are checked against, and they are
+themselves checked bit-exactly against cv2 4.13.0 in
+``tests/test_oracle_cvmodel.py`` (exhaustive 2^24 colours for the colour
+conversions, random images for resize / morphology).
+
+The reference reaches these primitives at (paths relative to the reference
+root): ``cv2.cvtColor`` unscreen/colorfiltering/agent.py:310,352 and
+unscreen/utils/fgfuncs.py:36,39,55,100-101,109,129,136; ``cv2.resize``
+unscreen/colorfiltering/agent.py:315-316,342, unscreen/trimap/agent.py:52,59;
+``cv2.dilate/erode/getStructuringElement`` unscreen/utils/maskprocess.py:16-18,
+31-33; ``cv2.inRange`` unscreen/utils/fgfuncs.py:60.
+"""
+import numpy as np
+
+# --------------------------------------------------------------------------
+# colour conversions
+# --------------------------------------------------------------------------
+
+_HSV_SHIFT = 12
+
+
+def hsv_div_tables():
+    """sdiv/hdiv fixed-point reciprocal tables of cv2's 8-bit BGR2HSV
+    (round-half-even construction, H range 180)."""
+    i = np.arange(1, 256, dtype=np.float64)
+    sdiv = np.zeros(256, np.int32)
+    hdiv = np.zeros(256, np.int32)
+    sdiv[1:] = np.rint((255 << _HSV_SHIFT) / i).astype(np.int32)
+    hdiv[1:] = np.rint((180 << _HSV_SHIFT) / (6.0 * i)).astype(np.int32)
+    return sdiv, hdiv
+
+
+_SDIV, _HDIV = hsv_div_tables()
+
+
+def bgr2hsv(img):
+    """cv2.cvtColor(img, COLOR_BGR2HSV) for uint8 (H in [0,179])."""
+    img = np.asarray(img)
+    b = img[..., 0].astype(np.int32)
+    g = img[..., 1].astype(np.int32)
+    r = img[..., 2].astype(np.int32)
+    v = np.maximum(np.maximum(b, g), r)
+    mn = np.minimum(np.minimum(b, g), r)
+    d = v - mn
+    s = (d * _SDIV[v] + (1 << (_HSV_SHIFT - 1))) >> _HSV_SHIFT
+    # hue numerator, priority r, then g, then b
+    h = np.where(v == r, g - b, np.where(v == g, b - r + 2 * d, r - g + 4 * d))
+    h = (h * _HDIV[d] + (1 << (_HSV_SHIFT - 1))) >> _HSV_SHIFT  # arithmetic shift
+    h = np.where(h < 0, h + 180, h)
+    return np.stack([h, s, v], axis=-1).astype(np.uint8)
+
+
+def bgr2gray(img):
+    """cv2.cvtColor(img, COLOR_BGR2GRAY) for uint8 (15-bit coefficients)."""
+    img = np.asarray(img)
+    b = img[..., 0].astype(np.int32)
+    g = img[..., 1].astype(np.int32)
+    r = img[..., 2].astype(np.int32)
+    return ((3735 * b + 19235 * g + 9798 * r + 16384) >> 15).astype(np.uint8)
+
+
+_SECTOR = np.array([[1, 3, 0], [1, 0, 2], [3, 0, 1], [0, 2, 1], [0, 1, 3], [2, 1, 0]])
+
+
+def hsv2bgr_f32(hsv):
+    """The float32 value cv2's HSV2BGR computes before the final cast to u8
+    (scaled by 255).  cv2 is not self-consistent about that cast: whole-image
+    (SIMD) calls truncate, 1-pixel (scalar tail) calls round-half-even
+     -- hence the reference's composites are +-1 LSB."""
+    hsv = np.asarray(hsv)
+    f = np.float32
+    h = hsv[..., 0].astype(f) * f(6.0 / 180.0)
+    s = hsv[..., 1].astype(f) * f(1.0 / 255.0)
+    v = hsv[..., 2].astype(f) * f(1.0 / 255.0)
+    h = np.fmod(h, f(6.0)).astype(f)
+    sec = np.floor(h).astype(np.int32)
+    fr = (h - sec.astype(f)).astype(f)
+    bad = (sec < 0) | (sec >= 6)
+    sec = np.where(bad, 0, sec)
+    fr = np.where(bad, f(0), fr).astype(f)
+    one = f(1.0)
+    tab = np.stack([
+        v,
+        (v * (one - s)).astype(f),
+        (v * (one - (s * fr).astype(f))).astype(f),
+        (v * (one - (s * (one - fr)).astype(f))).astype(f),
+    ], axis=-1)
+    idx = _SECTOR[sec]  # (...,3)
+    out = np.take_along_axis(tab, idx, axis=-1)
+    grey = (hsv[..., 1] == 0)
+    out = np.where(grey[..., None], v[..., None], out)
+    return (out * f(255.0)).astype(f)
+
+
+def hsv2bgr(hsv, rounding="trunc"):
+    """cv2.cvtColor(hsv, COLOR_HSV2BGR) for uint8; ``rounding`` is 'trunc'
+    (whole images) or 'rint' (single pixels)."""
+    x = hsv2bgr_f32(hsv)
+    if rounding == "trunc":
+        return np.clip(x, 0, 255).astype(np.uint8)
+    return np.clip(np.rint(x), 0, 255).astype(np.uint8)
+
+
+def in_range(img, lo, hi):
+    """cv2.inRange: 255 where lo<=img<=hi on every channel (inclusive)."""
+    img = np.asarray(img).astype(np.int32)
+    lo = np.asarray(lo).astype(np.int32)
+    hi = np.asarray(hi).astype(np.int32)
+    ok = np.all((img >= lo) & (img <= hi), axis=-1)
+    return (ok * 255).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# resize
+# --------------------------------------------------------------------------
+
+_COEF_BITS = 11
+_COEF_SCALE = 1 << _COEF_BITS
+
+
+def _linear_axis(dst, src, horizontal):
+    """index / weight tables of cv2's fixed-point bilinear resize for one axis.
+    Horizontal: fraction reset at both borders.  Vertical: index clamp only."""
+    inv_scale = float(dst) / float(src)
+    scale = 1.0 / inv_scale
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    i0 = np.floor(f).astype(np.int32)
+    fr = (f - i0.astype(np.float32)).astype(np.float32)
+    if horizontal:
+        lo = i0 < 0
+        i0 = np.where(lo, 0, i0)
+        fr = np.where(lo, np.float32(0), fr)
+        hi = i0 >= src - 1
+        i0 = np.where(hi, src - 1, i0)
+        fr = np.where(hi, np.float32(0), fr).astype(np.float32)
+        i1 = np.minimum(i0 + 1, src - 1)
+    else:
+        i1 = np.clip(i0 + 1, 0, src - 1)
+        i0 = np.clip(i0, 0, src - 1)
+    w0 = np.rint((np.float32(1.0) - fr).astype(np.float32) * np.float32(_COEF_SCALE)).astype(np.int32)
+    w1 = np.rint(fr * np.float32(_COEF_SCALE)).astype(np.int32)
+    return i0, i1, w0, w1
+
+
+def resize_linear(src, dw, dh):
+    """cv2.resize(src, (dw, dh)) with the default INTER_LINEAR on uint8.
+    Exact 2x down-scaling in both axes silently becomes INTER_AREA (rounded
+    2x2 mean)."""
+    src = np.asarray(src)
+    sh, sw = src.shape[:2]
+    if dw == sw and dh == sh:
+        return src.copy()
+    if sw == 2 * dw and sh == 2 * dh:
+        s = src.astype(np.int32)
+        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2
+        return out.astype(np.uint8)
+    x0, x1, a0, a1 = _linear_axis(dw, sw, True)
+    y0, y1, b0, b1 = _linear_axis(dh, sh, False)
+    s = src.astype(np.int32)
+    if s.ndim == 3:
+        a0 = a0[None, :, None]
+        a1 = a1[None, :, None]
+        b0 = b0[:, None, None]
+        b1 = b1[:, None, None]
+    else:
+        a0 = a0[None, :]
+        a1 = a1[None, :]
+        b0 = b0[:, None]
+        b1 = b1[:, None]
+    rows = s[:, x0] * a0 + s[:, x1] * a1  # (sh, dw[, c]) scaled by 2048
+    r0 = rows[y0]
+    r1 = rows[y1]
+    out = (((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def resize_nearest(src, dw, dh):
+    """cv2.resize(src, (dw, dh), interpolation=INTER_NEAREST)."""
+    src = np.asarray(src)
+    sh, sw = src.shape[:2]
+    ifx = 1.0 / (float(dw) / float(sw))
+    ify = 1.0 / (float(dh) / float(sh))
+    xs = np.minimum(np.floor(np.arange(dw) * ifx).astype(np.int64), sw - 1)
+    ys = np.minimum(np.floor(np.arange(dh) * ify).astype(np.int64), sh - 1)
+    return src[ys][:, xs].copy()
+
+
+# --------------------------------------------------------------------------
+# morphology
+# --------------------------------------------------------------------------
+
+
+def ellipse_se(k):
+    """cv2.getStructuringElement(MORPH_ELLIPSE, (k, k)) as a 0/1 array; the
+    anchor is (k//2, k//2).  k=3 is the 5-tap cross."""
+    r = k // 2
+    c = k // 2
+    inv_r2 = 1.0 / (float(r) * r) if r else 0.0
+    se = np.zeros((k, k), np.uint8)
+    for i in range(k):
+        dy = i - r
+        if abs(dy) <= r:
+            dx = int(np.rint(c * np.sqrt((r * r - dy * dy) * inv_r2)))
+            j1 = max(c - dx, 0)
+            j2 = min(c + dx + 1, k)
+            se[i, j1:j2] = 1
+    return se
+
+
+def se_offsets(k):
+    se = ellipse_se(k)
+    a = k // 2
+    return [(i - a, j - a) for i in range(k) for j in range(k) if se[i, j]]
+
+
+def _morph_once(img, offs, dilate):
+    h, w = img.shape
+    pad = max(max(abs(dy), abs(dx)) for dy, dx in offs)
+    fill = 0 if dilate else 255
+    p = np.full((h + 2 * pad, w + 2 * pad), fill, np.uint8)
+    p[pad:pad + h, pad:pad + w] = img
+    out = None
+    for dy, dx in offs:
+        v = p[pad + dy:pad + dy + h, pad + dx:pad + dx + w]
+        if out is None:
+            out = v.copy()
+        elif dilate:
+            np.maximum(out, v, out=out)
+        else:
+            np.minimum(out, v, out=out)
+    return out
+
+
+def morph(img, k, iters, dilate):
+    """cv2.dilate / cv2.erode(img, ellipse_se(k), iterations=iters) on a
+    single-channel uint8 image (taps outside the image are ignored)."""
+    img = np.ascontiguousarray(img)
+    offs = se_offsets(k)
+    for _ in range(iters):
+        img = _morph_once(img, offs, dilate)
+    return img
+
+
+def dilate(img, k, iters):
+    if img.ndim == 3:
+        return np.stack([morph(img[..., c], k, iters, True) for c in range(img.shape[2])], -1)
+    return morph(img, k, iters, True)
+
+
+def erode(img, k, iters):
+    if img.ndim == 3:
+        return np.stack([morph(img[..., c], k, iters, False) for c in range(img.shape[2])], -1)
+    return morph(img, k, iters, False)

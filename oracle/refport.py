@@ -1,0 +1,398 @@
+"""Restatement of the reference's hot-path functions on top of ``cvmodel``.
+
+TEST INFRASTRUCTURE (see ``oracle/__init__.py``).  Every function cites the
+reference lines it follows (paths relative to the reference root).  Arrays are
+numpy uint8, HWC, BGR, masks HW -- the reference's conventions.  Nothing here
+mutates its arguments.
+"""
+import numpy as np
+
+from . import cvmodel as cvm
+
+# --------------------------------------------------------------------------
+# size math / morphology wrappers
+# --------------------------------------------------------------------------
+
+
+def get_target_size(h, w, target_long_side, division=1):
+    """unscreen/utils/imgprocess.py:164-192."""
+    if h > w:
+        th = target_long_side
+        tw = int(float(target_long_side) * w / h)
+        if tw % division != 0:
+            tw = (tw // division + 1) * division
+    else:
+        tw = target_long_side
+        th = int(float(target_long_side) * h / w)
+        if th % division != 0:
+            th = (th // division + 1) * division
+    return th, tw
+
+
+def adaptive_resize(img, img_target):
+    """unscreen/utils/imgprocess.py:33-37."""
+    return cvm.resize_linear(img, img_target.shape[1], img_target.shape[0])
+
+
+def dilate_mask(mask, kernelsize=5, iters=10):
+    """unscreen/utils/maskprocess.py:7-19."""
+    return cvm.dilate(mask, kernelsize, iters)
+
+
+def erode_mask(mask, kernelsize=5, iters=10):
+    """unscreen/utils/maskprocess.py:22-34."""
+    return cvm.erode(mask, kernelsize, iters)
+
+
+def exist_foreground(mask, fg_exist_thr):
+    """unscreen/utils/maskprocess.py:56-60 (strict '>')."""
+    h, w = mask.shape
+    return bool(int((mask >= 128).sum()) > fg_exist_thr * h * w)
+
+
+def get_outer_boundary(mask, kernelsize=7, iters=10):
+    """unscreen/utils/maskprocess.py:63-74: uint8 subtraction wraps, the clip
+    is a no-op."""
+    d = dilate_mask(mask, kernelsize, iters)
+    return (d - mask).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# is_pixel_inrange
+# --------------------------------------------------------------------------
+
+
+def is_pixel_inrange(img, bgimg, winsize=(20, 20, 120), long_side_input=-1):
+    """unscreen/utils/fgfuncs.py:9-65.  ``bgimg`` is (h,w,3) or (3,)."""
+    assert bgimg.ndim == 3 or bgimg.ndim == 1
+    h, w = img.shape[:2]
+    if long_side_input > 0:
+        ih, iw = get_target_size(h, w, long_side_input)
+        img = cvm.resize_linear(img, iw, ih)
+        if bgimg.ndim == 3:
+            bgimg = cvm.resize_linear(bgimg, iw, ih)
+    hsv = cvm.bgr2hsv(img).astype(np.int32)
+    half = np.array(winsize, dtype=np.int32) // 2
+    if bgimg.ndim == 3:
+        bg = cvm.bgr2hsv(bgimg).astype(np.int32)
+    else:
+        bg = cvm.bgr2hsv(bgimg[None, None, :])[0, 0].astype(np.int32)
+    lo = np.clip(bg - half, 10, 255)
+    hi = np.clip(bg + half, 10, 255)
+    mask = np.all((hsv >= lo) & (hsv <= hi), axis=-1)
+    if long_side_input > 0:
+        # fgfuncs.py:51,63: INTER_NEAREST lands in the dst slot => bilinear
+        m8 = mask.astype(np.uint8) * (1 if bgimg.ndim == 3 else 255)
+        mask = cvm.resize_linear(m8, w, h) > 0
+    return mask
+
+
+# --------------------------------------------------------------------------
+# colour filtering
+# --------------------------------------------------------------------------
+
+POW_EXP = np.float64(np.float32(1 / 3.))  # torch casts the python double to f32
+
+
+def gmm_lut(means, covariances, weights):
+    """256-entry float32 table of ColorFilteringAgent.get_prob_by_gmm
+    (unscreen/colorfiltering/agent.py:201-230) evaluated on samples 0..255.
+    Uses the same torch CPU ops in the same order as the reference, so the
+    table is bitwise what the reference computes per pixel."""
+    import torch
+    means = np.asarray(means, dtype=np.float64).reshape(-1)
+    stds = np.sqrt(np.asarray(covariances, dtype=np.float64).reshape(-1))
+    weights = np.asarray(weights, dtype=np.float64).reshape(-1)
+    samples = np.arange(256, dtype=np.float64).reshape(1, -1)
+    samples_t = torch.from_numpy(samples).float()
+    means_t = torch.from_numpy(means[..., np.newaxis]).float()
+    stds_t = torch.from_numpy(stds[..., np.newaxis]).float()
+    weights_t = torch.from_numpy(weights).float().unsqueeze(dim=0)
+    x = (samples_t - means_t) / stds_t
+    y = 1. / (stds_t * np.sqrt(2 * np.pi)) * torch.exp(-1. / 2 * torch.pow(x, 2))
+    prob = torch.mm(weights_t, y).squeeze()
+    return prob.numpy().astype(np.float32).reshape(256)
+
+
+def gmm_luts_from_models(gmms):
+    """three sklearn GaussianMixture (spherical) -> (3,256) float32."""
+    return np.stack([gmm_lut(g.means_.squeeze(), g.covariances_.squeeze(), g.weights_.squeeze())
+                     for g in gmms])
+
+
+def pow_third(x):
+    """torch.pow(x_f32, 1/3.) model: the exponent is the *float32* nearest to
+    1/3 (0.3333333432674408); evaluated in float64 and rounded once to
+    float32.  torch's SLEEF powf is a 1-ULP routine, so 1.8 % of values differ
+    from this by one ULP on this container's AVX-512 build -- irreproducible
+    across CPUs, and invisible after the uint8 cast except within ~1e-5 of an
+    integer boundary."""
+    x = np.asarray(x, dtype=np.float32).astype(np.float64)
+    with np.errstate(all="ignore"):
+        return np.power(x, POW_EXP).astype(np.float32)
+
+
+def alpha_from_luts(img_hsv, lut_bg, lut_fg):
+    """ColorFilteringAgent.get_alpha_by_gmm, unscreen/colorfiltering/agent.py:
+    232-257, with the per-channel mixtures folded into tables."""
+    f = np.float32
+    h = img_hsv[..., 0]
+    s = img_hsv[..., 1]
+    v = img_hsv[..., 2]
+    bg = ((f(1.0) * lut_bg[0][h]).astype(f) * lut_bg[1][s]).astype(f) * lut_bg[2][v]
+    fg = ((f(1.0) * lut_fg[0][h]).astype(f) * lut_fg[1][s]).astype(f) * lut_fg[2][v]
+    bg = pow_third(bg.astype(f))
+    fg = pow_third(fg.astype(f))
+    den = ((bg + fg).astype(f) + f(1e-6)).astype(f)
+    prob = (fg / den).astype(f)
+    return np.clip((prob * f(255)).astype(f), 0, 255).astype(np.uint8)
+
+
+def cf_postprocess(alpha, mask, thr_ratio=0.8):
+    """ColorFilteringAgent.postprocess, unscreen/colorfiltering/agent.py:
+    259-283.  Empty consistent area => NaN threshold => nothing zeroed."""
+    alpha = alpha.copy()
+    sel = (alpha > 128) & (mask > 0)
+    n = int(sel.sum())
+    if n > 0:
+        thr = alpha[sel].astype(np.float64).mean() * thr_ratio
+        alpha[alpha < thr] = 0
+    alpha = erode_mask(dilate_mask(alpha, 3, 2), 3, 2)
+    alpha = dilate_mask(erode_mask(alpha, 3, 2), 3, 2)
+    return alpha
+
+
+def get_color_prior(img_hsv, mask, winsize, max_num_samples=10000):
+    """ColorFilteringAgent.get_color_prior, agent.py:113-146.  Returns
+    (mask_by_prior, peak)."""
+    samples = img_hsv[:, :, 0][mask]
+    if len(samples) > max_num_samples:
+        samples = samples[::len(samples) // max_num_samples]
+    hist = np.bincount(samples.astype(np.int64), minlength=256)[:256]
+    peak = int(np.argmax(hist))
+    hch = img_hsv[:, :, 0].astype(np.int64)
+    return (hch > peak - winsize // 2) & (hch < peak + winsize // 2), peak
+
+
+def strided_samples(channel, mask, max_num_samples=10000):
+    """the ordered, strided sample gather of agent.py:163-167 / 190-194."""
+    s = channel[mask].astype(np.float64)
+    if len(s) > max_num_samples:
+        s = s[::len(s) // max_num_samples]
+    return s
+
+
+def bg_color_hsv(bg_means0):
+    """agent.py:345-351: int(mean(component-0 mean)) per channel."""
+    return np.array([int(np.mean(m)) for m in bg_means0], dtype=np.uint8)
+
+
+def cf_forward_predict(img, mask, lut_bg, lut_fg, bg_hsv, input_long_side=960,
+                       fg_ncomp=(10, 10, 10), bg_ncomp=(3, 5, 5)):
+    """ColorFilteringAgent.forward(img, mask, iters=0), agent.py:285-354, with
+    the fitted mixtures supplied as tables + the component-0 mean colour."""
+    if int((mask > 128).sum()) < max(fg_ncomp) * 5:
+        return mask, img, 1.0
+    if int((mask < 128).sum()) < max(bg_ncomp) * 5:
+        return mask, np.zeros_like(img), 1.0
+    hsv = cvm.bgr2hsv(img)
+    oh, ow = hsv.shape[:2]
+    th, tw = get_target_size(oh, ow, input_long_side)
+    hsv_lo = cvm.resize_linear(hsv, tw, th)
+    mask_lo = cvm.resize_linear(mask, tw, th)
+    alpha = alpha_from_luts(hsv_lo, lut_bg, lut_fg)
+    alpha = cf_postprocess(alpha, mask_lo)
+    alpha = cvm.resize_linear(alpha, ow, oh)
+    bg_img = cvm.hsv2bgr(np.broadcast_to(np.asarray(bg_hsv, np.uint8), (oh, ow, 3)))
+    return alpha, bg_img, None
+
+
+# --------------------------------------------------------------------------
+# trimap
+# --------------------------------------------------------------------------
+
+
+def generate_trimap(mask, input_long_side=960, kernelsize=3, iters=5):
+    """TrimapAgent.generate_trimap, unscreen/trimap/agent.py:35-61.  The
+    up-scale at :59 is bilinear (INTER_NEAREST is passed in the dst slot)."""
+    oh, ow = mask.shape
+    ih, iw = get_target_size(oh, ow, input_long_side)
+    m = cvm.resize_nearest(mask, iw, ih)
+    tri = np.full((ih, iw), 128, np.uint8)
+    dil = dilate_mask(m, kernelsize, iters)
+    ero = erode_mask(m, kernelsize, iters)
+    tri[ero > 127] = 255
+    tri[dil < 128] = 0
+    tri = cvm.resize_linear(tri, ow, oh)
+    tri[(tri > 0) & (tri < 255)] = 128
+    return tri
+
+
+def generate_trimap_withbg(mask, img, bgimg, input_long_side=960, kernelsize=3, iters=5,
+                           color_winsize=(10, 100, 180)):
+    """TrimapAgent.generate_trimap_withbg, unscreen/trimap/agent.py:63-101."""
+    npos = int((mask > 0).sum())
+    if npos == 0:
+        return mask
+    bgmask = is_pixel_inrange(img, bgimg, color_winsize)
+    fuzzy = (mask > 0) & bgmask
+    if float(fuzzy.sum()) / npos > 0.1:
+        return generate_trimap(mask, input_long_side, kernelsize, iters)
+    ens = mask.copy()
+    ens[fuzzy] = 0
+    tri = generate_trimap(ens, input_long_side, kernelsize, iters)
+    tri[fuzzy] = 128
+    return tri
+
+
+# --------------------------------------------------------------------------
+# compositing family
+# --------------------------------------------------------------------------
+
+
+def fg_hsv_stage(img, alpha, bg):
+    """the exactly reproducible part of get_fg (fgfuncs.py:100-108): float32
+    HSV arithmetic, clamp, truncate -- before the +-1 HSV2BGR."""
+    f = np.float32
+    ih = cvm.bgr2hsv(img).astype(f)
+    bh = cvm.bgr2hsv(bg).astype(f)
+    a = (alpha.astype(f) / f(255.))[..., None]
+    t = ((f(1) - a).astype(f) * bh).astype(f)
+    fg = np.clip((ih - t).astype(f), 0, 255)
+    return fg.astype(np.uint8)
+
+
+def get_fg(img, alpha, bg):
+    """unscreen/utils/fgfuncs.py:84-110."""
+    return cvm.hsv2bgr(fg_hsv_stage(img, alpha, bg))
+
+
+def bg_hsv_stage(alpha, bg):
+    f = np.float32
+    bh = cvm.bgr2hsv(bg).astype(f)
+    a = (alpha.astype(f) / f(255.))[..., None]
+    out = np.clip(((f(1) - a).astype(f) * bh).astype(f), 0, 255)
+    return out.astype(np.uint8)
+
+
+def get_bg(alpha, bg):
+    """unscreen/utils/fgfuncs.py:113-137."""
+    return cvm.hsv2bgr(bg_hsv_stage(alpha, bg))
+
+
+def get_fg_naive(img, alpha):
+    """unscreen/utils/fgfuncs.py:68-81 (float64)."""
+    a = alpha.astype(np.float64) / 255.
+    return (img.astype(np.float64) * a[..., None]).astype(np.uint8)
+
+
+def fuse_fgbg(fg, bg, mask):
+    """unscreen/utils/visualize.py:7-24 (float64)."""
+    a = mask.astype(np.float64)[..., None] / 255
+    return (a * fg.astype(np.float64) + (1 - a) * bg.astype(np.float64)).astype(np.uint8)
+
+
+def composite_fgbg(fg, alpha, bg, extend=False):
+    """unscreen/utils/fgfuncs.py:172-214."""
+    fg_h, fg_w = fg.shape[:2]
+    bg_h, bg_w = bg.shape[:2]
+    if float(fg_h) / fg_w > float(bg_h) / bg_w:
+        nh = fg_h
+        nw = int(float(bg_w) * nh / bg_h)
+    else:
+        nw = fg_w
+        nh = int(float(bg_h) * nw / bg_w)
+    bg = cvm.resize_linear(bg, nw, nh)
+    left = max(nw // 2 - fg_w // 2, 0)
+    top = max(nh // 2 - fg_h // 2, 0)
+    a = alpha.astype(np.float64) / 255.
+    a[a > 0.9] = 1
+    roi = bg[top:top + fg_h, left:left + fg_w].astype(np.float64)
+    comp = (fg.astype(np.float64) + roi * (1 - a[..., None])).clip(0, 255).astype(np.uint8)
+    if extend:
+        out = bg.copy()
+        out[top:top + fg_h, left:left + fg_w] = comp
+        return out
+    return comp
+
+
+def replace_blend(fg, mask3, bg):
+    """tools/replace/replace.py:74-76 (float64; mask has the image's shape, or
+    HW for the single-channel variant of BASELINE config 4)."""
+    m = mask3.astype(np.float64) / 255
+    if m.ndim == 2:
+        m = m[..., None]
+    res = fg.astype(np.float64) * m + bg.astype(np.float64) * (1 - m)
+    return res.astype(np.uint8)
+
+
+def patch_bg(bgimg, frame, alpha, mode):
+    """tools/unscreen/green.py:125 (mode 'lt128') and bg.py:99 /
+    bg_offline.py:171 (mode 'eq0'): predicated copy frame -> bgimg."""
+    out = bgimg.copy()
+    sel = (alpha < 128) if mode == "lt128" else (alpha == 0)
+    out[sel] = frame[sel]
+    return out
+
+
+def fuse_bg(bgimg, bg_always, beta):
+    """tools/unscreen/bg_offline.py:150-151: float32 array math with python
+    float scalars (scalars round to float32)."""
+    f = np.float32
+    return ((bgimg.astype(f) * f(beta)).astype(f) + (f(1 - beta) * bg_always.astype(f)).astype(f)).astype(np.uint8)
+
+
+def bgdiff_gate(frame, bgimg, mask, thr=25):
+    """tools/unscreen/bg.py:85-92 == bg_offline.py:154-160: absdiff ->
+    BGR2GRAY -> '>thr -> 255' (values <=thr are kept) -> dilate(4,2) ->
+    mask * (g // 255)."""
+    raw = np.abs(frame.astype(np.int32) - bgimg.astype(np.int32)).astype(np.uint8)
+    g = cvm.bgr2gray(raw)
+    g = g.copy()
+    g[g > thr] = 255
+    g = dilate_mask(g, 4, 2)
+    return (mask * (g // 255)).astype(np.uint8)
+
+
+def binarise_dilate(alpha):
+    """tools/unscreen/bg.py:74-77."""
+    a = np.where(alpha > 128, 255, 0).astype(np.uint8)
+    return dilate_mask(a, 3, 2)
+
+
+# --------------------------------------------------------------------------
+# temporal reducers
+# --------------------------------------------------------------------------
+
+
+def masked_temporal_mean(frames, masks, ksize=3, iters=2, min_count=10):
+    """tools/unscreen/bg_offline.py:106-125 (dead code in the reference; the
+    only temporal background estimator it contains).  ``masks`` is [N,H,W]
+    (single channel; the reference's 3-identical-channel JPEG masks give the
+    same result per channel).  Returns (bg_always HxWx3 u8, mask_always HxW u8).
+    The TELEA inpaint at :127-129 is out of scope."""
+    n, h, w, _ = frames.shape
+    acc = np.zeros((h, w, 3), np.int64)
+    cnt = np.zeros((h, w), np.int64)
+    for i in range(n):
+        m = dilate_mask(masks[i], ksize, iters)
+        keep = (1 - (m // 255).astype(np.int64))
+        acc += frames[i].astype(np.int64) * keep[..., None]
+        cnt += (m < 250)
+    mask_always = ((cnt <= min_count) * 255).astype(np.uint8)
+    den = np.maximum(cnt, 1).astype(np.float64)
+    bg = np.clip(acc.astype(np.float64) / den[..., None], 0, 255).astype(np.uint8)
+    bg[mask_always == 255] = 0
+    return bg, mask_always
+
+
+def temporal_median(frames):
+    """NEW SPECIFICATION (the reference has no
+    median): np.median(stack, 0).astype(np.uint8); for even N this equals
+    (sorted[N/2-1] + sorted[N/2]) >> 1."""
+    n = frames.shape[0]
+    k = (n - 1) // 2
+    part = np.partition(frames, (k, n // 2), axis=0)
+    lo = part[k].astype(np.uint16)
+    hi = part[n // 2].astype(np.uint16)
+    return ((lo + hi) >> 1).astype(np.uint8)
