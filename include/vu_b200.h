@@ -1,0 +1,176 @@
+/*
+ * vu_b200.h -- C ABI of the B200-native video_unscreen hot path.
+ *
+ * The reference (AnyiRao/video_unscreen) has no FFI: its boundary for this
+ * path is Python-import level.  Every entry point below
+ * names the reference function or inline lines it replaces; the Python package
+ * `video_unscreen_b200.unscreen` binds them with ctypes and mirrors the
+ * reference's signatures (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - every image pointer is a DEVICE pointer to dense, C-contiguous uint8:
+ *     frames [n][h][w][3] in BGR order, masks [n][h][w]; no pitches.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *     Calls only enqueue work; nothing here synchronises or allocates.
+ *   - workspaces are caller-provided; sizes come from the *_workspace_bytes
+ *     twins.  Workspace pointers must be 256-byte aligned.
+ *   - return value: VU_OK (0) or a negative vu_status.  No exceptions, no
+ *     CPU fallback: if the device code cannot run, the call fails.
+ */
+#ifndef VU_B200_H
+#define VU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VU_ABI_VERSION 1
+
+typedef void* vu_stream_t;
+
+enum vu_status {
+  VU_OK = 0,
+  VU_ERR_INVALID_ARG = -1,
+  VU_ERR_UNSUPPORTED = -2,
+  VU_ERR_WORKSPACE = -3,
+  VU_ERR_CUDA = -4
+};
+
+enum vu_morph_op { VU_DILATE = 0, VU_ERODE = 1 };
+enum vu_cmp_op { VU_CMP_GE = 0, VU_CMP_GT = 1, VU_CMP_LT = 2, VU_CMP_EQ = 3, VU_CMP_NE = 4 };
+enum vu_patch_mode { VU_PATCH_NONE = 0, VU_PATCH_ALPHA_LT128 = 1, VU_PATCH_ALPHA_EQ0 = 2 };
+enum vu_blend_mode {
+  VU_BLEND_NAIVE = 0,     /* u8(f64(img) * a)                        fgfuncs.py:68-81   */
+  VU_BLEND_FUSE = 1,      /* u8(a*fg + (1-a)*bg)                     visualize.py:7-24  */
+  VU_BLEND_COMPOSITE = 2, /* a[a>0.9]=1; u8(clip(fg + bg*(1-a)))     fgfuncs.py:201-207 */
+  VU_BLEND_REPLACE = 3    /* u8(fg*m + bg*(1-m)), m = mask/255       replace.py:74-76   */
+};
+
+int vu_abi_version(void);
+const char* vu_status_string(int status);
+/* text of the last CUDA error seen by this library on the calling thread */
+const char* vu_last_cuda_error(void);
+
+/* ---- colour ------------------------------------------------------------ */
+/* cv2.cvtColor(BGR2HSV) uint8, H in [0,179]; colorfiltering/agent.py:310,
+ * fgfuncs.py:36,39,100,101,129 */
+int vu_bgr2hsv_u8(const uint8_t* bgr, uint8_t* hsv, int64_t npix, vu_stream_t stream);
+/* cv2.cvtColor(HSV2BGR) uint8 (whole-image = truncating variant);
+ * colorfiltering/agent.py:352, fgfuncs.py:109,136 */
+int vu_hsv2bgr_u8(const uint8_t* hsv, uint8_t* bgr, int64_t npix, vu_stream_t stream);
+/* cv2.cvtColor(BGR2GRAY) uint8; bg.py:86, bg_offline.py:152,155 */
+int vu_bgr2gray_u8(const uint8_t* bgr, uint8_t* gray, int64_t npix, vu_stream_t stream);
+/* is_pixel_inrange, bg-colour variant (fgfuncs.py:53-64): out = 1 where
+ * lo[c] <= HSV(bgr)[c] <= hi[c] for all c, else 0.  lo/hi are HOST arrays. */
+int vu_inrange_color(const uint8_t* bgr, int64_t npix, const int32_t lo[3], const int32_t hi[3],
+                     uint8_t* mask01, vu_stream_t stream);
+/* is_pixel_inrange, bg-image variant (fgfuncs.py:37-52): per-pixel bounds
+ * clamp(HSV(bg) -/+ half, 10, 255).  The bg image repeats every bg_npix
+ * pixels (bg_npix == npix: one bg per frame; bg_npix == h*w: shared). */
+int vu_inrange_image(const uint8_t* bgr, const uint8_t* bgimg, int64_t npix, int64_t bg_npix,
+                     const int32_t half[3], uint8_t* mask01, vu_stream_t stream);
+
+/* ---- morphology: dilate_mask / erode_mask, maskprocess.py:7-34 ---------- */
+/* grey-scale max/min under cv2 MORPH_ELLIPSE(ksize,ksize), `iters` times,
+ * taps outside the image ignored.  ksize 3 runs as ONE pass with the L1
+ * diamond of radius `iters`; other sizes ping-pong through `workspace`. */
+size_t vu_morph_workspace_bytes(int n, int h, int w, int ksize, int iters);
+int vu_morph_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int ksize, int iters, int op,
+                void* workspace, size_t workspace_bytes, vu_stream_t stream);
+
+/* ---- resize: cv2.resize uint8 ------------------------------------------ */
+/* default INTER_LINEAR (exact 2x down-scale == rounded 2x2 mean);
+ * colorfiltering/agent.py:315-316,342, trimap/agent.py:59 (the "nearest"
+ * call that is really bilinear), imgprocess.py:36 */
+int vu_resize_linear_u8(const uint8_t* src, int n, int sh, int sw, int channels, uint8_t* dst, int dh, int dw,
+                        vu_stream_t stream);
+/* INTER_NEAREST; trimap/agent.py:52 */
+int vu_resize_nearest_u8(const uint8_t* src, int n, int sh, int sw, int channels, uint8_t* dst, int dh, int dw,
+                         vu_stream_t stream);
+
+/* ---- reductions -------------------------------------------------------- */
+/* counts[i] = #{ src[i][j] <op> thr }; exist_foreground (maskprocess.py:56-60),
+ * the early-outs of colorfiltering/agent.py:303-307 and trimap/agent.py:88 */
+int vu_count_cmp_u8(const uint8_t* src, int n, int64_t per_item, int op, int thr, uint64_t* counts,
+                    vu_stream_t stream);
+/* counts[i][0] = #{a>0 && b>0}, counts[i][1] = #{a>0}; the fuzzy-area ratio
+ * of trimap/agent.py:91-94 */
+int vu_count_and_u8(const uint8_t* a, const uint8_t* b, int n, int64_t per_item, uint64_t* counts2,
+                    vu_stream_t stream);
+/* out = a where b == 0 else 0 (trimap/agent.py:97-98: mask[fuzzy] = 0) and
+ * out = 128 where b != 0 else a (:100: trimap[fuzzy] = 128) */
+int vu_mask_clear_where(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t count, vu_stream_t stream);
+int vu_mask_set128_where(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t count, vu_stream_t stream);
+
+/* out = 1 where a > 0 && b > 0 else 0 (the fuzzy area itself, :91) */
+int vu_mask_and01(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t count, vu_stream_t stream);
+/* generate_trimap, trimap/agent.py:54-58: out = 0 where dilated < 128, else
+ * 255 where eroded > 127, else 128 */
+int vu_trimap_classify(const uint8_t* dilated, const uint8_t* eroded, uint8_t* out, int64_t count,
+                       vu_stream_t stream);
+/* trimap/agent.py:60: values strictly between 0 and 255 become 128 */
+int vu_trimap_snap(const uint8_t* a, int64_t count, uint8_t* out, vu_stream_t stream);
+
+/* ---- colour filtering: ColorFilteringAgent, colorfiltering/agent.py ----- */
+/* get_alpha_by_gmm (:232-257) with the six 1-D mixtures folded into 256-entry
+ * float32 tables (luts = [bg H,S,V, fg H,S,V][256], DEVICE): per pixel
+ * bg = (lutH[h]*lutS[s])*lutV[v], same for fg, p = fg^(1/3f) / (bg^(1/3f) +
+ * fg^(1/3f) + 1e-6), alpha = u8(clip(p*255)). */
+int vu_cf_alpha_u8(const uint8_t* hsv, int64_t npix, const float* luts, uint8_t* alpha, vu_stream_t stream);
+/* the same function tabulated over every (h<180, s, v): lut3d[180][256][256] */
+int vu_cf_build_lut3d(const float* luts, uint8_t* lut3d, vu_stream_t stream);
+int vu_cf_alpha_lut3d_u8(const uint8_t* hsv, int64_t npix, const uint8_t* lut3d, uint8_t* alpha,
+                         vu_stream_t stream);
+/* postprocess (:259-283) step 1: per frame sum/count of alpha over
+ * (alpha>128 && mask>0) -> stats[i] = {sum, count}; step 2 zeroes alpha below
+ * 0.8 * sum/count (f64; count==0 leaves alpha untouched).  The d2,e2,e2,d2
+ * morphology that follows is four vu_morph_u8 calls. */
+int vu_cf_threshold_stats(const uint8_t* alpha, const uint8_t* mask, int n, int64_t per_item, uint64_t* stats2,
+                          vu_stream_t stream);
+int vu_cf_threshold_apply(const uint8_t* alpha, int n, int64_t per_item, const uint64_t* stats2, double thr_ratio,
+                          uint8_t* out, vu_stream_t stream);
+/* ---- compositing -------------------------------------------------------- */
+/* get_fg, fgfuncs.py:84-110, optionally fused with the predicated background
+ * patch of green.py:125 (ALPHA_LT128) or bg.py:99 / bg_offline.py:171
+ * (ALPHA_EQ0).  bg repeats every bg_npix pixels.  If bg_out != NULL the
+ * patched background is also written (green.py saves it). */
+int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8_t* bg, int64_t npix, int64_t bg_npix,
+              int patch_mode, uint8_t* fg_out, uint8_t* bg_out, vu_stream_t stream);
+/* get_bg, fgfuncs.py:113-137 */
+int vu_get_bg(const uint8_t* alpha, const uint8_t* bg, int64_t npix, uint8_t* out, vu_stream_t stream);
+/* float64 blends (see vu_blend_mode).  alpha_channels is 1 (HW mask) or 3
+ * (HWC mask, replace.py).  bg repeats every bg_npix pixels; may be NULL for
+ * VU_BLEND_NAIVE. */
+int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int alpha_channels, const uint8_t* bg,
+             int64_t npix, int64_t bg_npix, uint8_t* out, vu_stream_t stream);
+/* bg_offline.py:150-151: u8(f32(bg)*beta + (1-beta)*f32(bg_always)) */
+int vu_fuse_bg(const uint8_t* bg, const uint8_t* bg_always, int64_t npix, int64_t always_npix, float beta,
+               float one_minus_beta, uint8_t* out, vu_stream_t stream);
+/* bg.py:85-88 == bg_offline.py:154-157: g = BGR2GRAY(|frame-bg|); g[g>thr]=255 */
+int vu_bgdiff_gray(const uint8_t* frame, const uint8_t* bg, int64_t npix, int64_t bg_npix, int thr, uint8_t* gray,
+                   vu_stream_t stream);
+/* bg.py:92 == bg_offline.py:160: out = mask * (g // 255) (uint8 wrap-free) */
+int vu_gate(const uint8_t* mask, const uint8_t* g, int64_t count, uint8_t* out, vu_stream_t stream);
+/* bg.py:74-76: >128 -> 255 else 0 */
+int vu_binarise(const uint8_t* alpha, int64_t count, int thr, uint8_t* out, vu_stream_t stream);
+/* get_outer_boundary tail, maskprocess.py:73: out = a - b (uint8 wrap) */
+int vu_sub_wrap_u8(const uint8_t* a, const uint8_t* b, int64_t count, uint8_t* out, vu_stream_t stream);
+
+/* ---- temporal background ------------------------------------------------ */
+/* exact per-element median over n frames of m bytes each (NEW SPEC, SURVEY.md
+ * section 8 a23; oracle np.median(stack,0).astype(u8)): even n ->
+ * (sorted[n/2-1] + sorted[n/2]) >> 1.  1 <= n <= 65535. */
+int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream);
+/* masked temporal mean, bg_offline.py:106-125.  masks are the ALREADY DILATED
+ * single-channel masks [n][h*w] (dilate_mask(mask,3,2) is a vu_morph_u8 call).
+ * bg_out[h*w*3], mask_always_out[h*w] (255 where count <= min_count). */
+int vu_masked_temporal_mean(const uint8_t* frames, const uint8_t* masks, int n, int64_t npix, int min_count,
+                            uint8_t* bg_out, uint8_t* mask_always_out, vu_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VU_B200_H */

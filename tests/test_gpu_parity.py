@@ -1,0 +1,291 @@
+"""Parity of the CUDA path (through the C ABI, via the reference-shaped Python
+layer) against the CPU oracle and the committed golden vectors produced by the
+unmodified reference.  Bit-exact for masks / trimaps / alpha / backgrounds;
+<= 1 LSB for anything that ends in cv2's HSV2BGR (tolerance: 1)."""
+import numpy as np
+import pytest
+
+from conftest import maxdiff
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import cvmodel as M  # noqa: E402
+from oracle import refport as R  # noqa: E402
+
+BGCOL = np.array([60, 200, 40], np.uint8)
+HSV2BGR_TOL = 1  # uint8 LSB
+
+
+@pytest.fixture(scope="module")
+def vu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import video_unscreen_b200.unscreen.utils as U
+    from video_unscreen_b200 import ops
+    from video_unscreen_b200.unscreen.colorfiltering import ColorFilteringAgent
+    from video_unscreen_b200.unscreen.trimap import TrimapAgent
+
+    class NS:
+        pass
+    ns = NS()
+    ns.U, ns.ops, ns.CF, ns.TA = U, ops, ColorFilteringAgent, TrimapAgent
+    return ns
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.cpu().numpy()
+
+
+# ---- primitives ------------------------------------------------------------
+
+def test_bgr2hsv_gray_exhaustive(vu):
+    a = np.arange(1 << 24, dtype=np.uint32)
+    img = np.stack([a & 255, (a >> 8) & 255, (a >> 16) & 255], -1).astype(np.uint8).reshape(4096, 4096, 3)
+    assert np.array_equal(host(vu.ops.bgr2hsv(dev(img))), M.bgr2hsv(img))
+    assert np.array_equal(host(vu.ops.bgr2gray(dev(img))), M.bgr2gray(img))
+    hsv = img.copy()
+    hsv[..., 0] %= 180
+    assert np.array_equal(host(vu.ops.hsv2bgr(dev(hsv))), M.hsv2bgr(hsv))  # same truncating f32 formula
+
+
+def test_pixel_kernels_ragged_sizes(vu):
+    rng = np.random.default_rng(0)
+    for h, w in [(1, 1), (3, 5), (7, 9), (33, 47)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(host(vu.ops.bgr2hsv(dev(img))), M.bgr2hsv(img))
+        assert np.array_equal(host(vu.ops.bgr2gray(dev(img))), M.bgr2gray(img))
+        assert np.array_equal(host(vu.ops.inrange_color(dev(img), [10, 20, 30], [100, 200, 250])) * 255,
+                              M.in_range(M.bgr2hsv(img), [10, 20, 30], [100, 200, 250]))
+
+
+@pytest.mark.parametrize("k,n", [(3, 1), (3, 2), (3, 5), (4, 2), (5, 3), (7, 10), (5, 10)])
+def test_morphology(vu, k, n):
+    rng = np.random.default_rng(k * 31 + n)
+    for shape in [(97, 131), (2, 64, 200), (5, 3)]:
+        m = rng.integers(0, 256, shape, dtype=np.uint8)
+        for fn, ref in ((vu.ops.dilate, M.dilate), (vu.ops.erode, M.erode)):
+            got = host(fn(dev(m), k, n))
+            want = ref(m, k, n) if m.ndim == 2 else np.stack([ref(x, k, n) for x in m])
+            assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("sh,sw,dh,dw", [(270, 480, 135, 240), (360, 640, 90, 160), (135, 240, 270, 480), (90, 160, 360, 640),
+                                         (250, 333, 150, 200), (150, 200, 250, 333), (480, 270, 240, 135), (61, 47, 122, 94), (9, 7, 4, 3)])
+def test_resize(vu, sh, sw, dh, dw):
+    rng = np.random.default_rng(sh * 7 + dw)
+    img = rng.integers(0, 256, (2, sh, sw, 3), dtype=np.uint8)
+    msk = rng.integers(0, 256, (2, sh, sw), dtype=np.uint8)
+    assert np.array_equal(host(vu.ops.resize_linear_image(dev(img), dh, dw)), np.stack([M.resize_linear(x, dw, dh) for x in img]))
+    assert np.array_equal(host(vu.ops.resize_linear_mask(dev(msk), dh, dw)), np.stack([M.resize_linear(x, dw, dh) for x in msk]))
+    assert np.array_equal(host(vu.ops.resize_nearest_mask(dev(msk), dh, dw)), np.stack([M.resize_nearest(x, dw, dh) for x in msk]))
+    assert np.array_equal(host(vu.ops.resize_nearest_image(dev(img), dh, dw)), np.stack([M.resize_nearest(x, dw, dh) for x in img]))
+
+
+def test_golden_primitives(vu, golden):
+    p = golden("primitives")
+    m = p["mask"]
+    U = vu.U
+    for k, n in [(3, 2), (3, 5), (4, 2), (5, 3), (7, 10), (5, 10)]:
+        assert np.array_equal(U.dilate_mask(m, k, n), p[f"dilate_{k}_{n}"])
+        assert np.array_equal(U.erode_mask(m, k, n), p[f"erode_{k}_{n}"])
+    assert np.array_equal(U.get_outer_boundary(m), p["outer_boundary"])
+    assert [U.exist_foreground(m, t) for t in (0.001, 0.4, 0.5, 0.6)] == list(p["exist_fg"])
+    assert np.array_equal(U.is_pixel_inrange(p["img"], p["bgcolor"], (10, 100, 180)), p["inrange_color"])
+    assert np.array_equal(U.is_pixel_inrange(p["img"], np.array([5, 9, 250], np.uint8), (60, 255, 255)), p["inrange_color_wide"])
+    assert np.array_equal(U.is_pixel_inrange(p["img"], p["bgimg"], (20, 20, 120)), p["inrange_image"])
+    assert np.array_equal(U.is_pixel_inrange(p["img"], p["bgimg"], (10, 100, 180)), p["inrange_image2"])
+    for th, tw, h, w, L in p["target_sizes"]:
+        assert U.get_target_size(h, w, L) == (th, tw)
+    # 3-channel masks go through per-channel morphology like cv2
+    m3 = np.stack([m, m[::-1].copy(), m[:, ::-1].copy()], -1)
+    assert np.array_equal(U.dilate_mask(m3, 3, 2), M.dilate(m3, 3, 2))
+    # long_side_input > 0 variant against the oracle
+    assert np.array_equal(U.is_pixel_inrange(p["img"], p["bgcolor"], (60, 255, 255), 64), R.is_pixel_inrange(p["img"], p["bgcolor"], (60, 255, 255), 64))
+    assert np.array_equal(U.is_pixel_inrange(p["img"], p["bgimg"], (20, 20, 120), 64), R.is_pixel_inrange(p["img"], p["bgimg"], (20, 20, 120), 64))
+
+
+# ---- colour filtering ----------------------------------------------------------
+
+def load_agent(vu, c, tag):
+    from test_oracle_golden import cf_tables
+    lb, lf, bgh = cf_tables(c, tag)
+    ag = vu.CF(input_long_side=int(c[f"{tag}_L"]))
+    ag.set_tables(lb, lf, bgh)
+    return ag, lb, lf, bgh
+
+
+@pytest.mark.parametrize("tag", ["x2", "x4", "frac", "portrait"])
+def test_colorfilter_predict_golden(vu, golden, tag):
+    c = golden("colorfilter")
+    ag, lb, lf, bgh = load_agent(vu, c, tag)
+    a, bgimg, _ = ag.forward(c[f"{tag}_frame"], c[f"{tag}_seg"], 0)
+    assert np.array_equal(a, c[f"{tag}_alpha_pred"])            # bit-exact vs the reference
+    assert maxdiff(bgimg, c[f"{tag}_bgimg"]) <= HSV2BGR_TOL
+    a2, _, _ = ag.forward(c[f"{tag}_frame2"], c[f"{tag}_seg2"], 0)
+    assert np.array_equal(a2, c[f"{tag}_alpha_pred2"])
+    # pieces
+    fr, seg = c[f"{tag}_frame"], c[f"{tag}_seg"]
+    th, tw = R.get_target_size(*fr.shape[:2], int(c[f"{tag}_L"]))
+    hl = M.resize_linear(M.bgr2hsv(fr), tw, th)
+    raw, _ = ag.get_alpha_by_gmm(hl)
+    assert np.array_equal(raw, c[f"{tag}_alpha_raw"])
+    assert np.array_equal(ag.postprocess(raw, M.resize_linear(seg, tw, th)), c[f"{tag}_alpha_post"])
+    # the tabulated (h,s,v) -> alpha volume gives the same answer
+    lut3d = vu.ops.cf_build_lut3d(ag._luts_dev)
+    assert np.array_equal(host(vu.ops.cf_alpha_lut3d(dev(hl), lut3d)), c[f"{tag}_alpha_raw"])
+
+
+def test_colorfilter_tables_match_oracle(vu, golden):
+    from video_unscreen_b200.unscreen.colorfiltering.agent import gmm_table
+    c = golden("colorfilter")
+    for nm in ("bg", "fg"):
+        for i in range(3):
+            means, covs, w = c[f"x2_{nm}{i}_means"], c[f"x2_{nm}{i}_covs"], c[f"x2_{nm}{i}_weights"]
+            assert np.array_equal(gmm_table(means, np.sqrt(covs), w).numpy(), R.gmm_lut(means, covs, w))
+
+
+def test_colorfilter_fit_matches_reference_fit(vu, golden):
+    """iters=3 with the same numpy RNG seed reproduces the reference's fitted
+    run (the EM itself is scikit-learn on both sides)."""
+    c = golden("colorfilter")
+    ag = vu.CF(input_long_side=int(c["x2_L"]))
+    np.random.seed(0)
+    a, _, _ = ag.forward(c["x2_frame"], c["x2_seg"], 3)
+    assert np.array_equal(a, c["x2_alpha_fit"])
+    assert ag.is_trained()
+
+
+def test_colorfilter_early_outs(vu, golden):
+    c = golden("colorfilter")
+    fr = c["early_frame"]
+    z = np.zeros(fr.shape[:2], np.uint8)
+    ag = vu.CF(input_long_side=48)
+    a, b, conf = ag.forward(fr, z, 0)
+    assert np.array_equal(a, c["early_nofg_alpha"]) and np.array_equal(b, c["early_nofg_bg"]) and conf == 1.0
+    a, b, conf = ag.forward(fr, z + 255, 0)
+    assert np.array_equal(a, c["early_nobg_alpha"]) and np.array_equal(b, c["early_nobg_bg"]) and conf == 1.0
+
+
+# ---- trimap ------------------------------------------------------------------------
+
+@pytest.mark.parametrize("tag", ["x2", "x4", "frac", "portrait", "up"])
+def test_trimap_golden(vu, golden, tag):
+    t = golden("trimap")
+    ta = vu.TA(input_long_side=int(t[f"{tag}_L"]))
+    fr = t[f"{tag}_frame"]
+    assert np.array_equal(ta.forward(t[f"{tag}_mask"]), t[f"{tag}_plain"])
+    assert np.array_equal(ta.forward(t[f"{tag}_soft"]), t[f"{tag}_plain_soft"])
+    assert np.array_equal(ta.forward(t[f"{tag}_soft"], fr, BGCOL), t[f"{tag}_withcolor"])
+    assert np.array_equal(ta.forward(t[f"{tag}_soft"], fr, t[f"{tag}_bgimg"]), t[f"{tag}_withimage"])
+    assert np.array_equal(ta.forward(t[f"{tag}_leak"], fr, BGCOL), t[f"{tag}_leak_withcolor"])
+    assert np.array_equal(ta.forward(t[f"{tag}_ring"], fr, BGCOL), t[f"{tag}_ring_withcolor"])
+    assert np.array_equal(ta.forward(t[f"{tag}_ring"], fr, t[f"{tag}_bgimg"]), t[f"{tag}_ring_withimage"])
+
+
+def test_trimap_empty_and_device_tensors(vu, golden):
+    t = golden("trimap")
+    z = np.zeros((40, 64), np.uint8)
+    out = vu.TA(input_long_side=64).forward(z, np.zeros((40, 64, 3), np.uint8), np.array([1, 2, 3], np.uint8))
+    assert np.array_equal(out, t["empty_withcolor"])
+    ta = vu.TA(input_long_side=int(t["x2_L"]))
+    got = ta.forward(dev(t["x2_soft"]), dev(t["x2_frame"]), BGCOL)
+    assert got.is_cuda and np.array_equal(host(got), t["x2_withcolor"])
+
+
+# ---- compositing -------------------------------------------------------------------------
+
+def test_composite_golden(vu, golden):
+    k = golden("composite")
+    U = vu.U
+    fr, al, bg = k["frame"], k["alpha"], k["bg"]
+    assert maxdiff(U.get_fg(fr, al, bg), k["get_fg"]) <= HSV2BGR_TOL
+    assert maxdiff(U.get_bg(al, bg), k["get_bg"]) <= HSV2BGR_TOL
+    assert maxdiff(U.get_fg(fr, al, bg, patch="lt128"), k["green_patch_fg"]) <= HSV2BGR_TOL
+    assert maxdiff(U.get_fg(fr, al, bg, patch="eq0"), k["bg_patch_fg"]) <= HSV2BGR_TOL
+    # and exactly the oracle's truncating HSV2BGR
+    assert np.array_equal(U.get_fg(fr, al, bg), R.get_fg(fr, al, bg))
+    assert np.array_equal(U.get_bg(al, bg), R.get_bg(al, bg))
+    assert np.array_equal(U.get_fg_naive(fr, al), k["get_fg_naive"])
+    assert np.array_equal(U.fuse_fgbg(fr, bg, al), k["fuse_fgbg"])
+    assert np.array_equal(U.composite_fgbg(fr, al, k["newbg"]), k["composite"])
+    assert np.array_equal(U.composite_fgbg(fr, al, k["newbg"], True), k["composite_ext"])
+    assert np.array_equal(U.composite_fgbg(fr, al, k["tallbg"]), k["composite_tall"])
+    assert np.array_equal(U.replace_blend(fr, np.stack([al] * 3, -1), bg), k["replace"])
+    assert np.array_equal(U.replace_blend(fr, al, bg), k["replace"])
+    assert np.array_equal(U.fuse_bg(bg, k["bg_always"], 0.1), k["fused_bg"])
+    assert np.array_equal(U.bgdiff_gate(fr, k["near_bg"], al, 25), k["gate"])
+    assert np.array_equal(U.binarise_dilate(al), k["binarise_dilate"])
+    # patched background is returned bit-exactly when asked for
+    fg, bgo = vu.ops.get_fg(dev(fr), dev(al), dev(bg), 1, want_bg=True)
+    assert np.array_equal(host(bgo), R.patch_bg(bg, fr, al, "lt128"))
+
+
+def test_blend_all_alpha_values(vu):
+    """every (fg, alpha, bg) byte triple class: float64 sequences are bit-exact."""
+    rng = np.random.default_rng(3)
+    fg = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    bg = rng.integers(0, 256, (256, 256, 3), dtype=np.uint8)
+    al = np.repeat(np.arange(256, dtype=np.uint8)[:, None], 256, 1)
+    U = vu.U
+    assert np.array_equal(U.replace_blend(fg, al, bg), R.replace_blend(fg, al, bg))
+    assert np.array_equal(U.fuse_fgbg(fg, bg, al), R.fuse_fgbg(fg, bg, al))
+    assert np.array_equal(U.get_fg_naive(fg, al), R.get_fg_naive(fg, al))
+    assert np.array_equal(U.composite_fgbg(fg, al, bg), R.composite_fgbg(fg, al, bg))
+    assert np.array_equal(U.get_fg(fg, al, bg), R.get_fg(fg, al, bg))
+
+
+# ---- temporal ----------------------------------------------------------------------------------
+
+def test_temporal_golden(vu, golden):
+    t = golden("temporal")
+    U = vu.U
+    bg, ma = U.masked_temporal_mean(t["frames"], t["masks"])
+    assert np.array_equal(bg, t["mean_bg"]) and np.array_equal(ma, t["mean_mask_always"])
+    assert np.array_equal(U.temporal_median(t["frames"]), t["median_even"])
+    assert np.array_equal(U.temporal_median(t["frames"][:23]), t["median_odd"])
+    assert np.array_equal(U.temporal_median(t["rnd"]), t["median_rnd"])   # 33x47x3: tail path + ragged size
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 255, 256, 300, 511])
+def test_temporal_median_vs_oracle(vu, n):
+    from video_unscreen_b200 import synth
+    h, w = 24, 64
+    frames = synth.random_clip(n, h, w, seed=n)
+    assert np.array_equal(vu.U.temporal_median(frames), R.temporal_median(frames))
+    # heavily repeated values (counter wrap / saturation hazards)
+    const = np.full((n, h, w, 3), 7, np.uint8)
+    const[: n // 3] = 200
+    assert np.array_equal(vu.U.temporal_median(const), R.temporal_median(const))
+
+
+def test_temporal_median_properties_full_size(vu):
+    """BASELINE config 2 size (300 x 1080p): size-independent properties.
+    median of a clip whose frames are a permutation of values is order
+    independent; median of [x, x, ..., x] is x; min <= median <= max."""
+    n, h, w = 300, 1080, 1920
+    g = torch.Generator(device="cuda").manual_seed(0)
+    base = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    noise = torch.randint(0, 13, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+    frames = (base.to(torch.int16)[None] + noise.to(torch.int16) - 6).clamp_(0, 255).to(torch.uint8)
+    del noise
+    med = vu.ops.temporal_median(frames)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    med2 = vu.ops.temporal_median(frames[perm].contiguous())
+    assert torch.equal(med, med2)
+    lo = frames.amin(0)
+    hi = frames.amax(0)
+    assert bool(((med >= lo) & (med <= hi)).all())
+    # exact check on a strip against torch's own sort-based order statistics
+    strip = frames[:, 500:520].to(torch.int16)
+    s, _ = strip.sort(0)
+    want = ((s[n // 2 - 1] + s[n // 2]) >> 1).to(torch.uint8)
+    assert torch.equal(med[500:520], want)
+    del frames
+    const = torch.full((n, 8, 64, 3), 77, dtype=torch.uint8, device="cuda")
+    assert bool((vu.ops.temporal_median(const) == 77).all())

@@ -1,0 +1,265 @@
+// Compositing family: get_fg / get_bg in
+// float32 HSV arithmetic (unscreen/utils/fgfuncs.py:84-137), fused with the
+// predicated background patch of the pipeline scripts; the float64 blends of
+// fgfuncs.py:68-81,172-214, visualize.py:7-24 and tools/replace/replace.py:
+// 74-76; the background fusion and difference gate of bg_offline.py:150-160.
+// Every float op is a single IEEE rounding (__f*_rn / __d*_rn) in the
+// reference's operation order, so the stages before cv2's HSV2BGR are
+// bit-exact; HSV2BGR itself is the truncating whole-image variant (+-1 LSB
+// against cv2 by cv2's own inconsistency).
+#include "vu_common.cuh"
+
+namespace vu {
+namespace {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ int trunc_clamp255(float x) { return (int)fminf(fmaxf(x, 0.f), 255.f); }
+
+// 4 pixels per thread; alpha word holds the 4 alphas
+template <int PATCH, bool WRITE_BG>
+__global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restrict__ frame, const uint8_t* __restrict__ alpha,
+                                                         const uint8_t* __restrict__ bg, int64_t ngroups, int64_t bg_groups,
+                                                         uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const unsigned* f4 = reinterpret_cast<const unsigned*>(frame) + 3 * g;
+    const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * (g % bg_groups);
+    int c[12], q[12], o[12];
+    unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
+    unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
+    const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = (aw >> (8 * i)) & 255;
+      const bool patch = (PATCH == VU_PATCH_ALPHA_LT128) ? (a < 128) : (PATCH == VU_PATCH_ALPHA_EQ0 ? (a == 0) : false);
+      if (patch) { q[3 * i] = c[3 * i]; q[3 * i + 1] = c[3 * i + 1]; q[3 * i + 2] = c[3 * i + 2]; }
+      int ih, is, iv, bh, bs, bv;
+      bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
+      bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bv);
+      const float k = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));   // 1 - alpha/255.
+      const int fh = trunc_clamp255(__fsub_rn((float)ih, __fmul_rn(k, (float)bh)));
+      const int fs = trunc_clamp255(__fsub_rn((float)is, __fmul_rn(k, (float)bs)));
+      const int fv = trunc_clamp255(__fsub_rn((float)iv, __fmul_rn(k, (float)bv)));
+      hsv2bgr_px(fh, fs, fv, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+    }
+    unsigned w0, w1, w2;
+    pack12(o, w0, w1, w2);
+    unsigned* d4 = reinterpret_cast<unsigned*>(fg_out) + 3 * g;
+    d4[0] = w0; d4[1] = w1; d4[2] = w2;
+    if (WRITE_BG) {
+      pack12(q, w0, w1, w2);
+      unsigned* e4 = reinterpret_cast<unsigned*>(bg_out) + 3 * g;
+      e4[0] = w0; e4[1] = w1; e4[2] = w2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) get_bg_kernel(const uint8_t* __restrict__ alpha, const uint8_t* __restrict__ bg, int64_t ngroups,
+                                                         uint8_t* __restrict__ out) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * g;
+    int q[12], o[12];
+    unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
+    const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int a = (aw >> (8 * i)) & 255;
+      int bh, bs, bv;
+      bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bv);
+      const float k = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
+      hsv2bgr_px(trunc_clamp255(__fmul_rn(k, (float)bh)), trunc_clamp255(__fmul_rn(k, (float)bs)), trunc_clamp255(__fmul_rn(k, (float)bv)),
+                 o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+    }
+    unsigned w0, w1, w2;
+    pack12(o, w0, w1, w2);
+    unsigned* d4 = reinterpret_cast<unsigned*>(out) + 3 * g;
+    d4[0] = w0; d4[1] = w1; d4[2] = w2;
+  }
+}
+
+// float64 blends, one thread per 4 pixels.  AC = alpha channels (1 or 3)
+template <int MODE, int AC>
+__global__ void __launch_bounds__(THREADS) blend_kernel(const uint8_t* __restrict__ fg, const uint8_t* __restrict__ alpha,
+                                                        const uint8_t* __restrict__ bg, int64_t ngroups, int64_t bg_groups,
+                                                        uint8_t* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const unsigned* f4 = reinterpret_cast<const unsigned*>(fg) + 3 * g;
+    int c[12], q[12], a[12], o[12];
+    unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
+    if (MODE != VU_BLEND_NAIVE) {
+      const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * (g % bg_groups);
+      unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
+    }
+    if (AC == 3) {
+      const unsigned* a4 = reinterpret_cast<const unsigned*>(alpha) + 3 * g;
+      unpack12(__ldg(a4), __ldg(a4 + 1), __ldg(a4 + 2), a);
+    } else {
+      const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[3 * i] = a[3 * i + 1] = a[3 * i + 2] = (aw >> (8 * i)) & 255;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      double m = __ddiv_rn((double)a[i], 255.0);
+      double r;
+      if (MODE == VU_BLEND_NAIVE) {
+        r = __dmul_rn((double)c[i], m);
+      } else if (MODE == VU_BLEND_FUSE) {
+        r = __dadd_rn(__dmul_rn(m, (double)c[i]), __dmul_rn(__dsub_rn(1.0, m), (double)q[i]));
+      } else if (MODE == VU_BLEND_COMPOSITE) {
+        if (m > 0.9) m = 1.0;
+        r = __dadd_rn((double)c[i], __dmul_rn((double)q[i], __dsub_rn(1.0, m)));
+        r = fmin(fmax(r, 0.0), 255.0);
+      } else {
+        r = __dadd_rn(__dmul_rn((double)c[i], m), __dmul_rn((double)q[i], __dsub_rn(1.0, m)));
+      }
+      o[i] = (int)r;
+    }
+    unsigned w0, w1, w2;
+    pack12(o, w0, w1, w2);
+    unsigned* d4 = reinterpret_cast<unsigned*>(out) + 3 * g;
+    d4[0] = w0; d4[1] = w1; d4[2] = w2;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) fuse_bg_kernel(const unsigned* __restrict__ bg, const unsigned* __restrict__ always, int64_t nwords,
+                                                          int64_t always_words, float beta, float omb, unsigned* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += stride) {
+    const unsigned a = __ldg(bg + i), b = __ldg(always + (i % always_words));
+    unsigned w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float x = (float)((a >> (8 * k)) & 255), y = (float)((b >> (8 * k)) & 255);
+      const float r = __fadd_rn(__fmul_rn(x, beta), __fmul_rn(omb, y));
+      w |= (unsigned)((int)r & 255) << (8 * k);
+    }
+    out[i] = w;
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) bgdiff_gray_kernel(const uint8_t* __restrict__ frame, const uint8_t* __restrict__ bg, int64_t ngroups,
+                                                              int64_t bg_groups, int thr, uint8_t* __restrict__ gray) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const unsigned* f4 = reinterpret_cast<const unsigned*>(frame) + 3 * g;
+    const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * (g % bg_groups);
+    int c[12], q[12];
+    unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
+    unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
+    unsigned w = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int y = bgr2gray_px(abs(c[3 * i] - q[3 * i]), abs(c[3 * i + 1] - q[3 * i + 1]), abs(c[3 * i + 2] - q[3 * i + 2]));
+      if (y > thr) y = 255;  // values <= thr are kept, not zeroed
+      w |= (unsigned)y << (8 * i);
+    }
+    reinterpret_cast<unsigned*>(gray)[g] = w;
+  }
+}
+
+inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
+
+}  // namespace
+}  // namespace vu
+
+using namespace vu;
+
+// The vector kernels need 4-byte aligned pointers and pixel counts that are
+// multiples of 4 (true for every even-sized frame); anything else is refused
+// rather than silently taking a different code path.
+#define VU_REQUIRE_VEC(npix, ...)                                   \
+  do {                                                              \
+    const void* ptrs__[] = {__VA_ARGS__};                           \
+    for (const void* p__ : ptrs__)                                  \
+      if (p__ && !al4(p__)) return VU_ERR_UNSUPPORTED;              \
+    if ((npix) % 4 != 0) return VU_ERR_UNSUPPORTED;                 \
+  } while (0)
+
+extern "C" int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8_t* bg, int64_t npix, int64_t bg_npix, int patch_mode,
+                         uint8_t* fg_out, uint8_t* bg_out, vu_stream_t stream) {
+  VU_REQUIRE(frame && alpha && bg && fg_out && npix >= 0 && bg_npix > 0);
+  VU_REQUIRE(patch_mode >= VU_PATCH_NONE && patch_mode <= VU_PATCH_ALPHA_EQ0);
+  VU_REQUIRE_VEC(npix, frame, alpha, bg, fg_out, bg_out);
+  if (bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
+  if (npix == 0) return VU_OK;
+  const int64_t ng = npix / 4, bgg = bg_npix / 4;
+  const int grid = grid_for(ng, THREADS, 8);
+#define LAUNCH(P, W) get_fg_kernel<P, W><<<grid, THREADS, 0, S(stream)>>>(frame, alpha, bg, ng, bgg, fg_out, bg_out)
+  if (bg_out) {
+    if (patch_mode == VU_PATCH_NONE) LAUNCH(VU_PATCH_NONE, true);
+    else if (patch_mode == VU_PATCH_ALPHA_LT128) LAUNCH(VU_PATCH_ALPHA_LT128, true);
+    else LAUNCH(VU_PATCH_ALPHA_EQ0, true);
+  } else {
+    if (patch_mode == VU_PATCH_NONE) LAUNCH(VU_PATCH_NONE, false);
+    else if (patch_mode == VU_PATCH_ALPHA_LT128) LAUNCH(VU_PATCH_ALPHA_LT128, false);
+    else LAUNCH(VU_PATCH_ALPHA_EQ0, false);
+  }
+#undef LAUNCH
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_get_bg(const uint8_t* alpha, const uint8_t* bg, int64_t npix, uint8_t* out, vu_stream_t stream) {
+  VU_REQUIRE(alpha && bg && out && npix >= 0);
+  VU_REQUIRE_VEC(npix, alpha, bg, out);
+  if (npix == 0) return VU_OK;
+  get_bg_kernel<<<grid_for(npix / 4, THREADS, 8), THREADS, 0, S(stream)>>>(alpha, bg, npix / 4, out);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int alpha_channels, const uint8_t* bg, int64_t npix,
+                        int64_t bg_npix, uint8_t* out, vu_stream_t stream) {
+  VU_REQUIRE(fg && alpha && out && npix >= 0);
+  VU_REQUIRE(mode >= VU_BLEND_NAIVE && mode <= VU_BLEND_REPLACE);
+  VU_REQUIRE(alpha_channels == 1 || alpha_channels == 3);
+  VU_REQUIRE(mode == VU_BLEND_NAIVE || (bg && bg_npix > 0));
+  VU_REQUIRE_VEC(npix, fg, alpha, bg, out);
+  if (mode != VU_BLEND_NAIVE && bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
+  if (npix == 0) return VU_OK;
+  const int64_t ng = npix / 4, bgg = (mode == VU_BLEND_NAIVE) ? 1 : bg_npix / 4;
+  const int grid = grid_for(ng, THREADS, 8);
+#define LAUNCH(M)                                                                                        \
+  do {                                                                                                   \
+    if (alpha_channels == 1) blend_kernel<M, 1><<<grid, THREADS, 0, S(stream)>>>(fg, alpha, bg, ng, bgg, out); \
+    else blend_kernel<M, 3><<<grid, THREADS, 0, S(stream)>>>(fg, alpha, bg, ng, bgg, out);               \
+  } while (0)
+  switch (mode) {
+    case VU_BLEND_NAIVE: LAUNCH(VU_BLEND_NAIVE); break;
+    case VU_BLEND_FUSE: LAUNCH(VU_BLEND_FUSE); break;
+    case VU_BLEND_COMPOSITE: LAUNCH(VU_BLEND_COMPOSITE); break;
+    default: LAUNCH(VU_BLEND_REPLACE); break;
+  }
+#undef LAUNCH
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_fuse_bg(const uint8_t* bg, const uint8_t* bg_always, int64_t npix, int64_t always_npix, float beta, float one_minus_beta,
+                          uint8_t* out, vu_stream_t stream) {
+  VU_REQUIRE(bg && bg_always && out && npix >= 0 && always_npix > 0);
+  VU_REQUIRE_VEC(npix, bg, bg_always, out);
+  if (always_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
+  if (npix == 0) return VU_OK;
+  const int64_t nwords = npix * 3 / 4, aw = always_npix * 3 / 4;
+  fuse_bg_kernel<<<grid_for(nwords, THREADS, 8), THREADS, 0, S(stream)>>>(reinterpret_cast<const unsigned*>(bg), reinterpret_cast<const unsigned*>(bg_always),
+                                                                           nwords, aw, beta, one_minus_beta, reinterpret_cast<unsigned*>(out));
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_bgdiff_gray(const uint8_t* frame, const uint8_t* bg, int64_t npix, int64_t bg_npix, int thr, uint8_t* gray,
+                              vu_stream_t stream) {
+  VU_REQUIRE(frame && bg && gray && npix >= 0 && bg_npix > 0);
+  VU_REQUIRE_VEC(npix, frame, bg, gray);
+  if (bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
+  if (npix == 0) return VU_OK;
+  bgdiff_gray_kernel<<<grid_for(npix / 4, THREADS, 8), THREADS, 0, S(stream)>>>(frame, bg, npix / 4, bg_npix / 4, thr, gray);
+  VU_RETURN_LAUNCH();
+}

@@ -1,0 +1,272 @@
+// Temporal background estimators.
+//
+// vu_temporal_median_u8: exact per-element median over n frames, built from
+// streaming 256-bin histograms in shared memory.  One warp owns a segment of
+// 32*PX consecutive bytes of every frame; lane l owns PX of them and a private
+// column of 256 packed counters laid out so that its bank is always `lane`
+// (bin stride = WARPS*128 bytes): every increment is a conflict-free shared
+// atomic, whatever the pixel values are.  Warps never synchronise with each
+// other, so one warp's histogram scan overlaps the other warps' streaming.
+//   n <= 255   : four 8-bit counters per word  (PX = 4, 128-byte segments)
+//   n <= 65535 : two 16-bit counters per word  (PX = 2,  64-byte segments)
+// The median is read back with a two-level scan (16 coarse groups, then 16
+// bins); even n returns (lo + hi) >> 1 like np.median(...).astype(uint8).
+//
+// vu_masked_temporal_mean: tools/unscreen/bg_offline.py:106-125 as integer
+// sums and counts per pixel, one float64 divide at the end.
+#include "vu_common.cuh"
+
+namespace vu {
+namespace {
+
+constexpr int WARPS = 7;
+constexpr int MTHREADS = WARPS * 32;
+constexpr int BIN_STRIDE = WARPS * 128;  // bytes between bins
+constexpr int HIST_BYTES = 256 * BIN_STRIDE;
+
+struct PolU8x4 {
+  static constexpr int PX = 4;
+  __device__ static __forceinline__ void add(unsigned char* base, unsigned w) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) atomicAdd(reinterpret_cast<unsigned*>(base + ((w >> (8 * j)) & 0xFFu) * BIN_STRIDE), 1u << (8 * j));
+  }
+  __device__ static __forceinline__ void unpack(unsigned w, unsigned* c) {
+    c[0] = w & 255u; c[1] = (w >> 8) & 255u; c[2] = (w >> 16) & 255u; c[3] = w >> 24;
+  }
+};
+struct PolU16x2 {
+  static constexpr int PX = 2;
+  __device__ static __forceinline__ void add(unsigned char* base, unsigned w) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) atomicAdd(reinterpret_cast<unsigned*>(base + ((w >> (8 * j)) & 0xFFu) * BIN_STRIDE), 1u << (16 * j));
+  }
+  __device__ static __forceinline__ void unpack(unsigned w, unsigned* c) { c[0] = w & 0xFFFFu; c[1] = w >> 16; }
+};
+
+template <int PX>
+__device__ __forceinline__ unsigned load_px(const uint8_t* p) {
+  if (PX == 4) return __ldg(reinterpret_cast<const unsigned*>(p));
+  return __ldg(reinterpret_cast<const unsigned short*>(p));
+}
+
+template <class P, int U>
+__global__ void __launch_bounds__(MTHREADS, 1) median_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
+                                                             int nseg) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int PX = P::PX;
+  constexpr int SEG = 32 * PX;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* base = smem + warp * 128 + lane * 4;
+  const unsigned klo = (unsigned)(n - 1) >> 1, khi = (unsigned)n >> 1;
+  const int nb = n / U;
+  for (int seg = blockIdx.x * WARPS + warp; seg < nseg; seg += gridDim.x * WARPS) {
+#pragma unroll 8
+    for (int b = 0; b < 256; ++b) *reinterpret_cast<unsigned*>(base + b * BIN_STRIDE) = 0u;
+    __syncwarp();
+    {
+      const uint8_t* p = frames + (long long)seg * SEG + lane * PX;
+      unsigned ra[U], rb[U];
+      auto load = [&](unsigned(&r)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { r[u] = load_px<PX>(p); p += m; }
+      };
+      auto proc = [&](unsigned(&r)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) P::add(base, r[u]);
+      };
+      if (nb > 0) load(ra);
+      for (int i = 0; i < nb; i += 2) {
+        if (i + 1 < nb) load(rb);
+        proc(ra);
+        if (i + 1 < nb) {
+          if (i + 2 < nb) load(ra);
+          proc(rb);
+        }
+      }
+      for (int f = nb * U; f < n; ++f) { P::add(base, load_px<PX>(p)); p += m; }
+    }
+    __syncwarp();
+    // two-level scan
+    unsigned cum[PX], gsel[PX][2], before[PX][2];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) { cum[j] = 0; gsel[j][0] = gsel[j][1] = 0; before[j][0] = before[j][1] = 0; }
+#pragma unroll 1
+    for (int g = 0; g < 16; ++g) {
+      unsigned c[PX];
+#pragma unroll
+      for (int j = 0; j < PX; ++j) c[j] = 0;
+#pragma unroll
+      for (int b = 0; b < 16; ++b) {
+        unsigned t[PX];
+        P::unpack(*reinterpret_cast<unsigned*>(base + (g * 16 + b) * BIN_STRIDE), t);
+#pragma unroll
+        for (int j = 0; j < PX; ++j) c[j] += t[j];
+      }
+#pragma unroll
+      for (int j = 0; j < PX; ++j) {
+        const unsigned nc = cum[j] + c[j];
+        if (nc <= klo) { gsel[j][0] = g + 1; before[j][0] = nc; }
+        if (nc <= khi) { gsel[j][1] = g + 1; before[j][1] = nc; }
+        cum[j] = nc;
+      }
+    }
+    unsigned res = 0;
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+      unsigned med[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const unsigned k = q ? khi : klo;
+        if (q == 1 && khi == klo) { med[1] = med[0]; continue; }
+        const unsigned g = min(gsel[j][q], 15u);
+        unsigned v = g * 16, c2 = before[j][q];
+#pragma unroll 4
+        for (int b = 0; b < 16; ++b) {
+          unsigned t[PX];
+          P::unpack(*reinterpret_cast<unsigned*>(base + (g * 16 + b) * BIN_STRIDE), t);
+          c2 += t[j];
+          if (c2 <= k) v = g * 16 + b + 1;
+        }
+        med[q] = min(v, 255u);
+      }
+      res |= ((med[0] + med[1]) >> 1) << (8 * j);
+    }
+    uint8_t* dst = out + (long long)seg * SEG;
+    if (PX == 4) reinterpret_cast<unsigned*>(dst)[lane] = res;
+    else reinterpret_cast<unsigned short*>(dst)[lane] = (unsigned short)res;
+    __syncwarp();
+  }
+}
+
+// elements that do not fill a whole segment (and unaligned inputs): one CTA
+// per element, 256-bin shared histogram
+__global__ void __launch_bounds__(256) median_tail_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
+                                                          long long first) {
+  __shared__ unsigned hist[256];
+  const long long e = first + blockIdx.x;
+  hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int f = threadIdx.x; f < n; f += 256) atomicAdd(&hist[__ldg(frames + (long long)f * m + e)], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned klo = (unsigned)(n - 1) >> 1, khi = (unsigned)n >> 1;
+    unsigned cum = 0, lo = 255, hi = 255;
+    bool flo = false, fhi = false;
+    for (int b = 0; b < 256; ++b) {
+      cum += hist[b];
+      if (!flo && cum > klo) { lo = b; flo = true; }
+      if (!fhi && cum > khi) { hi = b; fhi = true; }
+    }
+    out[e] = (uint8_t)((lo + hi) >> 1);
+  }
+}
+
+// ---- masked temporal mean -------------------------------------------------
+constexpr int TT = 256;
+__global__ void __launch_bounds__(TT) masked_mean_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int n,
+                                                         int64_t ngroups, int64_t npix, int min_count, uint8_t* __restrict__ bg_out,
+                                                         uint8_t* __restrict__ always_out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    unsigned sum[12], cnt[4];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sum[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cnt[i] = 0;
+    const unsigned* f4 = reinterpret_cast<const unsigned*>(frames) + 3 * g;
+    const unsigned* m4 = reinterpret_cast<const unsigned*>(masks) + g;
+    const int64_t fstride = npix * 3 / 4, mstride = npix / 4;
+#pragma unroll 4
+    for (int f = 0; f < n; ++f) {
+      int c[12];
+      unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
+      const unsigned mw = __ldg(m4);
+      f4 += fstride;
+      m4 += mstride;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const unsigned mv = (mw >> (8 * i)) & 255u;
+        const unsigned keep = 1u - mv / 255u;  // frame * (1 - mask // 255)
+        sum[3 * i] += c[3 * i] * keep;
+        sum[3 * i + 1] += c[3 * i + 1] * keep;
+        sum[3 * i + 2] += c[3 * i + 2] * keep;
+        cnt[i] += mv < 250u;               // count += (mask < 250)
+      }
+    }
+    int o[12];
+    unsigned aw = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const bool always = cnt[i] <= (unsigned)min_count;
+      const double den = (double)(cnt[i] ? cnt[i] : 1u);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double q = fmin(fmax(__ddiv_rn((double)sum[3 * i + k], den), 0.0), 255.0);
+        o[3 * i + k] = always ? 0 : (int)q;
+      }
+      aw |= (always ? 255u : 0u) << (8 * i);
+    }
+    unsigned w0, w1, w2;
+    pack12(o, w0, w1, w2);
+    unsigned* d4 = reinterpret_cast<unsigned*>(bg_out) + 3 * g;
+    d4[0] = w0; d4[1] = w1; d4[2] = w2;
+    reinterpret_cast<unsigned*>(always_out)[g] = aw;
+  }
+}
+
+template <class P, int U>
+int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    int e = record_cuda(cudaFuncSetAttribute(median_kernel<P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_BYTES));
+    if (e) return e;
+    configured = true;
+  }
+  int grid = device_sms();
+  const int64_t need = (nseg + WARPS - 1) / WARPS;
+  if (need < grid) grid = (int)need;
+  median_kernel<P, U><<<grid, MTHREADS, HIST_BYTES, S(stream)>>>(frames, out, n, m, (int)nseg);
+  return record_cuda(cudaGetLastError());
+}
+
+}  // namespace
+}  // namespace vu
+
+using namespace vu;
+
+extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream) {
+  VU_REQUIRE(frames && out && m >= 0);
+  if (n < 1 || n > 65535) return VU_ERR_UNSUPPORTED;
+  if (m == 0) return VU_OK;
+  const bool small = n <= 255;
+  const int seg = small ? 128 : 64;
+  const int align = small ? 4 : 2;
+  // vector path needs element-aligned frame rows
+  const bool ok = (reinterpret_cast<uintptr_t>(frames) % align == 0) && (reinterpret_cast<uintptr_t>(out) % align == 0) && (m % align == 0);
+  int64_t nseg = ok ? m / seg : 0;
+  if (nseg > 0x7fffffff) return VU_ERR_UNSUPPORTED;
+  if (nseg > 0) {
+    int e = small ? launch_median<PolU8x4, 32>(frames, n, m, nseg, out, stream) : launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
+    if (e) return e;
+  }
+  const int64_t first = nseg * seg;
+  if (first < m) {
+    if (m - first > 0x7fffffff) return VU_ERR_UNSUPPORTED;
+    median_tail_kernel<<<(unsigned)(m - first), 256, 0, S(stream)>>>(frames, out, n, m, first);
+    return record_cuda(cudaGetLastError());
+  }
+  return VU_OK;
+}
+
+extern "C" int vu_masked_temporal_mean(const uint8_t* frames, const uint8_t* masks, int n, int64_t npix, int min_count, uint8_t* bg_out,
+                                       uint8_t* mask_always_out, vu_stream_t stream) {
+  VU_REQUIRE(frames && masks && bg_out && mask_always_out && n >= 1 && npix >= 0);
+  if (n > 16000000) return VU_ERR_UNSUPPORTED;  // 32-bit sums: 255 * n must fit
+  if (npix % 4 != 0) return VU_ERR_UNSUPPORTED;
+  const void* ptrs[] = {frames, masks, bg_out, mask_always_out};
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 3) return VU_ERR_UNSUPPORTED;
+  if (npix == 0) return VU_OK;
+  masked_mean_kernel<<<grid_for(npix / 4, TT, 8), TT, 0, S(stream)>>>(frames, masks, n, npix / 4, npix, min_count, bg_out, mask_always_out);
+  VU_RETURN_LAUNCH();
+}

@@ -1,0 +1,323 @@
+"""Device-level operators: thin, typed wrappers over the C ABI.
+
+Inputs and outputs are contiguous uint8 CUDA tensors (torch is used for device
+memory and streams only).  Images are [H,W,3] or [N,H,W,3] (BGR), masks [H,W]
+or [N,H,W].  Every function enqueues on torch's current stream and returns
+device tensors; nothing synchronises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, i3, lib
+
+u8 = torch.uint8
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _dev(t, dtype=u8):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == dtype):
+        raise TypeError(f"expected a CUDA {dtype} tensor, got {type(t)} {getattr(t, 'dtype', None)} {getattr(t, 'device', None)}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _img(t):
+    t = _dev(t)
+    if t.ndim not in (3, 4) or t.shape[-1] != 3:
+        raise ValueError(f"expected [H,W,3] or [N,H,W,3], got {tuple(t.shape)}")
+    return t
+
+
+def _mask(t):
+    t = _dev(t)
+    if t.ndim not in (2, 3):
+        raise ValueError(f"expected [H,W] or [N,H,W], got {tuple(t.shape)}")
+    return t
+
+
+# ---- colour ---------------------------------------------------------------
+
+def bgr2hsv(x):
+    x = _img(x)
+    out = torch.empty_like(x)
+    check(lib().vu_bgr2hsv_u8(_p(x), _p(out), x.numel() // 3, _stream()))
+    return out
+
+
+def hsv2bgr(x):
+    x = _img(x)
+    out = torch.empty_like(x)
+    check(lib().vu_hsv2bgr_u8(_p(x), _p(out), x.numel() // 3, _stream()))
+    return out
+
+
+def bgr2gray(x):
+    x = _img(x)
+    out = torch.empty(x.shape[:-1], dtype=u8, device=x.device)
+    check(lib().vu_bgr2gray_u8(_p(x), _p(out), x.numel() // 3, _stream()))
+    return out
+
+
+def inrange_color(x, lo, hi):
+    """0/1 mask of lo <= HSV(x) <= hi (inclusive, per channel)."""
+    x = _img(x)
+    out = torch.empty(x.shape[:-1], dtype=u8, device=x.device)
+    check(lib().vu_inrange_color(_p(x), x.numel() // 3, i3(lo), i3(hi), _p(out), _stream()))
+    return out
+
+
+def inrange_image(x, bg, half):
+    """0/1 mask of clamp(HSV(bg)-half,10,255) <= HSV(x) <= clamp(HSV(bg)+half,10,255)."""
+    x, bg = _img(x), _img(bg)
+    if bg.shape[-3:] != x.shape[-3:]:
+        raise ValueError("background image must have the frame's H,W")
+    if bg.ndim == 4 and bg.shape != x.shape:
+        raise ValueError("batched background must match the frames' shape")
+    out = torch.empty(x.shape[:-1], dtype=u8, device=x.device)
+    check(lib().vu_inrange_image(_p(x), _p(bg), x.numel() // 3, bg.numel() // 3, i3(half), _p(out), _stream()))
+    return out
+
+
+# ---- morphology / resize ----------------------------------------------------
+
+def morph(x, ksize, iters, op):
+    x = _mask(x)
+    n = 1 if x.ndim == 2 else x.shape[0]
+    h, w = x.shape[-2:]
+    out = torch.empty_like(x)
+    check(lib().vu_morph_u8(_p(x), _p(out), n, h, w, int(ksize), int(iters), op, ctypes.c_void_p(0), 0, _stream()))
+    return out
+
+
+def dilate(x, ksize, iters):
+    return morph(x, ksize, iters, _lib.DILATE)
+
+
+def erode(x, ksize, iters):
+    return morph(x, ksize, iters, _lib.ERODE)
+
+
+def _resize(fn, x, dh, dw, channels):
+    x = _dev(x)
+    if channels == 3:
+        x = _img(x)
+        n = 1 if x.ndim == 3 else x.shape[0]
+        sh, sw = x.shape[-3:-1]
+        shape = (dh, dw, 3) if x.ndim == 3 else (n, dh, dw, 3)
+    else:
+        x = _mask(x)
+        n = 1 if x.ndim == 2 else x.shape[0]
+        sh, sw = x.shape[-2:]
+        shape = (dh, dw) if x.ndim == 2 else (n, dh, dw)
+    out = torch.empty(shape, dtype=u8, device=x.device)
+    check(fn(_p(x), n, sh, sw, channels, _p(out), int(dh), int(dw), _stream()))
+    return out
+
+
+def resize_linear_mask(x, dh, dw):
+    return _resize(lib().vu_resize_linear_u8, x, dh, dw, 1)
+
+
+def resize_linear_image(x, dh, dw):
+    return _resize(lib().vu_resize_linear_u8, x, dh, dw, 3)
+
+
+def resize_nearest_mask(x, dh, dw):
+    return _resize(lib().vu_resize_nearest_u8, x, dh, dw, 1)
+
+
+def resize_nearest_image(x, dh, dw):
+    return _resize(lib().vu_resize_nearest_u8, x, dh, dw, 3)
+
+
+# ---- reductions / mask algebra ----------------------------------------------
+
+def _items(x, item_ndim):
+    n = 1 if x.ndim == item_ndim else x.shape[0]
+    return n, x.numel() // max(n, 1)
+
+
+def count_cmp(x, op, thr, item_ndim=2):
+    """per-item counts (int64 device tensor [n]) of x <op> thr."""
+    x = _dev(x)
+    n, per = _items(x, item_ndim)
+    out = torch.empty(n, dtype=torch.int64, device=x.device)
+    check(lib().vu_count_cmp_u8(_p(x), n, per, op, int(thr), _p(out), _stream()))
+    return out
+
+
+def count_and(a, b, item_ndim=2):
+    """[n,2] int64: (#{a>0 & b>0}, #{a>0}) per item."""
+    a, b = _dev(a), _dev(b)
+    n, per = _items(a, item_ndim)
+    out = torch.empty((n, 2), dtype=torch.int64, device=a.device)
+    check(lib().vu_count_and_u8(_p(a), _p(b), n, per, _p(out), _stream()))
+    return out
+
+
+def _binary(fn, a, b):
+    a, b = _dev(a), _dev(b)
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    out = torch.empty_like(a)
+    check(fn(_p(a), _p(b), _p(out), a.numel(), _stream()))
+    return out
+
+
+def mask_clear_where(a, b):
+    return _binary(lib().vu_mask_clear_where, a, b)
+
+
+def mask_set128_where(a, b):
+    return _binary(lib().vu_mask_set128_where, a, b)
+
+
+def mask_and01(a, b):
+    return _binary(lib().vu_mask_and01, a, b)
+
+
+def trimap_classify(dilated, eroded):
+    return _binary(lib().vu_trimap_classify, dilated, eroded)
+
+
+def trimap_snap(a):
+    a = _dev(a)
+    out = torch.empty_like(a)
+    check(lib().vu_trimap_snap(_p(a), a.numel(), _p(out), _stream()))
+    return out
+
+
+def gate(mask, g):
+    mask, g = _dev(mask), _dev(g)
+    out = torch.empty_like(mask)
+    check(lib().vu_gate(_p(mask), _p(g), mask.numel(), _p(out), _stream()))
+    return out
+
+
+def sub_wrap(a, b):
+    a, b = _dev(a), _dev(b)
+    out = torch.empty_like(a)
+    check(lib().vu_sub_wrap_u8(_p(a), _p(b), a.numel(), _p(out), _stream()))
+    return out
+
+
+def binarise(a, thr=128):
+    a = _dev(a)
+    out = torch.empty_like(a)
+    check(lib().vu_binarise(_p(a), a.numel(), int(thr), _p(out), _stream()))
+    return out
+
+
+# ---- colour filtering ---------------------------------------------------------
+
+def cf_alpha(hsv, luts):
+    hsv = _img(hsv)
+    luts = _dev(luts, torch.float32)
+    assert luts.numel() == 6 * 256
+    out = torch.empty(hsv.shape[:-1], dtype=u8, device=hsv.device)
+    check(lib().vu_cf_alpha_u8(_p(hsv), hsv.numel() // 3, _p(luts), _p(out), _stream()))
+    return out
+
+
+def cf_build_lut3d(luts):
+    luts = _dev(luts, torch.float32)
+    assert luts.numel() == 6 * 256
+    out = torch.empty((180, 256, 256), dtype=u8, device=luts.device)
+    check(lib().vu_cf_build_lut3d(_p(luts), _p(out), _stream()))
+    return out
+
+
+def cf_alpha_lut3d(hsv, lut3d):
+    hsv, lut3d = _img(hsv), _dev(lut3d)
+    assert lut3d.numel() == 180 * 256 * 256
+    out = torch.empty(hsv.shape[:-1], dtype=u8, device=hsv.device)
+    check(lib().vu_cf_alpha_lut3d_u8(_p(hsv), hsv.numel() // 3, _p(lut3d), _p(out), _stream()))
+    return out
+
+
+def cf_threshold(alpha, mask, thr_ratio=0.8):
+    """postprocess step 1 (adaptive threshold), per item."""
+    alpha, mask = _mask(alpha), _mask(mask)
+    n, per = _items(alpha, 2)
+    stats = torch.empty((n, 2), dtype=torch.int64, device=alpha.device)
+    check(lib().vu_cf_threshold_stats(_p(alpha), _p(mask), n, per, _p(stats), _stream()))
+    out = torch.empty_like(alpha)
+    check(lib().vu_cf_threshold_apply(_p(alpha), n, per, _p(stats), float(thr_ratio), _p(out), _stream()))
+    return out
+
+
+# ---- compositing ----------------------------------------------------------------
+
+def get_fg(frame, alpha, bg, patch=_lib.PATCH_NONE, want_bg=False):
+    frame, alpha, bg = _img(frame), _mask(alpha), _img(bg)
+    if alpha.shape != frame.shape[:-1]:
+        raise ValueError("alpha must have the frame's [N,]H,W")
+    fg = torch.empty_like(frame)
+    bgo = torch.empty_like(frame) if want_bg else None
+    check(lib().vu_get_fg(_p(frame), _p(alpha), _p(bg), frame.numel() // 3, bg.numel() // 3, patch, _p(fg), _p(bgo), _stream()))
+    return (fg, bgo) if want_bg else fg
+
+
+def get_bg(alpha, bg):
+    alpha, bg = _mask(alpha), _img(bg)
+    out = torch.empty_like(bg)
+    check(lib().vu_get_bg(_p(alpha), _p(bg), bg.numel() // 3, _p(out), _stream()))
+    return out
+
+
+def blend(mode, fg, alpha, bg=None):
+    fg, alpha = _img(fg), _dev(alpha)
+    ac = 3 if alpha.shape == fg.shape else 1
+    if ac == 1 and alpha.shape != fg.shape[:-1]:
+        raise ValueError("alpha must be [N,]H,W or the image's shape")
+    if bg is not None:
+        bg = _img(bg)
+    out = torch.empty_like(fg)
+    check(lib().vu_blend(mode, _p(fg), _p(alpha), ac, _p(bg), fg.numel() // 3, (bg.numel() // 3) if bg is not None else 0, _p(out), _stream()))
+    return out
+
+
+def fuse_bg(bg, bg_always, beta):
+    import numpy as np
+    bg, bg_always = _img(bg), _img(bg_always)
+    out = torch.empty_like(bg)
+    b = float(np.float32(beta))
+    omb = float(np.float32(1 - beta))
+    check(lib().vu_fuse_bg(_p(bg), _p(bg_always), bg.numel() // 3, bg_always.numel() // 3, b, omb, _p(out), _stream()))
+    return out
+
+
+def bgdiff_gray(frame, bg, thr):
+    frame, bg = _img(frame), _img(bg)
+    out = torch.empty(frame.shape[:-1], dtype=u8, device=frame.device)
+    check(lib().vu_bgdiff_gray(_p(frame), _p(bg), frame.numel() // 3, bg.numel() // 3, int(thr), _p(out), _stream()))
+    return out
+
+
+# ---- temporal ---------------------------------------------------------------------
+
+def temporal_median(frames, out=None):
+    frames = _dev(frames)
+    n = frames.shape[0]
+    m = frames.numel() // n
+    if out is None:
+        out = torch.empty(frames.shape[1:], dtype=u8, device=frames.device)
+    check(lib().vu_temporal_median_u8(_p(frames), n, m, _p(out), _stream()))
+    return out
+
+
+def masked_temporal_mean(frames, masks_dilated, min_count=10):
+    frames, masks_dilated = _img(frames), _mask(masks_dilated)
+    n, h, w, _ = frames.shape
+    bg = torch.empty((h, w, 3), dtype=u8, device=frames.device)
+    always = torch.empty((h, w), dtype=u8, device=frames.device)
+    check(lib().vu_masked_temporal_mean(_p(frames), _p(masks_dilated), n, h * w, int(min_count), _p(bg), _p(always), _stream()))
+    return bg, always

@@ -1,0 +1,5 @@
+from .fgfuncs import *  # noqa
+from .imgprocess import *  # noqa
+from .maskprocess import *  # noqa
+from .visualize import *  # noqa
+from .temporal import *  # noqa
