@@ -53,6 +53,8 @@ int vu_abi_version(void);
 const char* vu_status_string(int status);
 /* text of the last CUDA error seen by this library on the calling thread */
 const char* vu_last_cuda_error(void);
+/* number of kernels this library has launched in this process (all threads) */
+uint64_t vu_launch_count(void);
 
 /* ---- colour ------------------------------------------------------------ */
 /* cv2.cvtColor(BGR2HSV) uint8, H in [0,179]; colorfiltering/agent.py:310,

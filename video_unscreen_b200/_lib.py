@@ -30,6 +30,7 @@ SIGNATURES = {
     "vu_abi_version": (_i, []),
     "vu_status_string": (ctypes.c_char_p, [_i]),
     "vu_last_cuda_error": (ctypes.c_char_p, []),
+    "vu_launch_count": (ctypes.c_uint64, []),
     "vu_bgr2hsv_u8": (_i, [_p, _p, _i64, _p]),
     "vu_hsv2bgr_u8": (_i, [_p, _p, _i64, _p]),
     "vu_bgr2gray_u8": (_i, [_p, _p, _i64, _p]),

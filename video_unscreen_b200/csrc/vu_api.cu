@@ -1,4 +1,5 @@
 // Library plumbing: status strings, CUDA error capture, device properties.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 
@@ -7,6 +8,9 @@
 namespace vu {
 
 static thread_local char g_last_error[256] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void note_launch(int kernels) { g_launches.fetch_add((unsigned long long)kernels, std::memory_order_relaxed); }
 
 int record_cuda(cudaError_t e) {
   if (e == cudaSuccess) return VU_OK;
@@ -42,3 +46,5 @@ extern "C" const char* vu_status_string(int status) {
 }
 
 extern "C" const char* vu_last_cuda_error(void) { return vu::g_last_error; }
+
+extern "C" uint64_t vu_launch_count(void) { return vu::g_launches.load(); }

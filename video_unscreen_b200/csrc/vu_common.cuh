@@ -12,9 +12,14 @@ namespace vu {
 
 int record_cuda(cudaError_t e);  // stores the message for vu_last_cuda_error
 int device_sms();
+void note_launch(int kernels = 1);  // feeds vu_launch_count (bench.py reports it as gpu_launches)
 inline cudaStream_t S(vu_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
-#define VU_RETURN_LAUNCH() return ::vu::record_cuda(cudaGetLastError())
+#define VU_RETURN_LAUNCH()                        \
+  do {                                            \
+    ::vu::note_launch();                          \
+    return ::vu::record_cuda(cudaGetLastError()); \
+  } while (0)
 #define VU_REQUIRE(cond) \
   do {                   \
     if (!(cond)) return VU_ERR_INVALID_ARG; \

@@ -226,6 +226,7 @@ int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t
   const int64_t need = (nseg + WARPS - 1) / WARPS;
   if (need < grid) grid = (int)need;
   median_kernel<P, U><<<grid, MTHREADS, HIST_BYTES, S(stream)>>>(frames, out, n, m, (int)nseg);
+  note_launch();
   return record_cuda(cudaGetLastError());
 }
 
@@ -253,6 +254,7 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
   if (first < m) {
     if (m - first > 0x7fffffff) return VU_ERR_UNSUPPORTED;
     median_tail_kernel<<<(unsigned)(m - first), 256, 0, S(stream)>>>(frames, out, n, m, first);
+    note_launch();
     return record_cuda(cudaGetLastError());
   }
   return VU_OK;
