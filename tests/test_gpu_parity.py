@@ -252,7 +252,7 @@ def test_temporal_golden(vu, golden):
     assert np.array_equal(U.temporal_median(t["rnd"]), t["median_rnd"])   # 33x47x3: tail path + ragged size
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 16, 255, 256, 300, 511])
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 151, 152, 153, 255, 256, 299, 300, 304, 305, 511, 608, 609, 700])
 def test_temporal_median_vs_oracle(vu, n):
     from video_unscreen_b200 import synth
     h, w = 24, 64

@@ -1,14 +1,27 @@
 // Temporal background estimators.
 //
-// vu_temporal_median_u8: exact per-element median over n frames, built from
-// streaming 256-bin histograms in shared memory.  One warp owns a segment of
+// vu_temporal_median_u8: exact per-element median over n frames.
+//
+// n <= 608: register-resident bit-wise binary search on the median value.  A
+// warp owns a 64-byte (SPLIT=2) or 32-byte (SPLIT=4) segment of every frame;
+// each lane loads its 4 bytes of up to 152 frames straight into registers (one
+// coalesced LDG.32 per frame, all of them in flight at once), transposes 4x4
+// byte blocks with PRMT so that a register holds 4 frames of ONE element, and
+// then resolves the 8 bits of the median MSB-first.  The counting primitive is
+// VABSDIFF4 with accumulate: S(m) = sum_f |x_f - m| costs one instruction per
+// 4 frames, and count(x <= m) = (S(m+1) - S(m) + N) / 2.  Frames are split over
+// half / quarter warps and the partial sums meet in a shuffle.  Unused slots are
+// padded with 255, which no probe (<= 254) ever counts.  For even n both middle
+// order statistics are searched; the second search only costs extra from the
+// round where some lane's two searches part.
+//
+// n > 608: streaming 256-bin histograms in shared memory.  One warp owns a segment of
 // 32*PX consecutive bytes of every frame; lane l owns PX of them and a private
 // column of 256 packed counters laid out so that its bank is always `lane`
 // (bin stride = WARPS*128 bytes): every increment is a conflict-free shared
 // atomic, whatever the pixel values are.  Warps never synchronise with each
 // other, so one warp's histogram scan overlaps the other warps' streaming.
-//   n <= 255   : four 8-bit counters per word  (PX = 4, 128-byte segments)
-//   n <= 65535 : two 16-bit counters per word  (PX = 2,  64-byte segments)
+// Two 16-bit counters per word (PX = 2, 64-byte segments), n <= 65535.
 // The median is read back with a two-level scan (16 coarse groups, then 16
 // bins); even n returns (lo + hi) >> 1 like np.median(...).astype(uint8).
 //
@@ -24,16 +37,6 @@ constexpr int MTHREADS = WARPS * 32;
 constexpr int BIN_STRIDE = WARPS * 128;  // bytes between bins
 constexpr int HIST_BYTES = 256 * BIN_STRIDE;
 
-struct PolU8x4 {
-  static constexpr int PX = 4;
-  __device__ static __forceinline__ void add(unsigned char* base, unsigned w) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) atomicAdd(reinterpret_cast<unsigned*>(base + ((w >> (8 * j)) & 0xFFu) * BIN_STRIDE), 1u << (8 * j));
-  }
-  __device__ static __forceinline__ void unpack(unsigned w, unsigned* c) {
-    c[0] = w & 255u; c[1] = (w >> 8) & 255u; c[2] = (w >> 16) & 255u; c[3] = w >> 24;
-  }
-};
 struct PolU16x2 {
   static constexpr int PX = 2;
   __device__ static __forceinline__ void add(unsigned char* base, unsigned w) {
@@ -138,6 +141,104 @@ __global__ void __launch_bounds__(MTHREADS, 1) median_kernel(const uint8_t* __re
   }
 }
 
+// ---- register-resident SAD search ------------------------------------------
+__device__ __forceinline__ unsigned sad_acc(unsigned a, unsigned b, unsigned c) {
+  unsigned d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <int SPLIT, int G, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
+                                                               int nseg) {
+  constexpr int LPS = 32 / SPLIT;  // lanes per frame-part
+  constexpr int SEG = LPS * 4;     // bytes of a frame one warp owns
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane / LPS, li = lane % LPS;
+  const int seg = blockIdx.x * 4 + warp;
+  if (seg >= nseg) return;
+  const int base_cnt = n / SPLIT, rem = n % SPLIT;
+  const int f_cnt = base_cnt + (part < rem ? 1 : 0);
+  const int f_begin = part * base_cnt + min(part, rem);
+  const uint8_t* p = frames + (long long)seg * SEG + li * 4 + (long long)f_begin * m;
+  unsigned d[4 * G];
+#pragma unroll
+  for (int k = 0; k < 4 * G; ++k) {
+    d[k] = (k < f_cnt) ? __ldg(reinterpret_cast<const unsigned*>(p)) : 0xFFFFFFFFu;
+    p += m;
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const unsigned a = d[4 * g], b = d[4 * g + 1], c = d[4 * g + 2], e = d[4 * g + 3];
+    const unsigned ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);
+    const unsigned ce_lo = __byte_perm(c, e, 0x5140), ce_hi = __byte_perm(c, e, 0x7362);
+    d[4 * g] = __byte_perm(ab_lo, ce_lo, 0x5410);
+    d[4 * g + 1] = __byte_perm(ab_lo, ce_lo, 0x7632);
+    d[4 * g + 2] = __byte_perm(ab_hi, ce_hi, 0x5410);
+    d[4 * g + 3] = __byte_perm(ab_hi, ce_hi, 0x7632);
+  }
+  constexpr int ntot = SPLIT * 4 * G;  // slots per element, pads are 255
+  const int ta = ((n - 1) >> 1) + 1, tb = (n >> 1) + 1;
+  unsigned ma[4] = {0, 0, 0, 0}, mb[4] = {0, 0, 0, 0};
+  bool diverged = false;
+  auto count_le = [&](const unsigned(&mm)[4], unsigned step, int(&cnt)[4]) {
+    unsigned s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, q0[4], q1[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q0[j] = (mm[j] + step - 1) * 0x01010101u;
+      q1[j] = q0[j] + 0x01010101u;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s0[j] = sad_acc(d[4 * g + j], q0[j], s0[j]);
+        s1[j] = sad_acc(d[4 * g + j], q1[j], s1[j]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int ds = (int)s1[j] - (int)s0[j];
+#pragma unroll
+      for (int o = LPS; o < 32; o <<= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      cnt[j] = (ds + ntot) >> 1;
+    }
+  };
+#pragma unroll 1
+  for (int bit = 7; bit >= 0; --bit) {
+    const unsigned step = 1u << bit;
+    int ca[4], cb[4];
+    count_le(ma, step, ca);
+    if (diverged) {
+      count_le(mb, step, cb);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cb[j] = ca[j];
+    }
+    bool dv = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (ca[j] < ta) ma[j] += step;
+      if (cb[j] < tb) mb[j] += step;
+      dv |= (ma[j] != mb[j]);
+    }
+    diverged = __any_sync(0xffffffffu, dv);
+  }
+  if (part == 0) {
+    unsigned res = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) res |= ((ma[j] + mb[j]) >> 1) << (8 * j);
+    reinterpret_cast<unsigned*>(out + (long long)seg * SEG)[li] = res;
+  }
+}
+
+template <int SPLIT, int G, int CTAS>
+int launch_median_sad(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream) {
+  median_sad_kernel<SPLIT, G, CTAS><<<(unsigned)((nseg + 3) / 4), 128, 0, S(stream)>>>(frames, out, n, m, (int)nseg);
+  note_launch();
+  return record_cuda(cudaGetLastError());
+}
+
 // elements that do not fill a whole segment (and unaligned inputs): one CTA
 // per element, 256-bin shared histogram
 __global__ void __launch_bounds__(256) median_tail_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
@@ -239,15 +340,27 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
   VU_REQUIRE(frames && out && m >= 0);
   if (n < 1 || n > 65535) return VU_ERR_UNSUPPORTED;
   if (m == 0) return VU_OK;
-  const bool small = n <= 255;
-  const int seg = small ? 128 : 64;
-  const int align = small ? 4 : 2;
-  // vector path needs element-aligned frame rows
+  // path: 0 = SAD search, half-warp split (n <= 304); 1 = SAD search, quarter-warp split (n <= 608);
+  //       2 = shared-memory histograms with 16-bit counters
+  const int path = n <= 304 ? 0 : (n <= 608 ? 1 : 2);
+  const int seg = path == 0 ? 64 : (path == 1 ? 32 : 64);
+  const int align = path == 2 ? 2 : 4;
+  // vector paths need element-aligned frame rows
   const bool ok = (reinterpret_cast<uintptr_t>(frames) % align == 0) && (reinterpret_cast<uintptr_t>(out) % align == 0) && (m % align == 0);
   int64_t nseg = ok ? m / seg : 0;
   if (nseg > 0x7fffffff) return VU_ERR_UNSUPPORTED;
   if (nseg > 0) {
-    int e = small ? launch_median<PolU8x4, 32>(frames, n, m, nseg, out, stream) : launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
+    int e;
+    // G = register groups of 4 frames per lane: the smallest variant that holds ceil(n / SPLIT) frames
+    if (path == 0) {
+      if (n <= 80) e = launch_median_sad<2, 10, 4>(frames, n, m, nseg, out, stream);
+      else if (n <= 152) e = launch_median_sad<2, 19, 4>(frames, n, m, nseg, out, stream);
+      else if (n <= 232) e = launch_median_sad<2, 29, 2>(frames, n, m, nseg, out, stream);
+      else e = launch_median_sad<2, 38, 2>(frames, n, m, nseg, out, stream);
+    } else if (path == 1) {
+      e = n <= 464 ? launch_median_sad<4, 29, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<4, 38, 2>(frames, n, m, nseg, out, stream);
+    }
+    else e = launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
     if (e) return e;
   }
   const int64_t first = nseg * seg;
