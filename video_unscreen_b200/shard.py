@@ -1,0 +1,70 @@
+"""Partitioning of the hot path across the GPUs of one box.
+
+No data-path collective is needed: per-frame stages shard by contiguous frame
+range (mirroring the reference's ``--range a-b``, tools/unscreen/green.py:147),
+temporal reducers shard by row tile because every pixel is independent.  The
+functions here are pure host-side arithmetic plus an optional gather of result
+tiles through ``torch.distributed`` (off the hot path, once per clip).
+"""
+
+
+def frame_ranges(n_frames, world, align=1):
+    """contiguous [start, stop) per rank; interior boundaries are multiples of
+    ``align`` (use the colour-filter refit cadence, 30, so every shard starts on
+    a refit frame -- green.py:88)."""
+    if world < 1 or n_frames < 0 or align < 1:
+        raise ValueError("bad arguments")
+    units = -(-n_frames // align)  # ceil
+    out, start = [], 0
+    for r in range(world):
+        u = units // world + (1 if r < units % world else 0)
+        stop = min(n_frames, start + u * align)
+        out.append((start, stop))
+        start = stop
+    return out
+
+
+def row_tiles(height, world, halo=0):
+    """[(row_start, row_stop, halo_top, halo_bottom)] per rank.  ``halo`` rows
+    of neighbouring tiles are needed when a tile is later pushed through the
+    stencil stages without gathering (dilate(4,2) reaches -4..+2 rows, the
+    r=5 trimap at 1/4 scale ~20 rows + bilinear taps: 24 covers both)."""
+    if world < 1 or height < 0 or halo < 0:
+        raise ValueError("bad arguments")
+    out, start = [], 0
+    for r in range(world):
+        rows = height // world + (1 if r < height % world else 0)
+        stop = start + rows
+        out.append((start, stop, min(halo, start), min(halo, height - stop)))
+        start = stop
+    return out
+
+
+def my_frame_range(n_frames, rank, world, align=1):
+    return frame_ranges(n_frames, world, align)[rank]
+
+
+def my_row_tile(height, rank, world, halo=0):
+    return row_tiles(height, world, halo)[rank]
+
+
+def reduce_rows_sharded(frames, fn, rank, world, gather=False):
+    """temporal reduction of frames[N,H,W,C] over this rank's row tile with
+    ``fn(frames_tile) -> [rows,W,C]``; optionally assemble the full result on
+    every rank with one all_gather (not on the hot path)."""
+    h = frames.shape[1]
+    r0, r1, _, _ = my_row_tile(h, rank, world)
+    tile = fn(frames[:, r0:r1])
+    if not gather or world == 1:
+        return tile, (r0, r1)
+    import torch
+    import torch.distributed as dist
+    t = tile if isinstance(tile, torch.Tensor) else torch.from_numpy(tile)
+    sizes = [b - a for a, b, _, _ in row_tiles(h, world)]
+    pad = max(sizes)
+    buf = torch.zeros((pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    buf[: t.shape[0]] = t
+    parts = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(parts, buf)
+    full = torch.cat([p[:s] for p, s in zip(parts, sizes)], 0)
+    return (full if isinstance(tile, torch.Tensor) else full.numpy()), (0, h)
