@@ -262,6 +262,16 @@ def test_temporal_median_vs_oracle(vu, n):
     const = np.full((n, h, w, 3), 7, np.uint8)
     const[: n // 3] = 200
     assert np.array_equal(vu.U.temporal_median(const), R.temporal_median(const))
+    # two-valued data: for even n the two middle order statistics can be 0 and 255 (longest possible plateau)
+    rng = np.random.default_rng(n)
+    two = np.where(rng.integers(0, 2, (n, h, w, 3)) > 0, 255, 0).astype(np.uint8)
+    two[:, 0] = 0
+    two[: n // 2, 0] = 255          # exact half split on row 0
+    two[:, 1] = np.where(np.arange(n)[:, None, None] % 2 == 0, 3, 250)
+    assert np.array_equal(vu.U.temporal_median(two), R.temporal_median(two))
+    # sparse values with gaps of every size
+    gaps = (rng.integers(0, 4, (n, h, w, 3)) * rng.integers(1, 80, (1, h, w, 3))).astype(np.uint8)
+    assert np.array_equal(vu.U.temporal_median(gaps), R.temporal_median(gaps))
 
 
 def test_temporal_median_properties_full_size(vu):

@@ -7,13 +7,12 @@
 // each lane loads its 4 bytes of up to 152 frames straight into registers (one
 // coalesced LDG.32 per frame, all of them in flight at once), transposes 4x4
 // byte blocks with PRMT so that a register holds 4 frames of ONE element, and
-// then resolves the 8 bits of the median MSB-first.  The counting primitive is
-// VABSDIFF4 with accumulate: S(m) = sum_f |x_f - m| costs one instruction per
-// 4 frames, and count(x <= m) = (S(m+1) - S(m) + N) / 2.  Frames are split over
-// half / quarter warps and the partial sums meet in a shuffle.  Unused slots are
-// padded with 255, which no probe (<= 254) ever counts.  For even n both middle
-// order statistics are searched; the second search only costs extra from the
-// round where some lane's two searches part.
+// then minimises the convex S(m) = sum_f |x_f - m| with a Fibonacci search: S
+// costs one VABSDIFF4-with-accumulate per 4 frames per probe, 12 probes find
+// the minimiser among 0..255 (see sad_search).  Frames are split over half /
+// quarter warps and the partial sums meet in a shuffle.  Unused slots are
+// padded with 0 on one side and 255 on the other, which keeps the middle order
+// statistics where they are.
 //
 // n > 608: streaming 256-bin histograms in shared memory.  One warp owns a segment of
 // 32*PX consecutive bytes of every frame; lane l owns PX of them and a private
@@ -148,25 +147,27 @@ __device__ __forceinline__ unsigned sad_acc(unsigned a, unsigned b, unsigned c) 
   return d;
 }
 
-template <int SPLIT, int G, int CTAS>
-__global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
-                                                               int nseg) {
-  constexpr int LPS = 32 / SPLIT;  // lanes per frame-part
-  constexpr int SEG = LPS * 4;     // bytes of a frame one warp owns
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int part = lane / LPS, li = lane % LPS;
-  const int seg = blockIdx.x * 4 + warp;
-  if (seg >= nseg) return;
-  const int base_cnt = n / SPLIT, rem = n % SPLIT;
-  const int f_cnt = base_cnt + (part < rem ? 1 : 0);
-  const int f_begin = part * base_cnt + min(part, rem);
-  const uint8_t* p = frames + (long long)seg * SEG + li * 4 + (long long)f_begin * m;
-  unsigned d[4 * G];
-#pragma unroll
-  for (int k = 0; k < 4 * G; ++k) {
-    d[k] = (k < f_cnt) ? __ldg(reinterpret_cast<const unsigned*>(p)) : 0xFFFFFFFFu;
-    p += m;
+// frames of one element are split over SPLIT lane groups ("parts").  Parts on
+// the low side (part < SPLIT/2) pad their unused slots with 0, parts on the
+// high side with 255, and the surplus frames go to the sides alternately, so
+// the padded multiset keeps the data's middle order statistics.
+template <int SPLIT>
+__device__ __forceinline__ void part_frames(int n, int part, int& f_begin, int& f_cnt) {
+  const int base = n / SPLIT, rem = n % SPLIT;
+  if (SPLIT == 4) {
+    // surplus order: parts 0, 2, 1, 3
+    const int c0 = base + (rem > 0), c1 = base + (rem > 2), c2 = base + (rem > 1), c3 = base;
+    f_cnt = part == 0 ? c0 : (part == 1 ? c1 : (part == 2 ? c2 : c3));
+    f_begin = part == 0 ? 0 : (part == 1 ? c0 : (part == 2 ? c0 + c1 : c0 + c1 + c2));
+  } else {
+    f_cnt = base + (part < rem ? 1 : 0);
+    f_begin = part * base + min(part, rem);
   }
+}
+
+// 4x4 byte transposes: d[4g+j] <- 4 consecutive frame slots of element j
+template <int G>
+__device__ __forceinline__ void transpose_groups(unsigned (&d)[4 * G]) {
 #pragma unroll
   for (int g = 0; g < G; ++g) {
     const unsigned a = d[4 * g], b = d[4 * g + 1], c = d[4 * g + 2], e = d[4 * g + 3];
@@ -177,198 +178,209 @@ __global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __
     d[4 * g + 2] = __byte_perm(ab_hi, ce_hi, 0x5410);
     d[4 * g + 3] = __byte_perm(ab_hi, ce_hi, 0x7632);
   }
-  constexpr int ntot = SPLIT * 4 * G;  // slots per element, pads are 255
-  const int ta = ((n - 1) >> 1) + 1, tb = (n >> 1) + 1;
-  unsigned ma[4] = {0, 0, 0, 0}, mb[4] = {0, 0, 0, 0};
-  bool diverged = false;
-  auto count_le = [&](const unsigned(&mm)[4], unsigned step, int(&cnt)[4]) {
-    unsigned s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, q0[4], q1[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      q0[j] = (mm[j] + step - 1) * 0x01010101u;
-      q1[j] = q0[j] + 0x01010101u;
-    }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        s0[j] = sad_acc(d[4 * g + j], q0[j], s0[j]);
-        s1[j] = sad_acc(d[4 * g + j], q1[j], s1[j]);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int ds = (int)s1[j] - (int)s0[j];
-#pragma unroll
-      for (int o = LPS; o < 32; o <<= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
-      cnt[j] = (ds + ntot) >> 1;
-    }
-  };
-#pragma unroll 1
-  for (int bit = 7; bit >= 0; --bit) {
-    const unsigned step = 1u << bit;
-    int ca[4], cb[4];
-    count_le(ma, step, ca);
-    if (diverged) {
-      count_le(mb, step, cb);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) cb[j] = ca[j];
-    }
-    bool dv = false;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (ca[j] < ta) ma[j] += step;
-      if (cb[j] < tb) mb[j] += step;
-      dv |= (ma[j] != mb[j]);
-    }
-    diverged = __any_sync(0xffffffffu, dv);
-  }
-  if (part == 0) {
-    unsigned res = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) res |= ((ma[j] + mb[j]) >> 1) << (8 * j);
-    reinterpret_cast<unsigned*>(out + (long long)seg * SEG)[li] = res;
-  }
 }
 
-// Persistent variant for the half-warp split: every warp walks segments with a
-// grid stride and, while it searches segment i in registers, the next
-// segment's rows (64 bytes of each of its <= 8G frames) stream into a private
-// shared-memory buffer with cp.async.  The register fill is then conflict-free
-// LDS instead of a dependent-latency global load phase.
-constexpr int PF_WARPS = 4;
-template <int G>
-struct PfLayout {
-  static constexpr int FT = 4 * G;              // frame slots per half
-  static constexpr int HALF_STRIDE = FT * 64 + 64;  // +64 B: the two halves land on different banks
-  static constexpr int WARP_BYTES = 2 * HALF_STRIDE;
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-template <int G, int CTAS>
-__global__ void __launch_bounds__(PF_WARPS * 32, CTAS) median_sad_pf_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n,
-                                                                             long long m, int nseg) {
-  using L = PfLayout<G>;
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned char* buf = smem + warp * L::WARP_BYTES;
-  const int part = lane >> 4, li = lane & 15;
-  const int n0 = (n + 1) >> 1;                   // frames of half 0; half 1 has n - n0
-  // pads (slots past a half's frame count) hold 255 for the whole kernel
-  for (int i = lane; i < L::WARP_BYTES / 4; i += 32) reinterpret_cast<unsigned*>(buf)[i] = 0xFFFFFFFFu;
-  __syncwarp();
-  const int total_warps = gridDim.x * PF_WARPS;
-  int seg = blockIdx.x * PF_WARPS + warp;
-  // lane -> (frame lane>>2 of every group of 8, 16-byte chunk lane&3)
-  auto prefetch = [&](int sg) {
-    const uint8_t* src = frames + (long long)sg * 64 + (lane & 3) * 16 + (long long)(lane >> 2) * m;
-    for (int f = lane >> 2; f < n; f += 8) {
-      const int slot_off = f < n0 ? f * 64 : L::HALF_STRIDE + (f - n0) * 64;
-      cp_async16(buf + slot_off + (lane & 3) * 16, src);
-      src += 8 * m;
+// The median minimises the convex S(m) = sum_f |x_f - m| (one VABSDIFF4.ACC per
+// 4 frames per probe).  Fibonacci search over m = 0..255 needs 12 evaluations
+// of S per element (each round re-uses one of its two probes).  For odd n one
+// high-side pad "floats" (it is overwritten with the probe itself and so adds
+// nothing): the minimiser is unique and is the median.  For even n the
+// minimisers form the plateau [x_lo, x_hi] of the two middle order statistics;
+// its ends are found by probing outwards (S(m) == S_min is monotone on either
+// side), a few linear steps first, binary search for pathological plateaus.
+template <int SPLIT, int G>
+__device__ __forceinline__ unsigned sad_search(const unsigned (&d)[4 * G], int n, int part) {
+  constexpr int LPS = 32 / SPLIT;
+  constexpr unsigned INF = 0x7fffffffu;
+  constexpr unsigned FULL = 0xffffffffu;
+  const unsigned fmask = ((n & 1) && part == SPLIT - 1) ? 0xFF000000u : 0u;
+  // idx = m + 1 (the search runs on indices 1..376; m > 255 evaluates to +inf)
+  auto evalS = [&](const int(&idx)[4], unsigned(&S)[4]) {
+    unsigned q[4], s[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j] = (unsigned)min(max(idx[j] - 1, 0), 255) * 0x01010101u;
+      s[j] = 0;
+    }
+#pragma unroll
+    for (int g = 0; g < G - 1; ++g) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[j] = sad_acc(d[4 * g + j], q[j], s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const unsigned w = (d[4 * (G - 1) + j] & ~fmask) | (q[j] & fmask);
+      s[j] = sad_acc(w, q[j], s[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = LPS; o < 32; o <<= 1) s[j] += __shfl_xor_sync(FULL, s[j], o);
+      S[j] = (idx[j] < 1 || idx[j] > 256) ? INF : s[j];
     }
   };
-  if (seg < nseg) prefetch(seg);
-  constexpr int ntot = 2 * 4 * G;
-  const int ta = ((n - 1) >> 1) + 1, tb = (n >> 1) + 1;
-  for (; seg < nseg; seg += total_warps) {
-    cp_async_wait_all();
-    __syncwarp();
-    unsigned d[4 * G];
-    const unsigned* rd = reinterpret_cast<const unsigned*>(buf + part * L::HALF_STRIDE) + li;
+  int a[4] = {0, 0, 0, 0};
+  unsigned S1[4], S2[4];
+  int fa = 233, fb = 144, fc = 89;  // F(k-1), F(k-2), F(k-3) for k = 14
+  {
+    int i1[4], i2[4];
 #pragma unroll
-    for (int k = 0; k < 4 * G; ++k) d[k] = rd[k * 16];
-    __syncwarp();
-    if (seg + total_warps < nseg) prefetch(seg + total_warps);
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const unsigned a = d[4 * g], b = d[4 * g + 1], c = d[4 * g + 2], e = d[4 * g + 3];
-      const unsigned ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);
-      const unsigned ce_lo = __byte_perm(c, e, 0x5140), ce_hi = __byte_perm(c, e, 0x7362);
-      d[4 * g] = __byte_perm(ab_lo, ce_lo, 0x5410);
-      d[4 * g + 1] = __byte_perm(ab_lo, ce_lo, 0x7632);
-      d[4 * g + 2] = __byte_perm(ab_hi, ce_hi, 0x5410);
-      d[4 * g + 3] = __byte_perm(ab_hi, ce_hi, 0x7632);
-    }
-    unsigned ma[4] = {0, 0, 0, 0}, mb[4] = {0, 0, 0, 0};
-    bool diverged = false;
-    auto count_le = [&](const unsigned(&mm)[4], unsigned step, int(&cnt)[4]) {
-      unsigned s0[4] = {0, 0, 0, 0}, s1[4] = {0, 0, 0, 0}, q0[4], q1[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        q0[j] = (mm[j] + step - 1) * 0x01010101u;
-        q1[j] = q0[j] + 0x01010101u;
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          s0[j] = sad_acc(d[4 * g + j], q0[j], s0[j]);
-          s1[j] = sad_acc(d[4 * g + j], q1[j], s1[j]);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        int ds = (int)s1[j] - (int)s0[j];
-        ds += __shfl_xor_sync(0xffffffffu, ds, 16);
-        cnt[j] = (ds + ntot) >> 1;
-      }
-    };
+    for (int j = 0; j < 4; ++j) { i1[j] = fb; i2[j] = fa; }
+    evalS(i1, S1);
+    evalS(i2, S2);
+  }
 #pragma unroll 1
-    for (int bit = 7; bit >= 0; --bit) {
-      const unsigned step = 1u << bit;
-      int ca[4], cb[4];
-      count_le(ma, step, ca);
-      if (diverged) {
-        count_le(mb, step, cb);
+  for (int k = 14; k >= 5; --k) {
+    int nidx[4];
+    bool left[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      left[j] = S1[j] <= S2[j];
+      if (left[j]) {
+        S2[j] = S1[j];
+        nidx[j] = a[j] + fc;
       } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) cb[j] = ca[j];
+        a[j] += fb;
+        S1[j] = S2[j];
+        nidx[j] = a[j] + fb;
       }
-      bool dv = false;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (ca[j] < ta) ma[j] += step;
-        if (cb[j] < tb) mb[j] += step;
-        dv |= (ma[j] != mb[j]);
-      }
-      diverged = __any_sync(0xffffffffu, dv);
     }
-    if (part == 0) {
-      unsigned res = 0;
+    unsigned Sn[4];
+    evalS(nidx, Sn);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) res |= ((ma[j] + mb[j]) >> 1) << (8 * j);
-      reinterpret_cast<unsigned*>(out + (long long)seg * 64)[li] = res;
+    for (int j = 0; j < 4; ++j) {
+      if (left[j]) S1[j] = Sn[j];
+      else S2[j] = Sn[j];
+    }
+    const int t = fb - fc;
+    fa = fb; fb = fc; fc = t;
+  }
+  int lo[4], hi[4];
+  unsigned Smin[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool left = S1[j] <= S2[j];
+    lo[j] = hi[j] = (left ? a[j] + fb : a[j] + fa) - 1;
+    Smin[j] = left ? S1[j] : S2[j];
+  }
+  if (!(n & 1)) {
+    bool actL[4], actR[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { actL[j] = lo[j] > 0; actR[j] = hi[j] < 255; }
+#pragma unroll 1
+    for (int it = 0; it < 3; ++it) {
+      const bool anyL = actL[0] | actL[1] | actL[2] | actL[3];
+      if (__any_sync(FULL, anyL)) {
+        int idx[4];
+        unsigned S[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = lo[j];  // m = lo - 1
+        evalS(idx, S);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (actL[j]) {
+            if (S[j] == Smin[j]) { --lo[j]; actL[j] = lo[j] > 0; }
+            else actL[j] = false;
+          }
+      }
+      const bool anyR = actR[0] | actR[1] | actR[2] | actR[3];
+      if (__any_sync(FULL, anyR)) {
+        int idx[4];
+        unsigned S[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = hi[j] + 2;  // m = hi + 1
+        evalS(idx, S);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (actR[j]) {
+            if (S[j] == Smin[j]) { ++hi[j]; actR[j] = hi[j] < 255; }
+            else actR[j] = false;
+          }
+      }
+    }
+    // plateaus longer than 3 on a side (e.g. two-valued data): binary search for the end
+    if (__any_sync(FULL, actL[0] | actL[1] | actL[2] | actL[3])) {
+      int L[4], R[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { R[j] = lo[j]; L[j] = actL[j] ? 0 : lo[j]; }
+      while (__any_sync(FULL, (L[0] < R[0]) | (L[1] < R[1]) | (L[2] < R[2]) | (L[3] < R[3]))) {
+        int idx[4];
+        unsigned S[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = ((L[j] + R[j]) >> 1) + 1;
+        evalS(idx, S);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (L[j] < R[j]) {
+            const int mid = (L[j] + R[j]) >> 1;
+            if (S[j] == Smin[j]) R[j] = mid;
+            else L[j] = mid + 1;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lo[j] = R[j];
+    }
+    if (__any_sync(FULL, actR[0] | actR[1] | actR[2] | actR[3])) {
+      int L[4], R[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { L[j] = hi[j]; R[j] = actR[j] ? 255 : hi[j]; }
+      while (__any_sync(FULL, (L[0] < R[0]) | (L[1] < R[1]) | (L[2] < R[2]) | (L[3] < R[3]))) {
+        int idx[4];
+        unsigned S[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = ((L[j] + R[j] + 1) >> 1) + 1;
+        evalS(idx, S);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (L[j] < R[j]) {
+            const int mid = (L[j] + R[j] + 1) >> 1;
+            if (S[j] == Smin[j]) L[j] = mid;
+            else R[j] = mid - 1;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hi[j] = L[j];
     }
   }
+  unsigned res = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) res |= (unsigned)((lo[j] + hi[j]) >> 1) << (8 * j);
+  return res;
 }
 
-template <int G, int CTAS>
-int launch_median_sad_pf(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream) {
-  constexpr int smem = PF_WARPS * PfLayout<G>::WARP_BYTES;
-  static bool configured = false;
-  if (!configured) {
-    int e = record_cuda(cudaFuncSetAttribute(median_sad_pf_kernel<G, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    if (e) return e;
-    configured = true;
+// GMIN = register groups that are full for every n the variant is dispatched for (no bounds test on those loads)
+template <int SPLIT, int G, int GMIN, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
+                                                               int nseg) {
+  constexpr int LPS = 32 / SPLIT;  // lanes per frame-part
+  constexpr int SEG = LPS * 4;     // bytes of a frame one warp owns
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane / LPS, li = lane % LPS;
+  const int seg = blockIdx.x * 4 + warp;
+  if (seg >= nseg) return;
+  int f_begin, f_cnt;
+  part_frames<SPLIT>(n, part, f_begin, f_cnt);
+  const unsigned pad = part >= SPLIT / 2 ? 0xFFFFFFFFu : 0u;
+  const uint8_t* p = frames + (long long)seg * SEG + li * 4 + (long long)f_begin * m;
+  unsigned d[4 * G];
+#pragma unroll
+  for (int k = 0; k < 4 * GMIN; ++k) {
+    d[k] = __ldg(reinterpret_cast<const unsigned*>(p));
+    p += m;
   }
-  int64_t grid = (int64_t)device_sms() * CTAS;
-  const int64_t need = (nseg + PF_WARPS - 1) / PF_WARPS;
-  if (need < grid) grid = need;
-  median_sad_pf_kernel<G, CTAS><<<(unsigned)grid, PF_WARPS * 32, smem, S(stream)>>>(frames, out, n, m, (int)nseg);
-  note_launch();
-  return record_cuda(cudaGetLastError());
+#pragma unroll
+  for (int k = 4 * GMIN; k < 4 * G; ++k) {
+    d[k] = (k < f_cnt) ? __ldg(reinterpret_cast<const unsigned*>(p)) : pad;
+    p += m;
+  }
+  transpose_groups<G>(d);
+  const unsigned res = sad_search<SPLIT, G>(d, n, part);
+  if (part == 0) reinterpret_cast<unsigned*>(out + (long long)seg * SEG)[li] = res;
 }
 
-template <int SPLIT, int G, int CTAS>
+template <int SPLIT, int G, int GMIN, int CTAS>
 int launch_median_sad(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream) {
-  median_sad_kernel<SPLIT, G, CTAS><<<(unsigned)((nseg + 3) / 4), 128, 0, S(stream)>>>(frames, out, n, m, (int)nseg);
+  median_sad_kernel<SPLIT, G, GMIN, CTAS><<<(unsigned)((nseg + 3) / 4), 128, 0, S(stream)>>>(frames, out, n, m, (int)nseg);
   note_launch();
   return record_cuda(cudaGetLastError());
 }
@@ -485,20 +497,15 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
   if (nseg > 0x7fffffff) return VU_ERR_UNSUPPORTED;
   if (nseg > 0) {
     int e;
-    // G = register groups of 4 frames per lane: the smallest variant that holds ceil(n / SPLIT) frames
+    // G = register groups of 4 frames per lane: the smallest variant that holds ceil(n / SPLIT) frames;
+    // GMIN = groups every lane fills for the whole n-range of the variant
     if (path == 0) {
-      if (n <= 80) e = launch_median_sad<2, 10, 4>(frames, n, m, nseg, out, stream);
-      else if (n <= 152) e = launch_median_sad<2, 19, 4>(frames, n, m, nseg, out, stream);
-      else {
-        // cp.async moves 16-byte chunks: needs 16-byte aligned frame rows
-        // (measured on B200, 300x1080p: the prefetching variant wins when both middle order statistics are
-        // searched (even n: 0.81 vs 0.86 ms) and loses slightly when not (odd n: 0.72 vs 0.69 ms))
-        const bool pf = (n % 2 == 0) && (reinterpret_cast<uintptr_t>(frames) % 16 == 0) && (m % 16 == 0);
-        if (n <= 232) e = pf ? launch_median_sad_pf<29, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<2, 29, 2>(frames, n, m, nseg, out, stream);
-        else e = pf ? launch_median_sad_pf<38, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<2, 38, 2>(frames, n, m, nseg, out, stream);
-      }
+      if (n <= 80) e = launch_median_sad<2, 10, 0, 4>(frames, n, m, nseg, out, stream);
+      else if (n <= 152) e = launch_median_sad<2, 19, 10, 4>(frames, n, m, nseg, out, stream);
+      else if (n <= 232) e = launch_median_sad<2, 29, 19, 2>(frames, n, m, nseg, out, stream);
+      else e = launch_median_sad<2, 38, 29, 2>(frames, n, m, nseg, out, stream);
     } else if (path == 1) {
-      e = n <= 464 ? launch_median_sad<4, 29, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<4, 38, 2>(frames, n, m, nseg, out, stream);
+      e = n <= 464 ? launch_median_sad<4, 29, 19, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<4, 38, 29, 2>(frames, n, m, nseg, out, stream);
     }
     else e = launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
     if (e) return e;
