@@ -116,6 +116,20 @@ int vu_trimap_classify(const uint8_t* dilated, const uint8_t* eroded, uint8_t* o
 /* trimap/agent.py:60: values strictly between 0 and 255 become 128 */
 int vu_trimap_snap(const uint8_t* a, int64_t count, uint8_t* out, vu_stream_t stream);
 
+/* per-frame branches taken on the device (batched clips, no host round trip):
+ * flags[i] = 2 if counts2[i][1] == 0 (trimap/agent.py:88: mask returned as is),
+ * 1 if float(counts2[i][0]) / counts2[i][1] > thr (:94: trust the mask), else 0 */
+int vu_ratio_flags(const uint64_t* counts2, int n, double thr, uint8_t* flags, vu_stream_t stream);
+/* colorfiltering/agent.py:303-307: flags[i] = 1 if nfg[i] < fg_min, 2 if nbg[i] < bg_min, else 0 */
+int vu_cf_degenerate_flags(const uint64_t* nfg, const uint64_t* nbg, int n, uint64_t fg_min, uint64_t bg_min,
+                           uint8_t* flags, vu_stream_t stream);
+/* out[i] = flags[i] ? a[i] : b[i] for whole frames of per_item bytes */
+int vu_select_frames(const uint8_t* a, const uint8_t* b, const uint8_t* flags, int n, int64_t per_item,
+                     uint8_t* out, vu_stream_t stream);
+/* out = 128 where flags[i] == 0 && b != 0, else a (trimap/agent.py:100 on the ensemble branch only) */
+int vu_set128_unflagged(const uint8_t* a, const uint8_t* b, const uint8_t* flags, int n, int64_t per_item,
+                        uint8_t* out, vu_stream_t stream);
+
 /* ---- colour filtering: ColorFilteringAgent, colorfiltering/agent.py ----- */
 /* get_alpha_by_gmm (:232-257) with the six 1-D mixtures folded into 256-entry
  * float32 tables (luts = [bg H,S,V, fg H,S,V][256], DEVICE): per pixel

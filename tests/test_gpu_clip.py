@@ -1,0 +1,97 @@
+"""Batched clip pipelines == the per-frame agents, frame by frame (which are
+themselves checked against the reference goldens in test_gpu_parity.py), and
+against the oracle on the same seeded clips."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+from oracle import refport as R  # noqa: E402
+from video_unscreen_b200 import synth  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def env(golden):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from test_oracle_golden import cf_tables
+    from video_unscreen_b200 import clip, ops
+    from video_unscreen_b200.unscreen.colorfiltering import ColorFilteringAgent
+    from video_unscreen_b200.unscreen.trimap import TrimapAgent
+    c = golden("colorfilter")
+
+    class E:
+        pass
+    e = E()
+    e.clip, e.ops, e.CF, e.TA = clip, ops, ColorFilteringAgent, TrimapAgent
+    e.tables = {tag: cf_tables(c, tag) for tag in ("x2", "x4")}
+    return e
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.mark.parametrize("tag,h,w,L", [("x2", 270, 480, 240), ("x4", 360, 640, 160)])
+def test_green_clip_matches_agents_and_oracle(env, tag, h, w, L):
+    n = 7
+    frames, segs = synth.green_clip(n, h, w, seed=5)
+    segs[3] = 0          # degenerate: no foreground -> early-out
+    segs[5] = 255        # degenerate: no background
+    lb, lf, bgh = env.tables[tag]
+    cf = env.CF(input_long_side=L)
+    cf.set_tables(lb, lf, bgh)
+    ta = env.TA(input_long_side=L)
+    alpha, tri, fg, bgo = env.clip.green_clip(dev(frames), dev(segs), cf, ta, chunk=3)
+    alpha, tri, fg, bgo = (t.cpu().numpy() for t in (alpha, tri, fg, bgo))
+    bg_color = cf.bg_color_bgr()
+    for i in range(n):
+        a_i, bgimg_i, _ = cf.forward(frames[i], segs[i], 0)
+        assert np.array_equal(alpha[i], a_i), i
+        assert np.array_equal(tri[i], ta.forward(a_i, frames[i], bg_color)), i
+        # oracle, end to end
+        a_o, _, _ = R.cf_forward_predict(frames[i], segs[i], lb, lf, bgh, L)
+        assert np.array_equal(alpha[i], a_o), i
+        assert np.array_equal(tri[i], R.generate_trimap_withbg(a_o, frames[i], bg_color, L)), i
+        bg_full = np.broadcast_to(bg_color, frames[i].shape)
+        patched = R.patch_bg(bg_full, frames[i], a_o, "lt128")
+        assert np.array_equal(bgo[i], patched), i
+        assert np.array_equal(fg[i], R.get_fg(frames[i], a_o, patched)), i
+
+
+def test_trimap_clip_variants(env, golden):
+    t = golden("trimap")
+    L = int(t["x2_L"])
+    ta = env.TA(input_long_side=L)
+    masks = np.stack([t["x2_soft"], t["x2_leak"], t["x2_ring"], np.zeros_like(t["x2_mask"]), t["x2_mask"]])
+    frames = np.stack([t["x2_frame"]] * 5)
+    bgcol = np.array([60, 200, 40], np.uint8)
+    got = env.clip.trimap_clip(dev(masks), ta, dev(frames), bgcol, chunk=2).cpu().numpy()
+    want = [t["x2_withcolor"], t["x2_leak_withcolor"], t["x2_ring_withcolor"], np.zeros_like(t["x2_mask"]), None]
+    for i in range(5):
+        ref = want[i] if want[i] is not None else R.generate_trimap_withbg(masks[i], frames[i], bgcol, L)
+        assert np.array_equal(got[i], ref), i
+    got = env.clip.trimap_clip(dev(masks), ta, dev(frames), dev(t["x2_bgimg"]), chunk=5).cpu().numpy()
+    assert np.array_equal(got[0], t["x2_withimage"]) and np.array_equal(got[2], t["x2_ring_withimage"])
+    got = env.clip.trimap_clip(dev(masks), ta).cpu().numpy()
+    assert np.array_equal(got[0], t["x2_plain_soft"]) and np.array_equal(got[4], t["x2_plain"])
+
+
+def test_bgstep_and_replace_clip(env):
+    n, h, w = 12, 96, 160
+    frames, masks, _ = synth.bgstep_clip(n, h, w, seed=4)
+    ta = env.TA(input_long_side=80)
+    bg, alpha, tri, fg = (x.cpu().numpy() for x in env.clip.bgstep_clip(dev(frames), dev(masks), ta, thr=25, chunk=5))
+    bg_o = R.temporal_median(frames)
+    assert np.array_equal(bg, bg_o)
+    for i in range(n):
+        a_o = R.bgdiff_gate(frames[i], bg_o, masks[i], 25)
+        assert np.array_equal(alpha[i], a_o), i
+        assert np.array_equal(tri[i], R.generate_trimap(a_o, 80)), i
+        assert np.array_equal(fg[i], R.get_fg(frames[i], a_o, R.patch_bg(bg_o, frames[i], a_o, "eq0"))), i
+    rng = np.random.default_rng(0)
+    newbg = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    out = env.clip.replace_clip(dev(fg), dev(alpha), dev(newbg)).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(out[i], R.replace_blend(fg[i], alpha[i], newbg)), i

@@ -219,3 +219,78 @@ extern "C" int vu_trimap_snap(const uint8_t* a, int64_t count, uint8_t* out, vu_
   snap_kernel<<<grid_for(count, THREADS * 4, 8), THREADS, 0, S(stream)>>>(a, out, count);
   VU_RETURN_LAUNCH();
 }
+
+// ---- per-frame branches without a host round trip ----------------------------
+namespace vu {
+namespace {
+// flags[i] = 1 when the frame takes the "trust the mask" branch of
+// generate_trimap_withbg (trimap/agent.py:94): float(fuzzy)/pos > thr, or no
+// positive pixel at all (:88, the mask is returned as is)
+__global__ void ratio_flags_kernel(const unsigned long long* counts2, int n, double thr, uint8_t* flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long fz = counts2[2 * i], pos = counts2[2 * i + 1];
+  flags[i] = (pos == 0) ? 2 : ((__ddiv_rn((double)fz, (double)pos) > thr) ? 1 : 0);
+}
+// degenerate-mask early-outs of ColorFilteringAgent.forward (agent.py:303-307):
+// flags[i] = 1 "no foreground" (alpha := mask), 2 "no background" (alpha := mask), else 0
+__global__ void cf_degenerate_flags_kernel(const unsigned long long* nfg, const unsigned long long* nbg, int n, unsigned long long fg_min,
+                                           unsigned long long bg_min, uint8_t* flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  flags[i] = nfg[i] < fg_min ? 1 : (nbg[i] < bg_min ? 2 : 0);
+}
+// out[i][:] = flags[i] ? a[i][:] : b[i][:]
+__global__ void __launch_bounds__(THREADS) select_frames_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                                const uint8_t* __restrict__ flags, int64_t per_item, uint8_t* __restrict__ out) {
+  const int64_t base = (int64_t)blockIdx.y * per_item;
+  const bool fa = flags[blockIdx.y] != 0;
+  const uint8_t* src = fa ? a : b;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_item; i += stride) out[base + i] = __ldg(src + base + i);
+}
+// out = (flags[i] == 0 && b != 0) ? 128 : a    (trimap[fuzzy] = 128 only on the ensemble branch)
+__global__ void __launch_bounds__(THREADS) set128_unflagged_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
+                                                                   const uint8_t* __restrict__ flags, int64_t per_item, uint8_t* __restrict__ out) {
+  const int64_t base = (int64_t)blockIdx.y * per_item;
+  const bool ens = flags[blockIdx.y] == 0;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_item; i += stride) {
+    const int av = __ldg(a + base + i);
+    out[base + i] = (ens && __ldg(b + base + i)) ? 128 : av;
+  }
+}
+}  // namespace
+}  // namespace vu
+
+extern "C" int vu_ratio_flags(const uint64_t* counts2, int n, double thr, uint8_t* flags, vu_stream_t stream) {
+  VU_REQUIRE(counts2 && flags && n >= 0);
+  if (n == 0) return VU_OK;
+  ratio_flags_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(reinterpret_cast<const unsigned long long*>(counts2), n, thr, flags);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_cf_degenerate_flags(const uint64_t* nfg, const uint64_t* nbg, int n, uint64_t fg_min, uint64_t bg_min, uint8_t* flags,
+                                      vu_stream_t stream) {
+  VU_REQUIRE(nfg && nbg && flags && n >= 0);
+  if (n == 0) return VU_OK;
+  cf_degenerate_flags_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(reinterpret_cast<const unsigned long long*>(nfg),
+                                                                       reinterpret_cast<const unsigned long long*>(nbg), n, fg_min, bg_min, flags);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_select_frames(const uint8_t* a, const uint8_t* b, const uint8_t* flags, int n, int64_t per_item, uint8_t* out,
+                                vu_stream_t stream) {
+  VU_REQUIRE(a && b && flags && out && n >= 0 && per_item >= 0);
+  if (n == 0 || per_item == 0) return VU_OK;
+  select_frames_kernel<<<item_grid(n, per_item), THREADS, 0, S(stream)>>>(a, b, flags, per_item, out);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_set128_unflagged(const uint8_t* a, const uint8_t* b, const uint8_t* flags, int n, int64_t per_item, uint8_t* out,
+                                   vu_stream_t stream) {
+  VU_REQUIRE(a && b && flags && out && n >= 0 && per_item >= 0);
+  if (n == 0 || per_item == 0) return VU_OK;
+  set128_unflagged_kernel<<<item_grid(n, per_item), THREADS, 0, S(stream)>>>(a, b, flags, per_item, out);
+  VU_RETURN_LAUNCH();
+}

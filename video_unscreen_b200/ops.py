@@ -321,3 +321,37 @@ def masked_temporal_mean(frames, masks_dilated, min_count=10):
     always = torch.empty((h, w), dtype=u8, device=frames.device)
     check(lib().vu_masked_temporal_mean(_p(frames), _p(masks_dilated), n, h * w, int(min_count), _p(bg), _p(always), _stream()))
     return bg, always
+
+
+# ---- per-frame branches on the device (batched clips) --------------------------------
+
+def ratio_flags(counts2, thr):
+    counts2 = _dev(counts2, torch.int64)
+    n = counts2.shape[0]
+    flags = torch.empty(n, dtype=u8, device=counts2.device)
+    check(lib().vu_ratio_flags(_p(counts2), n, float(thr), _p(flags), _stream()))
+    return flags
+
+
+def cf_degenerate_flags(nfg, nbg, fg_min, bg_min):
+    nfg, nbg = _dev(nfg, torch.int64), _dev(nbg, torch.int64)
+    flags = torch.empty(nfg.shape[0], dtype=u8, device=nfg.device)
+    check(lib().vu_cf_degenerate_flags(_p(nfg), _p(nbg), nfg.shape[0], int(fg_min), int(bg_min), _p(flags), _stream()))
+    return flags
+
+
+def select_frames(a, b, flags):
+    """out[i] = a[i] if flags[i] else b[i] (whole frames)."""
+    a, b, flags = _dev(a), _dev(b), _dev(flags)
+    n = a.shape[0]
+    out = torch.empty_like(a)
+    check(lib().vu_select_frames(_p(a), _p(b), _p(flags), n, a.numel() // n, _p(out), _stream()))
+    return out
+
+
+def set128_unflagged(a, b, flags):
+    a, b, flags = _dev(a), _dev(b), _dev(flags)
+    n = a.shape[0]
+    out = torch.empty_like(a)
+    check(lib().vu_set128_unflagged(_p(a), _p(b), _p(flags), n, a.numel() // n, _p(out), _stream()))
+    return out

@@ -109,6 +109,27 @@ class ColorFilteringAgent():
     def _refresh_tables(self):
         self.set_tables(*self.tables())
 
+    def tables_dev(self):
+        """[6,256] float32 device tensor: bg H,S,V then fg H,S,V mixture tables."""
+        if self._luts_dev is None:
+            self._refresh_tables()
+        return self._luts_dev
+
+    def lut3d_dev(self):
+        """alpha tabulated over every (h<180, s, v) for the current mixtures
+        (built once per fit on the device, 11.8 MB: L2-resident)."""
+        self.tables_dev()
+        if getattr(self, "_lut3d_for", None) is not self._luts_dev:
+            self._lut3d = ops.cf_build_lut3d(self._luts_dev)
+            self._lut3d_for = self._luts_dev
+        return self._lut3d
+
+    def bg_color_bgr(self):
+        """the constant background colour of forward()'s bg_img as a (3,) uint8 BGR array"""
+        self.tables_dev()
+        px = torch.from_numpy(np.tile(self._bg_hsv, (1, 4, 1))).cuda()
+        return ops.hsv2bgr(px)[0, 0].cpu().numpy()
+
     def _sample(self, channel, mask):
         samples = channel[mask].astype(float)
         if len(samples) > self.max_num_samples:
