@@ -319,7 +319,7 @@ def run_gpu_arm(args, wl):
                        "clip_bytes": n * m, "l2": "inputs (1.87 GB at 1080p) larger than the 126 MB L2; no flush needed",
                        "sharding": "one clip (spatial tile set) per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "vu::median_kernel", "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": traffic, "kernel": "vu::median_sad_kernel<2,38,29,2> (VABSDIFF4 Fibonacci search)", "algorithmic_bytes_per_launch": algo_bytes,
                          "launch_ms": kernel_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }

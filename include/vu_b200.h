@@ -83,6 +83,17 @@ size_t vu_morph_workspace_bytes(int n, int h, int w, int ksize, int iters);
 int vu_morph_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int ksize, int iters, int op,
                 void* workspace, size_t workspace_bytes, vu_stream_t stream);
 
+/* chains of 3x3-cross passes (== MORPH_ELLIPSE(3,3) with iterations) run in ONE
+ * kernel in shared memory: up to 4 segments {ops[i], iters[i]}, <= 12 passes in
+ * total, e.g. postprocess' d2,e2,e2,d2 (colorfiltering/agent.py:281-282).  If
+ * stats2 != NULL the adaptive threshold of agent.py:277-280 is applied on load
+ * (stats2[i] = {sum, count} of frame i, see vu_cf_threshold_stats). */
+int vu_cross_chain_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int nseg, const int32_t* ops,
+                      const int32_t* iters, const uint64_t* stats2, double thr_ratio, vu_stream_t stream);
+/* trimap/agent.py:53-58 at working resolution in one kernel:
+ * dst = 0 where dilate^iters(src) < 128, 255 where erode^iters(src) > 127, else 128 */
+int vu_trimap_core_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int iters, vu_stream_t stream);
+
 /* ---- resize: cv2.resize uint8 ------------------------------------------ */
 /* default INTER_LINEAR (exact 2x down-scale == rounded 2x2 mean);
  * colorfiltering/agent.py:315-316,342, trimap/agent.py:59 (the "nearest"

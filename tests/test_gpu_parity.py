@@ -75,6 +75,35 @@ def test_morphology(vu, k, n):
             assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("shape", [(97, 131), (3, 64, 200), (5, 3), (33, 128), (40, 257)])
+def test_cross_chain_and_trimap_core(vu, shape):
+    rng = np.random.default_rng(sum(shape))
+    m = rng.integers(0, 256, shape, dtype=np.uint8)
+    m3 = m if m.ndim == 3 else m[None]
+    D, E = 0, 1
+    for segs in ([(D, 2), (E, 2), (E, 2), (D, 2)], [(E, 3), (D, 1)], [(D, 12)], [(E, 5)], [(D, 0), (E, 4)]):
+        want = []
+        for x in m3:
+            for op, it in segs:
+                x = M.dilate(x, 3, it) if op == D else M.erode(x, 3, it)
+            want.append(x)
+        got = host(vu.ops.cross_chain(dev(m), segs))
+        assert np.array_equal(got.reshape(m3.shape), np.stack(want)), segs
+    for r in (1, 5, 12):
+        want = []
+        for x in m3:
+            dil, ero = M.dilate(x, 3, r), M.erode(x, 3, r)
+            t = np.full(x.shape, 128, np.uint8)
+            t[ero > 127] = 255
+            t[dil < 128] = 0
+            want.append(t)
+        assert np.array_equal(host(vu.ops.trimap_core(dev(m), r)).reshape(m3.shape), np.stack(want)), r
+    # fused threshold-on-load == threshold then chain
+    a = rng.integers(0, 256, m3.shape, dtype=np.uint8)
+    got = host(vu.ops.cf_postprocess(dev(a), dev(m3)))
+    assert np.array_equal(got, np.stack([R.cf_postprocess(x, y) for x, y in zip(a, m3)]))
+
+
 @pytest.mark.parametrize("sh,sw,dh,dw", [(270, 480, 135, 240), (360, 640, 90, 160), (135, 240, 270, 480), (90, 160, 360, 640),
                                          (250, 333, 150, 200), (150, 200, 250, 333), (480, 270, 240, 135), (61, 47, 122, 94), (9, 7, 4, 3)])
 def test_resize(vu, sh, sw, dh, dw):

@@ -1,0 +1,144 @@
+#!/usr/bin/env python
+"""Throughput of the batched clip pipelines for the other BASELINE.json configs
+(config 0 cf+trimap 1080p, config 2 full green pipeline 4K, config 3 person
+replacement 1080p, config 4 bg_step median+trimap+composite 4K), device
+resident, CUDA events, with the oracle port timed on a few frames beside it.
+One JSON line per workload.  bench.py (the driver contract) stays on config 1."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bench  # noqa: E402
+from oracle import refport as R  # noqa: E402
+from video_unscreen_b200 import _lib, clip, ops, synth  # noqa: E402
+from video_unscreen_b200.unscreen.colorfiltering import ColorFilteringAgent  # noqa: E402
+from video_unscreen_b200.unscreen.trimap import TrimapAgent  # noqa: E402
+
+
+def timed(fn, steps, warmup=2):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    L = _lib.lib()
+    l0 = L.vu_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    e1.synchronize()
+    return e0.elapsed_time(e1) / steps, int(L.vu_launch_count() - l0) // steps
+
+
+def green_clip_dev(n, h, w, distinct=6):
+    fr, sg = zip(*[synth.green_frame(h, w, t=t, n=distinct, seed=0) for t in range(distinct)])
+    fr = torch.from_numpy(np.stack(fr)).cuda()
+    sg = torch.from_numpy(np.stack(sg)).cuda()
+    idx = torch.arange(n, device="cuda") % distinct
+    return fr[idx].contiguous(), sg[idx].contiguous(), np.stack(fr.cpu().numpy()), np.stack(sg.cpu().numpy())
+
+
+def fitted_agent(frame, seg):
+    ag = ColorFilteringAgent()
+    np.random.seed(0)
+    ag.forward(frame, seg, 3)
+    return ag
+
+
+def report(name, desc, frames, ms, launches, algo_bytes, cpu_fps, cpu_note, peak):
+    ach = algo_bytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"workload": name, "description": desc, "value": frames / (ms * 1e-3), "unit": "frames/s", "ms_per_step": ms,
+                      "frames_per_step": frames, "gpu_launches_per_step": launches,
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                   "kernel": "whole pipeline (all launches of the step)", "algorithmic_bytes_per_step": algo_bytes},
+                      "cpu_baseline": {"value": cpu_fps, "unit": "frames/s", "cores": bench.host_threads(), "kind": "port", "sample": cpu_note}}),
+          flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    peak, _ = bench.measured_peak()
+    ta = TrimapAgent()
+    want = lambda k: not args.only or k in args.only.split(",")
+
+    if want("cf_trimap_1080p"):
+        n, h, w = 300, 1080, 1920
+        fr, sg, fr_h, sg_h = green_clip_dev(n, h, w)
+        cf = fitted_agent(fr_h[0], sg_h[0])
+        col = cf.bg_color_bgr()
+        alpha = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
+        tri = torch.empty_like(alpha)
+
+        def step():
+            clip.cf_predict_clip(fr, sg, cf, chunk=30, out=alpha)
+            clip.trimap_clip(alpha, ta, fr, col, chunk=30, out=tri)
+        ms, launches = timed(step, args.steps)
+        lb, lf, bgh = cf.tables()
+        t0 = time.perf_counter()
+        a_o, _, _ = R.cf_forward_predict(fr_h[1], sg_h[1], lb, lf, bgh, 960)
+        t_o = R.generate_trimap_withbg(a_o, fr_h[1], col, 960)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(alpha[1].cpu().numpy(), a_o) and np.array_equal(tri[1].cpu().numpy(), t_o)
+        report("cf_trimap_1080p", "BASELINE configs[0]: colour filtering predict + trimap with bg colour, 300 x 1080p", n, ms, launches,
+               n * 6 * h * w, 1 / dt, "oracle cf_forward_predict + generate_trimap_withbg on 1 frame (numpy, 1 thread); output bit-exact", peak)
+        del fr, sg, alpha, tri
+
+    if want("green_4k"):
+        n, h, w = 48, 2160, 3840
+        fr, sg, fr_h, sg_h = green_clip_dev(n, h, w, distinct=3)
+        cf = fitted_agent(fr_h[0], sg_h[0])
+
+        def step():
+            return clip.green_clip(fr, sg, cf, ta, chunk=8)
+        ms, launches = timed(step, max(2, args.steps // 2), warmup=1)
+        report("green_4k", "BASELINE configs[2]: cf predict -> trimap -> patched bg -> get_fg at 4K (CNN stages skipped), 48 frames", n, ms, launches,
+               n * 12 * h * w, float("nan"), "not timed on the CPU (the 1080p row covers the same functions)", peak)
+        del fr, sg
+
+    if want("replace_1080p"):
+        n, h, w = 300, 1080, 1080 * 16 // 9
+        g = torch.Generator(device="cuda").manual_seed(3)
+        fg = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+        al = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device="cuda", generator=g)
+        bg = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+        out = [None]
+
+        def step():
+            out[0] = clip.replace_clip(fg, al, bg)
+        ms, launches = timed(step, args.steps)
+        f0, a0, b0 = fg[0].cpu().numpy(), al[0].cpu().numpy(), bg.cpu().numpy()
+        t0 = time.perf_counter()
+        ref = R.replace_blend(f0, a0, b0)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(out[0][0].cpu().numpy(), ref)
+        report("replace_1080p", "BASELINE configs[3]: person-replacement blend (replace.py:74-76), 300 x 1080p, shared background", n, ms, launches,
+               n * 7 * h * w + 3 * h * w, 1 / dt, "oracle replace_blend on 1 frame (numpy float64, 1 thread); output bit-exact", peak)
+        del fg, al, bg, out
+
+    if want("bgstep_4k"):
+        n, h, w = 120, 2160, 3840
+        fr = bench.make_clip_device(n, h, w, 1, torch.device("cuda"))
+        yy = torch.arange(h, device="cuda", dtype=torch.float32)[:, None]
+        xx = torch.arange(w, device="cuda", dtype=torch.float32)[None, :]
+        masks = torch.stack([((((xx - w * (0.15 + 0.7 * t / (n - 1))) / (w * 0.12)) ** 2 + ((yy - h / 2.0) / (h * 0.45)) ** 2) <= 1.0).to(torch.uint8) * 255
+                             for t in range(n)])
+
+        def step():
+            return clip.bgstep_clip(fr, masks, ta, chunk=8)
+        ms, launches = timed(step, max(2, args.steps // 2), warmup=1)
+        report("bgstep_4k", "BASELINE configs[4] on one GPU tile: temporal median + difference gate + trimap + get_fg at 4K, 120 frames", n, ms, launches,
+               n * 12 * h * w + 6 * h * w, float("nan"), "not timed on the CPU", peak)
+
+
+if __name__ == "__main__":
+    main()

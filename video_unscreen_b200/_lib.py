@@ -38,6 +38,8 @@ SIGNATURES = {
     "vu_inrange_image": (_i, [_p, _p, _i64, _i64, _i3, _p, _p]),
     "vu_morph_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "vu_morph_u8": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "vu_cross_chain_u8": (_i, [_p, _p, _i, _i, _i, _i, _i3, _i3, _p, _d, _p]),
+    "vu_trimap_core_u8": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "vu_resize_linear_u8": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "vu_resize_nearest_u8": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "vu_count_cmp_u8": (_i, [_p, _i, _i64, _i, _i, _p, _p]),

@@ -38,9 +38,7 @@ def cf_predict_clip(frames, segmasks, agent, chunk=32, out=None):
         hsv_lo = ops.resize_linear_image(ops.bgr2hsv(fr), th, tw)
         mask_lo = ops.resize_linear_mask(sm, th, tw)
         a = ops.cf_alpha_lut3d(hsv_lo, lut3d) if lut3d is not None else ops.cf_alpha(hsv_lo, luts)
-        a = ops.cf_threshold(a, mask_lo, 0.8)
-        a = ops.erode(ops.dilate(a, 3, 2), 3, 2)
-        a = ops.dilate(ops.erode(a, 3, 2), 3, 2)
+        a = ops.cf_postprocess(a, mask_lo, 0.8)
         a = ops.resize_linear_mask(a, h, w)
         alpha[s:e] = ops.select_frames(sm, a, flags)     # degenerate masks are returned as they came (agent.py:303-307)
     return alpha
@@ -50,7 +48,10 @@ def _trimap_plain(masks, agent):
     n, h, w = masks.shape
     ih, iw = get_target_size(h, w, agent.input_long_side)
     m = ops.resize_nearest_mask(masks, ih, iw)
-    tri = ops.trimap_classify(ops.dilate(m, agent.kernelsize, agent.iters), ops.erode(m, agent.kernelsize, agent.iters))
+    if agent.kernelsize == 3 and agent.iters <= ops.CROSS_MAX_PASSES:
+        tri = ops.trimap_core(m, agent.iters)
+    else:
+        tri = ops.trimap_classify(ops.dilate(m, agent.kernelsize, agent.iters), ops.erode(m, agent.kernelsize, agent.iters))
     return ops.trimap_snap(ops.resize_linear_mask(tri, h, w))
 
 

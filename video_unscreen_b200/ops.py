@@ -88,12 +88,46 @@ def inrange_image(x, bg, half):
 
 # ---- morphology / resize ----------------------------------------------------
 
+CROSS_MAX_PASSES = 12
+
+
 def morph(x, ksize, iters, op):
+    """cv2.dilate / cv2.erode with MORPH_ELLIPSE(ksize, ksize), `iters` iterations."""
+    if int(ksize) == 3 and int(iters) <= CROSS_MAX_PASSES:
+        return cross_chain(x, [(op, iters)])
     x = _mask(x)
     n = 1 if x.ndim == 2 else x.shape[0]
     h, w = x.shape[-2:]
     out = torch.empty_like(x)
     check(lib().vu_morph_u8(_p(x), _p(out), n, h, w, int(ksize), int(iters), op, ctypes.c_void_p(0), 0, _stream()))
+    return out
+
+
+def cross_chain(x, segments, stats=None, thr_ratio=0.8):
+    """chain of (op, iters) segments of the 3x3 cross in one kernel; with
+    ``stats`` ([n,2] int64 sum/count) the colour-filter threshold is applied on load."""
+    x = _mask(x)
+    n = 1 if x.ndim == 2 else x.shape[0]
+    h, w = x.shape[-2:]
+    segs = [(int(o), int(i)) for o, i in segments]
+    if not 1 <= len(segs) <= 4 or sum(i for _, i in segs) > CROSS_MAX_PASSES:
+        raise ValueError("cross_chain: 1..4 segments, at most 12 passes")
+    segs += [(0, 0)] * (4 - len(segs))
+    ops_a = (ctypes.c_int32 * 4)(*[o for o, _ in segs])
+    it_a = (ctypes.c_int32 * 4)(*[i for _, i in segs])
+    out = torch.empty_like(x)
+    sp = _p(_dev(stats, torch.int64)) if stats is not None else ctypes.c_void_p(0)
+    check(lib().vu_cross_chain_u8(_p(x), _p(out), n, h, w, len(segments), ops_a, it_a, sp, float(thr_ratio), _stream()))
+    return out
+
+
+def trimap_core(mask_lo, iters):
+    """classify(dilate^iters, erode^iters) of the 3x3 cross in one kernel (trimap/agent.py:53-58)."""
+    x = _mask(mask_lo)
+    n = 1 if x.ndim == 2 else x.shape[0]
+    h, w = x.shape[-2:]
+    out = torch.empty_like(x)
+    check(lib().vu_trimap_core_u8(_p(x), _p(out), n, h, w, int(iters), _stream()))
     return out
 
 
@@ -241,6 +275,22 @@ def cf_alpha_lut3d(hsv, lut3d):
     out = torch.empty(hsv.shape[:-1], dtype=u8, device=hsv.device)
     check(lib().vu_cf_alpha_lut3d_u8(_p(hsv), hsv.numel() // 3, _p(lut3d), _p(out), _stream()))
     return out
+
+
+def cf_threshold_stats(alpha, mask):
+    """per item {sum, count} of alpha over (alpha > 128 and mask > 0)."""
+    alpha, mask = _mask(alpha), _mask(mask)
+    n, per = _items(alpha, 2)
+    stats = torch.empty((n, 2), dtype=torch.int64, device=alpha.device)
+    check(lib().vu_cf_threshold_stats(_p(alpha), _p(mask), n, per, _p(stats), _stream()))
+    return stats
+
+
+def cf_postprocess(alpha, mask, thr_ratio=0.8):
+    """ColorFilteringAgent.postprocess (agent.py:259-283): adaptive threshold then
+    d2,e2,e2,d2, the threshold fused into the morphology kernel's load."""
+    stats = cf_threshold_stats(alpha, mask)
+    return cross_chain(alpha, [(_lib.DILATE, 2), (_lib.ERODE, 2), (_lib.ERODE, 2), (_lib.DILATE, 2)], stats, thr_ratio)
 
 
 def cf_threshold(alpha, mask, thr_ratio=0.8):

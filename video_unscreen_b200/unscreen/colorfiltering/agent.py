@@ -178,9 +178,7 @@ class ColorFilteringAgent():
 
     @staticmethod
     def _postprocess_dev(alpha_dev, mask_dev, thr_ratio=0.8):
-        a = ops.cf_threshold(alpha_dev, mask_dev, thr_ratio)
-        a = ops.erode(ops.dilate(a, 3, 2), 3, 2)
-        return ops.dilate(ops.erode(a, 3, 2), 3, 2)
+        return ops.cf_postprocess(alpha_dev, mask_dev, thr_ratio)
 
     def get_alpha_by_gmm(self, img_hsv):
         """agent.py:232-257 -> (alpha, confidence).  The reference returns the

@@ -21,7 +21,10 @@ class TrimapAgent():
         ori_h, ori_w = mask.shape
         ih, iw = get_target_size(ori_h, ori_w, self.input_long_side)
         m = ops.resize_nearest_mask(mask, ih, iw)
-        tri = ops.trimap_classify(ops.dilate(m, self.kernelsize, self.iters), ops.erode(m, self.kernelsize, self.iters))
+        if self.kernelsize == 3 and self.iters <= ops.CROSS_MAX_PASSES:
+            tri = ops.trimap_core(m, self.iters)
+        else:
+            tri = ops.trimap_classify(ops.dilate(m, self.kernelsize, self.iters), ops.erode(m, self.kernelsize, self.iters))
         # trimap/agent.py:59 passes INTER_NEAREST in the dst slot: the up-scale is bilinear
         tri = ops.resize_linear_mask(tri, ori_h, ori_w)
         return ops.trimap_snap(tri)
