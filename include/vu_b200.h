@@ -104,6 +104,16 @@ int vu_resize_linear_u8(const uint8_t* src, int n, int sh, int sw, int channels,
 int vu_resize_nearest_u8(const uint8_t* src, int n, int sh, int sw, int channels, uint8_t* dst, int dh, int dw,
                          vu_stream_t stream);
 
+/* cv2.resize (bilinear) of single-channel maps with the coefficient math hoisted
+ * out of the pixel loop.  mode 1 fuses trimap/agent.py:60 (values strictly between
+ * 0 and 255 -> 128) and :100 (128 where fuzzy != 0, only for frames with
+ * flags[i] == 0).  alt_src / alt_flags (both NULL or both set): frames with
+ * alt_flags[i] != 0 are copied from alt_src[n][dh][dw] instead (the early-outs of
+ * colorfiltering/agent.py:303-307). */
+int vu_resize_up_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, int mode,
+                    const uint8_t* fuzzy, const uint8_t* flags, const uint8_t* alt_src, const uint8_t* alt_flags,
+                    vu_stream_t stream);
+
 /* ---- reductions -------------------------------------------------------- */
 /* counts[i] = #{ src[i][j] <op> thr }; exist_foreground (maskprocess.py:56-60),
  * the early-outs of colorfiltering/agent.py:303-307 and trimap/agent.py:88 */
@@ -120,6 +130,14 @@ int vu_mask_set128_where(const uint8_t* a, const uint8_t* b, uint8_t* out, int64
 
 /* out = 1 where a > 0 && b > 0 else 0 (the fuzzy area itself, :91) */
 int vu_mask_and01(const uint8_t* a, const uint8_t* b, uint8_t* out, int64_t count, vu_stream_t stream);
+/* trimap/agent.py:90-94 in one pass: fuzzy01 = (alpha > 0) && lo <= HSV(frame) <= hi,
+ * counts2[i] = {#fuzzy, #alpha>0} */
+int vu_fuzzy_count(const uint8_t* frames, const uint8_t* alpha, int n, int64_t npix, const int32_t lo[3],
+                   const int32_t hi[3], uint8_t* fuzzy01, uint64_t* counts2, vu_stream_t stream);
+/* trimap/agent.py:52 (INTER_NEAREST down-scale) with :97-98 fused:
+ * out[y][x] = (flags[i] == 0 && fuzzy[sy][sx]) ? 0 : mask[sy][sx]; fuzzy/flags may both be NULL */
+int vu_trimap_src_lo(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* flags, int n, int h, int w, int th,
+                     int tw, uint8_t* out, vu_stream_t stream);
 /* generate_trimap, trimap/agent.py:54-58: out = 0 where dilated < 128, else
  * 255 where eroded > 127, else 128 */
 int vu_trimap_classify(const uint8_t* dilated, const uint8_t* eroded, uint8_t* out, int64_t count,
@@ -151,6 +169,13 @@ int vu_cf_alpha_u8(const uint8_t* hsv, int64_t npix, const float* luts, uint8_t*
 int vu_cf_build_lut3d(const float* luts, uint8_t* lut3d, vu_stream_t stream);
 int vu_cf_alpha_lut3d_u8(const uint8_t* hsv, int64_t npix, const uint8_t* lut3d, uint8_t* alpha,
                          vu_stream_t stream);
+/* one pass over the full-resolution frames: BGR2HSV (:310) + cv2.resize of the
+ * HSV image and the mask for exact 2x / 4x down-scales (:315-316) + tabulated
+ * get_alpha_by_gmm (:319) + the statistics of postprocess (:277-279).
+ * h == s*th, w == s*tw, s in {2,4}; anything else returns VU_ERR_UNSUPPORTED and
+ * the caller composes the stage from the primitives above. */
+int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int th, int tw,
+                 const uint8_t* lut3d, uint8_t* alpha_lo, uint64_t* stats2, vu_stream_t stream);
 /* postprocess (:259-283) step 1: per frame sum/count of alpha over
  * (alpha>128 && mask>0) -> stats[i] = {sum, count}; step 2 zeroes alpha below
  * 0.8 * sum/count (f64; count==0 leaves alpha untouched).  The d2,e2,e2,d2

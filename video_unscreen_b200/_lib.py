@@ -53,6 +53,10 @@ SIGNATURES = {
     "vu_cf_degenerate_flags": (_i, [_p, _p, _i, ctypes.c_uint64, ctypes.c_uint64, _p, _p]),
     "vu_select_frames": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "vu_set128_unflagged": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
+    "vu_cf_lowres": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vu_resize_up_u8": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "vu_fuzzy_count": (_i, [_p, _p, _i, _i64, _i3, _i3, _p, _p, _p]),
+    "vu_trimap_src_lo": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "vu_cf_alpha_u8": (_i, [_p, _i64, _p, _p, _p]),
     "vu_cf_build_lut3d": (_i, [_p, _p, _p]),
     "vu_cf_alpha_lut3d_u8": (_i, [_p, _i64, _p, _p, _p]),

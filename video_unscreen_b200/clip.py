@@ -35,24 +35,31 @@ def cf_predict_clip(frames, segmasks, agent, chunk=32, out=None):
     for s, e in _chunks(n, chunk):
         fr, sm = frames[s:e], segmasks[s:e]
         flags = ops.cf_degenerate_flags(ops.count_cmp(sm, _lib.CMP_GT, 128), ops.count_cmp(sm, _lib.CMP_LT, 128), fg_min, bg_min)
-        hsv_lo = ops.resize_linear_image(ops.bgr2hsv(fr), th, tw)
-        mask_lo = ops.resize_linear_mask(sm, th, tw)
-        a = ops.cf_alpha_lut3d(hsv_lo, lut3d) if lut3d is not None else ops.cf_alpha(hsv_lo, luts)
-        a = ops.cf_postprocess(a, mask_lo, 0.8)
-        a = ops.resize_linear_mask(a, h, w)
-        alpha[s:e] = ops.select_frames(sm, a, flags)     # degenerate masks are returned as they came (agent.py:303-307)
+        if ops.cf_lowres_supported(h, w, th, tw):
+            # one pass over the frames, then threshold+d2e2e2d2 in shared memory, then the up-scale
+            a_lo, stats = ops.cf_lowres(fr, sm, th, tw, lut3d)
+            a_lo = ops.cross_chain(a_lo, [(_lib.DILATE, 2), (_lib.ERODE, 2), (_lib.ERODE, 2), (_lib.DILATE, 2)], stats, 0.8)
+        else:
+            hsv_lo = ops.resize_linear_image(ops.bgr2hsv(fr), th, tw)
+            a_lo = ops.cf_postprocess(ops.cf_alpha_lut3d(hsv_lo, lut3d), ops.resize_linear_mask(sm, th, tw), 0.8)
+        # degenerate masks are returned as they came (agent.py:303-307): alt_src / alt_flags
+        alpha[s:e] = ops.resize_up(a_lo, h, w, alt_src=sm, alt_flags=flags)
     return alpha
 
 
-def _trimap_plain(masks, agent):
+def _trimap_tail(masks, agent, fuzzy=None, flags=None):
+    """nearest down (+ ensemble clearing) -> dilate/erode/classify -> bilinear up + snap (+ fuzzy override)"""
     n, h, w = masks.shape
     ih, iw = get_target_size(h, w, agent.input_long_side)
-    m = ops.resize_nearest_mask(masks, ih, iw)
+    m = ops.trimap_src_lo(masks, ih, iw, fuzzy, flags)
     if agent.kernelsize == 3 and agent.iters <= ops.CROSS_MAX_PASSES:
         tri = ops.trimap_core(m, agent.iters)
     else:
         tri = ops.trimap_classify(ops.dilate(m, agent.kernelsize, agent.iters), ops.erode(m, agent.kernelsize, agent.iters))
-    return ops.trimap_snap(ops.resize_linear_mask(tri, h, w))
+    if (ih, iw) == (h, w) or (ih == 2 * h and iw == 2 * w):   # copy / cv2's INTER_AREA corner cases: unfused tail
+        t = ops.trimap_snap(ops.resize_linear_mask(tri, h, w))
+        return ops.set128_unflagged(t, fuzzy, flags) if fuzzy is not None else t
+    return ops.resize_up(tri, h, w, mode=1, fuzzy=fuzzy, flags=flags)
 
 
 def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
@@ -66,21 +73,20 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
     for s, e in _chunks(n, chunk):
         m = masks[s:e]
         if frames is None:
-            tri[s:e] = _trimap_plain(m, agent)
+            tri[s:e] = _trimap_tail(m, agent)
             continue
         fr = frames[s:e]
         if isinstance(bg, np.ndarray) and bg.ndim == 1:
             hsv = bgr2hsv_pixel(bg)
-            bgmask = ops.inrange_color(fr, np.clip(hsv - half, 10, 255), np.clip(hsv + half, 10, 255))
+            fuzzy, counts = ops.fuzzy_count(fr, m, np.clip(hsv - half, 10, 255), np.clip(hsv + half, 10, 255))
         else:
             b = bg[s:e] if bg.ndim == 4 else bg
             bgmask = ops.inrange_image(fr, b, half)
-        flags = ops.ratio_flags(ops.count_and(m, bgmask), 0.1)       # 0: ensemble, 1: trust mask, 2: empty mask
-        fuzzy = ops.mask_and01(m, bgmask)
-        src = ops.select_frames(m, ops.mask_clear_where(m, fuzzy), flags)
-        t = ops.set128_unflagged(_trimap_plain(src, agent), fuzzy, flags)
+            counts = ops.count_and(m, bgmask)
+            fuzzy = ops.mask_and01(m, bgmask)
+        flags = ops.ratio_flags(counts, 0.1)       # 0: ensemble, 1: trust mask, 2: empty mask
         # an empty mask is returned as is (all zeros); the plain branch of an all-zero mask is all zeros too
-        tri[s:e] = t
+        tri[s:e] = _trimap_tail(m, agent, fuzzy, flags)
     return tri
 
 

@@ -265,3 +265,313 @@ extern "C" int vu_trimap_core_u8(const uint8_t* src, uint8_t* dst, int n, int h,
   cross_chain_kernel<1><<<grid, CC_THREADS, smem, S(stream)>>>(src, dst, h, w, ch, nullptr, 0.0, iters);
   VU_RETURN_LAUNCH();
 }
+
+// =================================================================================
+// cf_lowres, resize_up, fuzzy_count, trimap_src_lo
+// =================================================================================
+namespace vu {
+namespace {
+
+constexpr int FT = 256;
+
+__device__ __forceinline__ void warp_block_atomic2(unsigned long long a, unsigned long long b, unsigned long long* dst) {
+  // reduce two counters over the block, one atomic pair per block
+  __shared__ unsigned long long sh[2][FT / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = threadIdx.x < FT / 32 ? sh[0][threadIdx.x] : 0;
+    b = threadIdx.x < FT / 32 ? sh[1][threadIdx.x] : 0;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      a += __shfl_down_sync(0xffffffffu, a, o);
+      b += __shfl_down_sync(0xffffffffu, b, o);
+    }
+    if (threadIdx.x == 0) {
+      if (a) atomicAdd(dst, a);
+      if (b) atomicAdd(dst + 1, b);
+    }
+  }
+}
+
+// S = 2: thread = two low-res pixels (a 2x4 block of the frame); S = 4: one low-res pixel (centre 2x2 of a 4x4 block)
+template <int S>
+__global__ void __launch_bounds__(FT) cf_lowres_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th, int tw,
+                                                       const uint8_t* __restrict__ lut3d, uint8_t* __restrict__ alpha_lo,
+                                                       unsigned long long* __restrict__ stats2) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int per_row = (S == 2) ? tw / 2 : tw;           // threads per low-res row
+  const int64_t items = (int64_t)th * per_row;
+  const uint8_t* fr = frames + (int64_t)n * h * w * 3;
+  const uint8_t* mk = masks + (int64_t)n * h * w;
+  uint8_t* out = alpha_lo + (int64_t)n * th * tw;
+  unsigned long long sum = 0, cnt = 0;
+  for (int64_t it = (int64_t)blockIdx.x * FT + threadIdx.x; it < items; it += (int64_t)gridDim.x * FT) {
+    const int y = (int)(it / per_row), xg = (int)(it - (int64_t)y * per_row);
+    const int r0 = (S == 2) ? 2 * y : 4 * y + 1;
+    const int c0 = 4 * xg;                              // first full-res column of this thread's 4-pixel span
+    int hs[4][3];                                       // S=2: [row][...] handled below
+    int px[2][12];
+    unsigned mw[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const unsigned* p = reinterpret_cast<const unsigned*>(fr + ((int64_t)(r0 + r) * w + c0) * 3);
+      unpack12(__ldg(p), __ldg(p + 1), __ldg(p + 2), px[r]);
+      mw[r] = __ldg(reinterpret_cast<const unsigned*>(mk + (int64_t)(r0 + r) * w + c0));
+    }
+    (void)hs;
+    if (S == 2) {
+      unsigned res = 0;
+#pragma unroll
+      for (int o = 0; o < 2; ++o) {                     // two outputs: columns (0,1) and (2,3)
+        int acc[3] = {0, 0, 0};
+        int macc = 0;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int q = 2 * o + k;
+            int hh, ss, vv;
+            bgr2hsv_px(px[r][3 * q], px[r][3 * q + 1], px[r][3 * q + 2], tab, hh, ss, vv);
+            acc[0] += hh; acc[1] += ss; acc[2] += vv;
+            macc += (mw[r] >> (8 * q)) & 255;
+          }
+        const int hh = (acc[0] + 2) >> 2, ss = (acc[1] + 2) >> 2, vv = (acc[2] + 2) >> 2, mm = (macc + 2) >> 2;
+        const unsigned a = __ldg(lut3d + ((hh << 16) | (ss << 8) | vv));
+        if (a > 128 && mm > 0) { sum += a; ++cnt; }
+        res |= a << (8 * o);
+      }
+      *reinterpret_cast<unsigned short*>(out + (int64_t)y * tw + 2 * xg) = (unsigned short)res;
+    } else {
+      int acc[3] = {0, 0, 0};
+      int macc = 0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int q = 1; q <= 2; ++q) {
+          int hh, ss, vv;
+          bgr2hsv_px(px[r][3 * q], px[r][3 * q + 1], px[r][3 * q + 2], tab, hh, ss, vv);
+          acc[0] += hh; acc[1] += ss; acc[2] += vv;
+          macc += (mw[r] >> (8 * q)) & 255;
+        }
+      const int hh = (acc[0] + 2) >> 2, ss = (acc[1] + 2) >> 2, vv = (acc[2] + 2) >> 2, mm = (macc + 2) >> 2;
+      const unsigned a = __ldg(lut3d + ((hh << 16) | (ss << 8) | vv));
+      if (a > 128 && mm > 0) { sum += a; ++cnt; }
+      out[(int64_t)y * tw + xg] = (uint8_t)a;
+    }
+  }
+  warp_block_atomic2(sum, cnt, stats2 + 2 * n);
+}
+
+struct AxisC {
+  int i0, i1, w0, w1;
+};
+__device__ __forceinline__ AxisC up_axis(int d, int dst, int src, bool reset) {
+  const double inv_scale = (double)dst / (double)src;
+  const double scale = 1.0 / inv_scale;
+  float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  int i0 = (int)floorf(f);
+  float fr = __fsub_rn(f, (float)i0);
+  AxisC a;
+  if (reset) {
+    if (i0 < 0) { i0 = 0; fr = 0.f; }
+    if (i0 >= src - 1) { i0 = src - 1; fr = 0.f; }
+    a.i0 = i0;
+    a.i1 = min(i0 + 1, src - 1);
+  } else {
+    a.i0 = min(max(i0, 0), src - 1);
+    a.i1 = min(max(i0 + 1, 0), src - 1);
+  }
+  a.w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, fr), 2048.f));
+  a.w1 = __float2int_rn(__fmul_rn(fr, 2048.f));
+  return a;
+}
+
+constexpr int RU_TW = 128, RU_TH = 64;   // dst tile; 256 threads = 32 column groups x 8 row lanes
+// MODE 0: plain   MODE 1: snap (0<v<255 -> 128), then 128 where flags[n]==0 && fuzzy
+template <int MODE>
+__global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
+                                                       const uint8_t* __restrict__ fuzzy, const uint8_t* __restrict__ flags,
+                                                       const uint8_t* __restrict__ alt_src, const uint8_t* __restrict__ alt_flags) {
+  __shared__ AxisC ytab[RU_TH];
+  const int n = blockIdx.z;
+  const int ty0 = blockIdx.y * RU_TH;
+  if (threadIdx.x < RU_TH && ty0 + threadIdx.x < dh) ytab[threadIdx.x] = up_axis(ty0 + threadIdx.x, dh, sh, false);
+  const int gx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int x = blockIdx.x * RU_TW + 4 * gx;
+  AxisC xa[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xa[k] = up_axis(min(x + k, dw - 1), dw, sw, true);
+  __syncthreads();
+  if (x >= dw) return;
+  const uint8_t* s = src + (int64_t)n * sh * sw;
+  uint8_t* d = dst + (int64_t)n * dh * dw;
+  const bool use_alt = alt_flags && alt_flags[n] != 0;
+  const bool ens = (MODE == 1) && fuzzy && flags && flags[n] == 0;
+  const bool vec = (dw & 3) == 0 && x + 3 < dw && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
+  for (int r = ry; r < RU_TH; r += 8) {
+    const int y = ty0 + r;
+    if (y >= dh) break;
+    unsigned word = 0;
+    if (use_alt) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x + k < dw) word |= (unsigned)__ldg(alt_src + ((int64_t)n * dh + y) * dw + x + k) << (8 * k);
+    } else {
+      const AxisC ya = ytab[r];
+      const uint8_t* r0 = s + (int64_t)ya.i0 * sw;
+      const uint8_t* r1 = s + (int64_t)ya.i1 * sw;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int R0 = __ldg(r0 + xa[k].i0) * xa[k].w0 + __ldg(r0 + xa[k].i1) * xa[k].w1;
+        const int R1 = __ldg(r1 + xa[k].i0) * xa[k].w0 + __ldg(r1 + xa[k].i1) * xa[k].w1;
+        int v = (((ya.w0 * (R0 >> 4)) >> 16) + ((ya.w1 * (R1 >> 4)) >> 16) + 2) >> 2;
+        v = min(255, max(0, v));
+        if (MODE == 1) {
+          if (v > 0 && v < 255) v = 128;
+          if (ens && x + k < dw && __ldg(fuzzy + ((int64_t)n * dh + y) * dw + x + k)) v = 128;
+        }
+        word |= (unsigned)v << (8 * k);
+      }
+    }
+    uint8_t* o = d + (int64_t)y * dw + x;
+    if (vec) *reinterpret_cast<unsigned*>(o) = word;
+    else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x + k < dw) o[k] = (uint8_t)(word >> (8 * k));
+    }
+  }
+}
+
+// fuzzy01 = (alpha > 0) && lo <= HSV(frame) <= hi; counts2[n] = {#fuzzy, #alpha>0}
+__global__ void __launch_bounds__(FT) fuzzy_count_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ alpha, int64_t ngroups,
+                                                         int lo0, int lo1, int lo2, int hi0, int hi1, int hi2, uint8_t* __restrict__ fuzzy,
+                                                         unsigned long long* __restrict__ counts2) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int n = blockIdx.y;
+  const unsigned* f4 = reinterpret_cast<const unsigned*>(frames) + (int64_t)n * ngroups * 3;
+  const unsigned* a4 = reinterpret_cast<const unsigned*>(alpha) + (int64_t)n * ngroups;
+  unsigned* o4 = reinterpret_cast<unsigned*>(fuzzy) + (int64_t)n * ngroups;
+  unsigned long long nf = 0, np = 0;
+  for (int64_t g = (int64_t)blockIdx.x * FT + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * FT) {
+    int c[12];
+    unpack12(__ldg(f4 + 3 * g), __ldg(f4 + 3 * g + 1), __ldg(f4 + 3 * g + 2), c);
+    const unsigned aw = __ldg(a4 + g);
+    unsigned w = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int hh, ss, vv;
+      bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, hh, ss, vv);
+      const bool in = (hh >= lo0) & (hh <= hi0) & (ss >= lo1) & (ss <= hi1) & (vv >= lo2) & (vv <= hi2);
+      const bool pos = ((aw >> (8 * i)) & 255u) != 0;
+      np += pos;
+      nf += pos && in;
+      w |= (unsigned)(pos && in) << (8 * i);
+    }
+    o4[g] = w;
+  }
+  warp_block_atomic2(nf, np, counts2 + 2 * n);
+}
+
+// nearest down-scale of the trimap source mask with the ensemble clearing fused:
+// out[y][x] = (flags[n] == 0 && fuzzy[sy][sx]) ? 0 : mask[sy][sx]
+__global__ void __launch_bounds__(FT) trimap_src_lo_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ fuzzy,
+                                                           const uint8_t* __restrict__ flags, int h, int w, int th, int tw, uint8_t* __restrict__ out) {
+  const int n = blockIdx.y;
+  const double ifx = 1.0 / ((double)tw / (double)w), ify = 1.0 / ((double)th / (double)h);
+  const bool ens = fuzzy && flags && flags[n] == 0;
+  const int64_t total = (int64_t)th * tw;
+  for (int64_t i = (int64_t)blockIdx.x * FT + threadIdx.x; i < total; i += (int64_t)gridDim.x * FT) {
+    const int y = (int)(i / tw), x = (int)(i - (int64_t)y * tw);
+    const int sx = min((int)floor(__dmul_rn((double)x, ifx)), w - 1);
+    const int sy = min((int)floor(__dmul_rn((double)y, ify)), h - 1);
+    const int64_t si = ((int64_t)n * h + sy) * w + sx;
+    int v = __ldg(mask + si);
+    if (ens && __ldg(fuzzy + si)) v = 0;
+    out[(int64_t)n * total + i] = (uint8_t)v;
+  }
+}
+
+inline dim3 frame_grid(int n, int64_t items_per_frame) {
+  int64_t bx = (items_per_frame + FT - 1) / FT;
+  int64_t cap = ((int64_t)device_sms() * 8 + n - 1) / n;
+  if (cap < 1) cap = 1;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  return dim3((unsigned)bx, n);
+}
+
+}  // namespace
+}  // namespace vu
+
+// BGR2HSV + cv2.resize (exact 2x or 4x) of the HSV image and of the mask +
+// tabulated mixture evaluation + postprocess statistics (colorfiltering/
+// agent.py:310-320, 277-279).  h == s*th and w == s*tw with s in {2, 4}.
+extern "C" int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int th, int tw, const uint8_t* lut3d,
+                            uint8_t* alpha_lo, uint64_t* stats2, vu_stream_t stream) {
+  VU_REQUIRE(frames && masks && lut3d && alpha_lo && stats2 && n >= 0 && h > 0 && w > 0 && th > 0 && tw > 0);
+  const int s = (h == 2 * th && w == 2 * tw) ? 2 : ((h == 4 * th && w == 4 * tw) ? 4 : 0);
+  if (s == 0 || (w & 3) || (tw & 1)) return VU_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(frames) & 3) || (reinterpret_cast<uintptr_t>(masks) & 3) || (reinterpret_cast<uintptr_t>(alpha_lo) & 1))
+    return VU_ERR_UNSUPPORTED;
+  if (n == 0) return VU_OK;
+  int e = record_cuda(cudaMemsetAsync(stats2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
+  if (e) return e;
+  auto* st = reinterpret_cast<unsigned long long*>(stats2);
+  if (s == 2) cf_lowres_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 2)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
+  else cf_lowres_kernel<4><<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
+  VU_RETURN_LAUNCH();
+}
+
+// cv2.resize (bilinear) of single-channel maps.  mode 1 fuses trimap/agent.py:60
+// (snap) and :100 (128 where fuzzy, only for frames with flags[i] == 0).
+// alt_src/alt_flags (nullable): frames with alt_flags[i] != 0 are copied from
+// alt_src (full resolution) instead (the early-outs of colorfiltering/agent.py:303-307).
+extern "C" int vu_resize_up_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, int mode, const uint8_t* fuzzy,
+                               const uint8_t* flags, const uint8_t* alt_src, const uint8_t* alt_flags, vu_stream_t stream) {
+  VU_REQUIRE(src && dst && n >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 && (mode == 0 || mode == 1));
+  VU_REQUIRE((alt_src == nullptr) == (alt_flags == nullptr));
+  if (sw == 2 * dw && sh == 2 * dh) return VU_ERR_UNSUPPORTED;  // cv2 switches to INTER_AREA there
+  if (n == 0) return VU_OK;
+  dim3 grid((dw + RU_TW - 1) / RU_TW, (dh + RU_TH - 1) / RU_TH, n);
+  if (mode == 0) resize_up_kernel<0><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
+  else resize_up_kernel<1><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_fuzzy_count(const uint8_t* frames, const uint8_t* alpha, int n, int64_t npix, const int32_t lo[3], const int32_t hi[3],
+                              uint8_t* fuzzy01, uint64_t* counts2, vu_stream_t stream) {
+  VU_REQUIRE(frames && alpha && lo && hi && fuzzy01 && counts2 && n >= 0 && npix >= 0);
+  if (npix % 4) return VU_ERR_UNSUPPORTED;
+  const void* ptrs[] = {frames, alpha, fuzzy01};
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 3) return VU_ERR_UNSUPPORTED;
+  if (n == 0) return VU_OK;
+  int e = record_cuda(cudaMemsetAsync(counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
+  if (e) return e;
+  if (npix == 0) return VU_OK;
+  fuzzy_count_kernel<<<frame_grid(n, npix / 4), FT, 0, S(stream)>>>(frames, alpha, npix / 4, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], fuzzy01,
+                                                                    reinterpret_cast<unsigned long long*>(counts2));
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_trimap_src_lo(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* flags, int n, int h, int w, int th, int tw, uint8_t* out,
+                                vu_stream_t stream) {
+  VU_REQUIRE(mask && out && n >= 0 && h > 0 && w > 0 && th > 0 && tw > 0);
+  VU_REQUIRE((fuzzy == nullptr) == (flags == nullptr));
+  if (n == 0) return VU_OK;
+  trimap_src_lo_kernel<<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, out);
+  VU_RETURN_LAUNCH();
+}

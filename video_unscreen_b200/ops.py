@@ -157,7 +157,56 @@ def _resize(fn, x, dh, dw, channels):
 
 
 def resize_linear_mask(x, dh, dw):
-    return _resize(lib().vu_resize_linear_u8, x, dh, dw, 1)
+    x = _mask(x)
+    sh, sw = x.shape[-2:]
+    if (sh, sw) == (dh, dw) or (sh == 2 * dh and sw == 2 * dw):
+        return _resize(lib().vu_resize_linear_u8, x, dh, dw, 1)   # copy / cv2's silent INTER_AREA
+    return resize_up(x, dh, dw)
+
+
+def resize_up(x, dh, dw, mode=0, fuzzy=None, flags=None, alt_src=None, alt_flags=None):
+    """cv2.resize (bilinear) of masks with fused epilogues (see vu_resize_up_u8)."""
+    x = _mask(x)
+    n = 1 if x.ndim == 2 else x.shape[0]
+    sh, sw = x.shape[-2:]
+    out = torch.empty((dh, dw) if x.ndim == 2 else (n, dh, dw), dtype=u8, device=x.device)
+    check(lib().vu_resize_up_u8(_p(x), n, sh, sw, _p(out), int(dh), int(dw), int(mode), _p(fuzzy), _p(flags), _p(alt_src), _p(alt_flags),
+                                _stream()))
+    return out
+
+
+def cf_lowres(frames, masks, th, tw, lut3d):
+    """fused BGR2HSV + down-scale + tabulated mixtures + postprocess statistics; -> (alpha_lo, stats)"""
+    frames, masks, lut3d = _img(frames), _mask(masks), _dev(lut3d)
+    n = 1 if frames.ndim == 3 else frames.shape[0]
+    h, w = frames.shape[-3:-1]
+    alpha = torch.empty((th, tw) if frames.ndim == 3 else (n, th, tw), dtype=u8, device=frames.device)
+    stats = torch.empty((n, 2), dtype=torch.int64, device=frames.device)
+    check(lib().vu_cf_lowres(_p(frames), _p(masks), n, h, w, int(th), int(tw), _p(lut3d), _p(alpha), _p(stats), _stream()))
+    return alpha, stats
+
+
+def cf_lowres_supported(h, w, th, tw):
+    return ((h == 2 * th and w == 2 * tw) or (h == 4 * th and w == 4 * tw)) and w % 4 == 0 and tw % 2 == 0
+
+
+def fuzzy_count(frames, alpha, lo, hi):
+    """-> (fuzzy01 [n,h,w], counts [n,2] = (#fuzzy, #alpha>0)); trimap/agent.py:90-94"""
+    frames, alpha = _img(frames), _mask(alpha)
+    n = 1 if frames.ndim == 3 else frames.shape[0]
+    fuzzy = torch.empty_like(alpha)
+    counts = torch.empty((n, 2), dtype=torch.int64, device=frames.device)
+    check(lib().vu_fuzzy_count(_p(frames), _p(alpha), n, alpha.numel() // n, i3(lo), i3(hi), _p(fuzzy), _p(counts), _stream()))
+    return fuzzy, counts
+
+
+def trimap_src_lo(mask, th, tw, fuzzy=None, flags=None):
+    mask = _mask(mask)
+    n = 1 if mask.ndim == 2 else mask.shape[0]
+    h, w = mask.shape[-2:]
+    out = torch.empty((th, tw) if mask.ndim == 2 else (n, th, tw), dtype=u8, device=mask.device)
+    check(lib().vu_trimap_src_lo(_p(mask), _p(fuzzy), _p(flags), n, h, w, int(th), int(tw), _p(out), _stream()))
+    return out
 
 
 def resize_linear_image(x, dh, dw):
