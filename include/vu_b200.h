@@ -119,6 +119,8 @@ int vu_resize_up_u8(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int
  * the early-outs of colorfiltering/agent.py:303-307 and trimap/agent.py:88 */
 int vu_count_cmp_u8(const uint8_t* src, int n, int64_t per_item, int op, int thr, uint64_t* counts,
                     vu_stream_t stream);
+/* counts2[i] = {#{src > thr}, #{src < thr}} in one pass */
+int vu_count_gt_lt_u8(const uint8_t* src, int n, int64_t per_item, int thr, uint64_t* counts2, vu_stream_t stream);
 /* counts[i][0] = #{a>0 && b>0}, counts[i][1] = #{a>0}; the fuzzy-area ratio
  * of trimap/agent.py:91-94 */
 int vu_count_and_u8(const uint8_t* a, const uint8_t* b, int n, int64_t per_item, uint64_t* counts2,
@@ -149,9 +151,10 @@ int vu_trimap_snap(const uint8_t* a, int64_t count, uint8_t* out, vu_stream_t st
  * flags[i] = 2 if counts2[i][1] == 0 (trimap/agent.py:88: mask returned as is),
  * 1 if float(counts2[i][0]) / counts2[i][1] > thr (:94: trust the mask), else 0 */
 int vu_ratio_flags(const uint64_t* counts2, int n, double thr, uint8_t* flags, vu_stream_t stream);
-/* colorfiltering/agent.py:303-307: flags[i] = 1 if nfg[i] < fg_min, 2 if nbg[i] < bg_min, else 0 */
-int vu_cf_degenerate_flags(const uint64_t* nfg, const uint64_t* nbg, int n, uint64_t fg_min, uint64_t bg_min,
-                           uint8_t* flags, vu_stream_t stream);
+/* colorfiltering/agent.py:303-307: flags[i] = 1 if nfg[i] < fg_min, 2 if nbg[i] < bg_min, else 0;
+ * nfg / nbg are read with a stride of `stride` uint64 (1: two arrays, 2: the interleaved output of vu_count_gt_lt_u8) */
+int vu_cf_degenerate_flags(const uint64_t* nfg, const uint64_t* nbg, int n, int stride, uint64_t fg_min,
+                           uint64_t bg_min, uint8_t* flags, vu_stream_t stream);
 /* out[i] = flags[i] ? a[i] : b[i] for whole frames of per_item bytes */
 int vu_select_frames(const uint8_t* a, const uint8_t* b, const uint8_t* flags, int n, int64_t per_item,
                      uint8_t* out, vu_stream_t stream);

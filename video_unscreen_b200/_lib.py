@@ -50,7 +50,8 @@ SIGNATURES = {
     "vu_trimap_classify": (_i, [_p, _p, _p, _i64, _p]),
     "vu_trimap_snap": (_i, [_p, _i64, _p, _p]),
     "vu_ratio_flags": (_i, [_p, _i, _d, _p, _p]),
-    "vu_cf_degenerate_flags": (_i, [_p, _p, _i, ctypes.c_uint64, ctypes.c_uint64, _p, _p]),
+    "vu_cf_degenerate_flags": (_i, [_p, _p, _i, _i, ctypes.c_uint64, ctypes.c_uint64, _p, _p]),
+    "vu_count_gt_lt_u8": (_i, [_p, _i, _i64, _i, _p, _p]),
     "vu_select_frames": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "vu_set128_unflagged": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "vu_cf_lowres": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -34,7 +34,7 @@ def cf_predict_clip(frames, segmasks, agent, chunk=32, out=None):
     fg_min, bg_min = max(agent.fg_ncomp) * 5, max(agent.bg_ncomp) * 5
     for s, e in _chunks(n, chunk):
         fr, sm = frames[s:e], segmasks[s:e]
-        flags = ops.cf_degenerate_flags(ops.count_cmp(sm, _lib.CMP_GT, 128), ops.count_cmp(sm, _lib.CMP_LT, 128), fg_min, bg_min)
+        flags = ops.cf_degenerate_flags(sm, fg_min, bg_min)
         if ops.cf_lowres_supported(h, w, th, tw):
             # one pass over the frames, then threshold+d2e2e2d2 in shared memory, then the up-scale
             a_lo, stats = ops.cf_lowres(fr, sm, th, tw, lut3d)

@@ -397,25 +397,42 @@ __device__ __forceinline__ AxisC up_axis(int d, int dst, int src, bool reset) {
 }
 
 constexpr int RU_TW = 128, RU_TH = 64;   // dst tile; 256 threads = 32 column groups x 8 row lanes
+constexpr int RU_SMAX = 6144;            // staged source bytes per tile (covers down-scales up to ~1.4x as well)
 // MODE 0: plain   MODE 1: snap (0<v<255 -> 128), then 128 where flags[n]==0 && fuzzy
 template <int MODE>
 __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
                                                        const uint8_t* __restrict__ fuzzy, const uint8_t* __restrict__ flags,
                                                        const uint8_t* __restrict__ alt_src, const uint8_t* __restrict__ alt_flags) {
   __shared__ AxisC ytab[RU_TH];
+  __shared__ uint8_t stile[RU_SMAX];
+  __shared__ int sbox[4];  // sx0, sy0, scols, srows of the staged source window
   const int n = blockIdx.z;
-  const int ty0 = blockIdx.y * RU_TH;
+  const int ty0 = blockIdx.y * RU_TH, tx0 = blockIdx.x * RU_TW;
   if (threadIdx.x < RU_TH && ty0 + threadIdx.x < dh) ytab[threadIdx.x] = up_axis(ty0 + threadIdx.x, dh, sh, false);
   const int gx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int x = blockIdx.x * RU_TW + 4 * gx;
+  const int x = tx0 + 4 * gx;
   AxisC xa[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) xa[k] = up_axis(min(x + k, dw - 1), dw, sw, true);
+  if (threadIdx.x == 0) {
+    const AxisC xl = up_axis(tx0, dw, sw, true), xr = up_axis(min(tx0 + RU_TW - 1, dw - 1), dw, sw, true);
+    const AxisC yt = up_axis(ty0, dh, sh, false), yb = up_axis(min(ty0 + RU_TH - 1, dh - 1), dh, sh, false);
+    sbox[0] = xl.i0; sbox[1] = yt.i0; sbox[2] = xr.i1 - xl.i0 + 1; sbox[3] = yb.i1 - yt.i0 + 1;
+  }
+  __syncthreads();
+  const uint8_t* s = src + (int64_t)n * sh * sw;
+  const int sx0 = sbox[0], sy0 = sbox[1], scols = sbox[2], srows = sbox[3];
+  const bool staged = scols * srows <= RU_SMAX;
+  const bool use_alt = alt_flags && alt_flags[n] != 0;
+  if (staged && !use_alt) {
+    for (int i = threadIdx.x; i < scols * srows; i += FT) {
+      const int r = i / scols, c = i - r * scols;
+      stile[i] = __ldg(s + (int64_t)(sy0 + r) * sw + sx0 + c);
+    }
+  }
   __syncthreads();
   if (x >= dw) return;
-  const uint8_t* s = src + (int64_t)n * sh * sw;
   uint8_t* d = dst + (int64_t)n * dh * dw;
-  const bool use_alt = alt_flags && alt_flags[n] != 0;
   const bool ens = (MODE == 1) && fuzzy && flags && flags[n] == 0;
   const bool vec = (dw & 3) == 0 && x + 3 < dw && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
   for (int r = ry; r < RU_TH; r += 8) {
@@ -428,17 +445,34 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
         if (x + k < dw) word |= (unsigned)__ldg(alt_src + ((int64_t)n * dh + y) * dw + x + k) << (8 * k);
     } else {
       const AxisC ya = ytab[r];
-      const uint8_t* r0 = s + (int64_t)ya.i0 * sw;
-      const uint8_t* r1 = s + (int64_t)ya.i1 * sw;
+      unsigned fz = 0;
+      if (ens) {
+        if (vec) fz = __ldg(reinterpret_cast<const unsigned*>(fuzzy + ((int64_t)n * dh + y) * dw + x));
+        else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (x + k < dw) fz |= (unsigned)__ldg(fuzzy + ((int64_t)n * dh + y) * dw + x + k) << (8 * k);
+        }
+      }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int R0 = __ldg(r0 + xa[k].i0) * xa[k].w0 + __ldg(r0 + xa[k].i1) * xa[k].w1;
-        const int R1 = __ldg(r1 + xa[k].i0) * xa[k].w0 + __ldg(r1 + xa[k].i1) * xa[k].w1;
+        int s00, s01, s10, s11;
+        if (staged) {
+          const uint8_t* r0 = stile + (ya.i0 - sy0) * scols - sx0;
+          const uint8_t* r1 = stile + (ya.i1 - sy0) * scols - sx0;
+          s00 = r0[xa[k].i0]; s01 = r0[xa[k].i1]; s10 = r1[xa[k].i0]; s11 = r1[xa[k].i1];
+        } else {
+          const uint8_t* r0 = s + (int64_t)ya.i0 * sw;
+          const uint8_t* r1 = s + (int64_t)ya.i1 * sw;
+          s00 = __ldg(r0 + xa[k].i0); s01 = __ldg(r0 + xa[k].i1); s10 = __ldg(r1 + xa[k].i0); s11 = __ldg(r1 + xa[k].i1);
+        }
+        const int R0 = s00 * xa[k].w0 + s01 * xa[k].w1;
+        const int R1 = s10 * xa[k].w0 + s11 * xa[k].w1;
         int v = (((ya.w0 * (R0 >> 4)) >> 16) + ((ya.w1 * (R1 >> 4)) >> 16) + 2) >> 2;
         v = min(255, max(0, v));
         if (MODE == 1) {
           if (v > 0 && v < 255) v = 128;
-          if (ens && x + k < dw && __ldg(fuzzy + ((int64_t)n * dh + y) * dw + x + k)) v = 128;
+          if ((fz >> (8 * k)) & 255u) v = 128;
         }
         word |= (unsigned)v << (8 * k);
       }
@@ -451,6 +485,37 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
         if (x + k < dw) o[k] = (uint8_t)(word >> (8 * k));
     }
   }
+}
+
+// counts2[n] = {#(v > thr), #(v < thr)} in one vectorised pass (the two early-out tests of colorfiltering/agent.py:303-307)
+__global__ void __launch_bounds__(FT) count_gt_lt_kernel(const uint8_t* __restrict__ src, int64_t per_item, int thr, unsigned long long* __restrict__ counts2) {
+  const int n = blockIdx.y;
+  const uint8_t* p = src + (int64_t)n * per_item;
+  unsigned long long gt = 0, lt = 0;
+  const int64_t nvec = ((reinterpret_cast<uintptr_t>(p) & 15) == 0) ? per_item / 16 : 0;
+  const uint4* p16 = reinterpret_cast<const uint4*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * FT + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * FT) {
+    const uint4 v = ldg_stream16(p16 + i);
+    const unsigned ws[4] = {v.x, v.y, v.z, v.w};
+    unsigned g = 0, l = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int x = (ws[k] >> (8 * b)) & 255;
+        g += x > thr;
+        l += x < thr;
+      }
+    gt += g;
+    lt += l;
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = nvec * 16 + threadIdx.x; i < per_item; i += FT) {
+      const int x = __ldg(p + i);
+      gt += x > thr;
+      lt += x < thr;
+    }
+  warp_block_atomic2(gt, lt, counts2 + 2 * n);
 }
 
 // fuzzy01 = (alpha > 0) && lo <= HSV(frame) <= hi; counts2[n] = {#fuzzy, #alpha>0}
@@ -548,6 +613,16 @@ extern "C" int vu_resize_up_u8(const uint8_t* src, int n, int sh, int sw, uint8_
   dim3 grid((dw + RU_TW - 1) / RU_TW, (dh + RU_TH - 1) / RU_TH, n);
   if (mode == 0) resize_up_kernel<0><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
   else resize_up_kernel<1><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_count_gt_lt_u8(const uint8_t* src, int n, int64_t per_item, int thr, uint64_t* counts2, vu_stream_t stream) {
+  VU_REQUIRE(src && counts2 && n >= 0 && per_item >= 0);
+  if (n == 0) return VU_OK;
+  int e = record_cuda(cudaMemsetAsync(counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
+  if (e) return e;
+  if (per_item == 0) return VU_OK;
+  count_gt_lt_kernel<<<frame_grid(n, per_item / 16 + 1), FT, 0, S(stream)>>>(src, per_item, thr, reinterpret_cast<unsigned long long*>(counts2));
   VU_RETURN_LAUNCH();
 }
 

@@ -234,11 +234,11 @@ __global__ void ratio_flags_kernel(const unsigned long long* counts2, int n, dou
 }
 // degenerate-mask early-outs of ColorFilteringAgent.forward (agent.py:303-307):
 // flags[i] = 1 "no foreground" (alpha := mask), 2 "no background" (alpha := mask), else 0
-__global__ void cf_degenerate_flags_kernel(const unsigned long long* nfg, const unsigned long long* nbg, int n, unsigned long long fg_min,
-                                           unsigned long long bg_min, uint8_t* flags) {
+__global__ void cf_degenerate_flags_kernel(const unsigned long long* nfg, const unsigned long long* nbg, int n, int stride,
+                                           unsigned long long fg_min, unsigned long long bg_min, uint8_t* flags) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  flags[i] = nfg[i] < fg_min ? 1 : (nbg[i] < bg_min ? 2 : 0);
+  flags[i] = nfg[(int64_t)i * stride] < fg_min ? 1 : (nbg[(int64_t)i * stride] < bg_min ? 2 : 0);
 }
 // out[i][:] = flags[i] ? a[i][:] : b[i][:]
 __global__ void __launch_bounds__(THREADS) select_frames_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b,
@@ -270,12 +270,13 @@ extern "C" int vu_ratio_flags(const uint64_t* counts2, int n, double thr, uint8_
   VU_RETURN_LAUNCH();
 }
 
-extern "C" int vu_cf_degenerate_flags(const uint64_t* nfg, const uint64_t* nbg, int n, uint64_t fg_min, uint64_t bg_min, uint8_t* flags,
-                                      vu_stream_t stream) {
-  VU_REQUIRE(nfg && nbg && flags && n >= 0);
+extern "C" int vu_cf_degenerate_flags(const uint64_t* nfg, const uint64_t* nbg, int n, int stride, uint64_t fg_min, uint64_t bg_min,
+                                      uint8_t* flags, vu_stream_t stream) {
+  VU_REQUIRE(nfg && nbg && flags && n >= 0 && stride >= 1);
   if (n == 0) return VU_OK;
   cf_degenerate_flags_kernel<<<(n + 127) / 128, 128, 0, S(stream)>>>(reinterpret_cast<const unsigned long long*>(nfg),
-                                                                       reinterpret_cast<const unsigned long long*>(nbg), n, fg_min, bg_min, flags);
+                                                                       reinterpret_cast<const unsigned long long*>(nbg), n, stride, fg_min, bg_min,
+                                                                       flags);
   VU_RETURN_LAUNCH();
 }
 

@@ -432,10 +432,22 @@ def ratio_flags(counts2, thr):
     return flags
 
 
-def cf_degenerate_flags(nfg, nbg, fg_min, bg_min):
-    nfg, nbg = _dev(nfg, torch.int64), _dev(nbg, torch.int64)
-    flags = torch.empty(nfg.shape[0], dtype=u8, device=nfg.device)
-    check(lib().vu_cf_degenerate_flags(_p(nfg), _p(nbg), nfg.shape[0], int(fg_min), int(bg_min), _p(flags), _stream()))
+def count_gt_lt(x, thr, item_ndim=2):
+    """[n,2] int64: (#{x > thr}, #{x < thr}) per item, one pass."""
+    x = _dev(x)
+    n, per = _items(x, item_ndim)
+    out = torch.empty((n, 2), dtype=torch.int64, device=x.device)
+    check(lib().vu_count_gt_lt_u8(_p(x), n, per, int(thr), _p(out), _stream()))
+    return out
+
+
+def cf_degenerate_flags(masks, fg_min, bg_min):
+    """per-frame early-out flags of ColorFilteringAgent.forward from the segmentation masks"""
+    c = count_gt_lt(masks, 128)
+    n = c.shape[0]
+    flags = torch.empty(n, dtype=u8, device=c.device)
+    second = ctypes.c_void_p(c.data_ptr() + 8)
+    check(lib().vu_cf_degenerate_flags(_p(c), second, n, 2, int(fg_min), int(bg_min), _p(flags), _stream()))
     return flags
 
 
