@@ -303,6 +303,27 @@ def test_temporal_median_vs_oracle(vu, n):
     assert np.array_equal(vu.U.temporal_median(gaps), R.temporal_median(gaps))
 
 
+@pytest.mark.parametrize("n", [81, 82, 83, 152, 153, 232, 233, 240, 241, 299, 300, 303, 304, 305, 306, 307, 464, 465, 607, 608])
+def test_temporal_median_concentrated(vu, n):
+    """background-like data (the estimate + windowed search path of vu_median_sad.cuh): static background with small
+    temporal noise, occluded for a contiguous run of frames, including backgrounds at the ends of the uint8 range;
+    a few elements per warp with wide noise force the fall-back to the full search inside the same warp."""
+    rng = np.random.default_rng(1000 + n)
+    h, w = 16, 128
+    base = rng.integers(0, 256, (h, w, 3)).astype(np.int16)
+    base[0] = 0
+    base[1] = 255
+    base[2] = rng.integers(0, 12, (w, 3))
+    base[3] = rng.integers(244, 256, (w, 3))
+    frames = base[None] + rng.integers(-6, 7, (n, h, w, 3))
+    t0 = n // 5
+    frames[t0:t0 + (28 * n) // 100, 4:12, 10:90] = rng.integers(80, 240, ((28 * n) // 100, 8, 80, 3))   # occluder
+    frames[:, 8:, ::17] = base[None, 8:, ::17] + rng.integers(-40, 41, (n, h - 8, len(range(0, w, 17)), 3))  # wide noise
+    frames[:, 12:, 5] = np.where(rng.integers(0, 2, (n, h - 12, 3)) > 0, base[None, 12:, 5] + 1, base[None, 12:, 5])  # two adjacent values
+    frames = np.clip(frames, 0, 255).astype(np.uint8)
+    assert np.array_equal(vu.U.temporal_median(frames), R.temporal_median(frames))
+
+
 def test_temporal_median_properties_full_size(vu):
     """BASELINE config 2 size (300 x 1080p): size-independent properties.
     median of a clip whose frames are a permutation of values is order

@@ -1,0 +1,354 @@
+// Exact temporal median of up to 608 uint8 frames, data resident in registers
+// (new specification, no reference code).
+//
+// The median of x_1..x_n minimises the convex S(m) = sum_f |x_f - m|.
+// VABSDIFF4 with accumulate evaluates S for 4 frames of one element per
+// instruction, which makes "one probe of S" cost n/4 ALU-pipe instructions per
+// element, and the ALU pipe (64 lanes/clk/SM) is what bounds this kernel.  The
+// design goal is therefore the smallest number of probes:
+//
+//   stage A  every frame-part estimates the median from 16 of its frames
+//            (spread over the whole clip) by bisection on the slope of S:
+//            8 steps x 8 instructions per element;
+//   stage B  Fibonacci search of the 20 values around the estimate on ALL
+//            frames: 6 probes.  The bracket ends keep their S values, so the
+//            search ends knowing S at both neighbours of the minimiser: a
+//            strict minimum IS the median (odd n) / both middle order
+//            statistics (even n), with no further probe;
+//   even n   a neighbour with the same S belongs to the plateau [x_lo, x_hi]
+//            of minimisers: its end is walked one probe at a time (one probe
+//            for the usual plateau of two adjacent values), binary search for
+//            long plateaus;
+//   fallback if the minimiser of any element of the warp sits on the edge of
+//            its window (estimate off by more than 8), the whole warp repeats
+//            stage B over 0..255 (12 probes).  Always exact; only the speed
+//            depends on the data.
+//
+// Layout.  A warp owns SEG = 128/SPLIT consecutive bytes of every frame.  The
+// frames are dealt to SPLIT lane groups ("parts"): part p holds frames
+// f = SPLIT*i + p.  Lane l of a part holds its 4 bytes of all those frames: one
+// coalesced LDG.32 per frame, every load of the warp in flight at once.  Slot
+// (g, r) of a lane (register 4g+r) holds frame index i = r*Q + g with
+// Q = ceil(ceil(n/SPLIT)/4), so that after the 4x4 byte transposes register
+// 4g+j holds four frames of element j a quarter of the clip apart, and any few
+// groups form a sample spread over the whole clip.  Unused slots are padded
+// with 0 in one half of the parts and 255 in the other, which leaves the middle
+// order statistics where they are; when the two pad counts differ by one (odd
+// n) the surplus pad is taken out of S arithmetically (S += delta * m).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+namespace vu {
+namespace msad {
+
+__device__ __forceinline__ unsigned sad_acc(unsigned a, unsigned b, unsigned c) {
+  unsigned d;
+  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+// 4x4 byte transposes: d[4g+j] <- byte j of the four registers of group g
+template <int G>
+__device__ __forceinline__ void transpose_groups(unsigned (&d)[4 * G]) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const unsigned a = d[4 * g], b = d[4 * g + 1], c = d[4 * g + 2], e = d[4 * g + 3];
+    const unsigned ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);
+    const unsigned ce_lo = __byte_perm(c, e, 0x5140), ce_hi = __byte_perm(c, e, 0x7362);
+    d[4 * g] = __byte_perm(ab_lo, ce_lo, 0x5410);
+    d[4 * g + 1] = __byte_perm(ab_lo, ce_lo, 0x7632);
+    d[4 * g + 2] = __byte_perm(ab_hi, ce_hi, 0x5410);
+    d[4 * g + 3] = __byte_perm(ab_hi, ce_hi, 0x7632);
+  }
+}
+
+// ld.global.nc.u32 of [base + g * stride]: the 64-bit address is formed by ONE IMAD.WIDE.U32 with g as an immediate
+// (FMA pipe), which keeps the address arithmetic of the ~150 loads per lane off the ALU pipe that bounds the search
+template <int GI>
+__device__ __forceinline__ unsigned ldg_strided(const uint8_t* base, unsigned stride) {
+  unsigned long long addr;
+  unsigned v;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(stride), "n"(GI), "l"(base));
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(addr));
+  return v;
+}
+
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+constexpr unsigned BIG = 0x7fffffffu;
+constexpr unsigned FULL = 0xffffffffu;
+
+// S(m[j]) over all frames of the warp's segment for the 4 elements of the lane.
+// RANGE: probes outside 0..255 are allowed and evaluate to BIG.
+template <int SPLIT, int G, bool RANGE>
+__device__ __forceinline__ void eval_s(const unsigned (&d)[4 * G], const int (&m)[4], int delta, unsigned (&S)[4]) {
+  constexpr int LPS = 32 / SPLIT;
+  unsigned q[4], s[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    q[j] = (unsigned)(RANGE ? min(max(m[j], 0), 255) : m[j]) * 0x01010101u;
+    s[j] = 0;
+  }
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = sad_acc(d[4 * g + j], q[j], s[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int o = LPS; o < 32; o <<= 1) s[j] += __shfl_xor_sync(FULL, s[j], o);
+    s[j] += (unsigned)(delta * m[j]);
+    S[j] = (RANGE && (m[j] < 0 || m[j] > 255)) ? BIG : s[j];
+  }
+}
+
+// Fibonacci search of the interior points a+1 .. a+F(K0)-1 of the bracket
+// (a, a+F(K0)).  On return r is the minimiser among them, smin = S(r), and
+// sl / sr are S(r-1) / S(r+1), or BIG where that neighbour is the bracket's
+// original end (never evaluated).  2 + (K0 - 4) evaluations of S.
+template <int SPLIT, int G, bool RANGE>
+__device__ __forceinline__ void fib_search(const unsigned (&d)[4 * G], int delta, int k0, int fa, int fb, int fc, int (&a)[4], int (&r)[4],
+                                           unsigned (&smin)[4], unsigned (&sl)[4], unsigned (&sr)[4]) {
+  unsigned S1[4], S2[4];
+  {
+    int i1[4], i2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      i1[j] = a[j] + fb;
+      i2[j] = a[j] + fa;
+      sl[j] = sr[j] = BIG;
+    }
+    eval_s<SPLIT, G, RANGE>(d, i1, delta, S1);
+    eval_s<SPLIT, G, RANGE>(d, i2, delta, S2);
+  }
+#pragma unroll 1
+  for (int k = k0; k >= 5; --k) {
+    int nidx[4];
+    bool left[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      left[j] = S1[j] <= S2[j];
+      if (left[j]) {
+        sr[j] = S2[j];
+        S2[j] = S1[j];
+        nidx[j] = a[j] + fc;
+      } else {
+        sl[j] = S1[j];
+        a[j] += fb;
+        S1[j] = S2[j];
+        nidx[j] = a[j] + fb;
+      }
+    }
+    unsigned Sn[4];
+    eval_s<SPLIT, G, RANGE>(d, nidx, delta, Sn);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (left[j]) S1[j] = Sn[j];
+      else S2[j] = Sn[j];
+    }
+    const int t = fb - fc;
+    fa = fb;
+    fb = fc;
+    fc = t;
+  }
+  // k == 4: bracket (a, a+3), S1 = S(a+1), S2 = S(a+2)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (S1[j] <= S2[j]) {
+      r[j] = a[j] + 1;
+      smin[j] = S1[j];
+      sr[j] = S2[j];
+    } else {
+      r[j] = a[j] + 2;
+      smin[j] = S2[j];
+      sl[j] = S1[j];
+    }
+  }
+}
+
+// SS = stride of the 4 sample groups of stage A (0: no stage A, straight to the full search)
+template <int SPLIT, int G, int SS>
+__device__ __forceinline__ unsigned sad_median(const unsigned (&d)[4 * G], int n, int delta) {
+  int a[4], r[4];
+  unsigned smin[4], sl[4], sr[4];
+  bool full = (SS == 0);
+  if (SS > 0) {
+    // ---- stage A: lower median of 16 frames of this part, bisection on the slope of S ----
+    int est[4] = {0, 0, 0, 0};
+#pragma unroll 1
+    for (int bit = 128; bit > 0; bit >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned q1 = (unsigned)(est[j] | bit) * 0x01010101u, q0 = q1 - 0x01010101u;
+        unsigned s0 = 0, s1 = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          s0 = sad_acc(d[4 * (t * SS) + j], q0, s0);
+          s1 = sad_acc(d[4 * (t * SS) + j], q1, s1);
+        }
+        if (s1 < s0) est[j] |= bit;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int o = 32 / SPLIT; o < 32; o <<= 1) est[j] += __shfl_xor_sync(FULL, est[j], o);
+      a[j] = min(max((est[j] + SPLIT / 2) / SPLIT - 10, -1), 235);   // interior a+1 .. a+20 within 0..255
+    }
+    // ---- stage B: the 20 values around the estimate ----
+    fib_search<SPLIT, G, false>(d, delta, 8, 13, 8, 5, a, r, smin, sl, sr);
+    bool fail = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) fail |= (sl[j] == BIG && r[j] > 0) || (sr[j] == BIG && r[j] < 255);
+    full = __any_sync(FULL, fail);
+  }
+  if (full) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = -1;
+    fib_search<SPLIT, G, true>(d, delta, 14, 233, 144, 89, a, r, smin, sl, sr);   // interior -1+1 .. 375: covers 0..255
+  }
+  int lo[4], hi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) lo[j] = hi[j] = r[j];
+  if (!(n & 1)) {
+    // even n: minimisers form the plateau [x_lo, x_hi]
+    bool openL[4], openR[4];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      openL[j] = openR[j] = false;
+      if (sl[j] == smin[j]) { lo[j] = r[j] - 1; openL[j] = lo[j] > 0; }
+      if (sr[j] == smin[j]) { hi[j] = r[j] + 1; openR[j] = hi[j] < 255; }
+      any |= openL[j] | openR[j];
+    }
+    // walk the open ends, one probe per lane and round
+#pragma unroll 1
+    for (int it = 0; it < 4 && __any_sync(FULL, any); ++it) {
+      int idx[4];
+      unsigned S[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) idx[j] = openL[j] ? lo[j] - 1 : (openR[j] ? hi[j] + 1 : r[j]);
+      eval_s<SPLIT, G, false>(d, idx, delta, S);
+      any = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (openL[j]) {
+          if (S[j] == smin[j]) { --lo[j]; openL[j] = lo[j] > 0; }
+          else openL[j] = false;
+        } else if (openR[j]) {
+          if (S[j] == smin[j]) { ++hi[j]; openR[j] = hi[j] < 255; }
+          else openR[j] = false;
+        }
+        any |= openL[j] | openR[j];
+      }
+    }
+    // long plateaus (e.g. two-valued data): binary search for the ends (S == smin is monotone on either side)
+    if (__any_sync(FULL, any)) {
+      int L[4], R[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { R[j] = lo[j]; L[j] = openL[j] ? 0 : lo[j]; }
+      while (__any_sync(FULL, (L[0] < R[0]) | (L[1] < R[1]) | (L[2] < R[2]) | (L[3] < R[3]))) {
+        int idx[4];
+        unsigned S[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = (L[j] + R[j]) >> 1;
+        eval_s<SPLIT, G, false>(d, idx, delta, S);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (L[j] < R[j]) {
+            const int mid = (L[j] + R[j]) >> 1;
+            if (S[j] == smin[j]) R[j] = mid;
+            else L[j] = mid + 1;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { lo[j] = R[j]; L[j] = hi[j]; R[j] = openR[j] ? 255 : hi[j]; }
+      while (__any_sync(FULL, (L[0] < R[0]) | (L[1] < R[1]) | (L[2] < R[2]) | (L[3] < R[3]))) {
+        int idx[4];
+        unsigned S[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) idx[j] = (L[j] + R[j] + 1) >> 1;
+        eval_s<SPLIT, G, false>(d, idx, delta, S);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (L[j] < R[j]) {
+            const int mid = (L[j] + R[j] + 1) >> 1;
+            if (S[j] == smin[j]) L[j] = mid;
+            else R[j] = mid - 1;
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) hi[j] = L[j];
+    }
+  }
+  unsigned res = 0;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) res |= (unsigned)((lo[j] + hi[j]) >> 1) << (8 * j);
+  return res;
+}
+
+// pads: 0 in parts {0} (SPLIT 2) / {0,3} (SPLIT 4), 255 in the others: the two pad counts differ by at most one
+template <int SPLIT>
+__device__ __forceinline__ bool pad_high(int part) { return SPLIT == 2 ? part == 1 : (part == 1 || part == 2); }
+
+// GFULL: groups whose rows 0..2 hold real frames for every n the variant is dispatched for (no bounds test on those loads).
+// SPLIT * m must fit 32 bits.
+template <int SPLIT, int G, int GFULL, int SS, int CTAS>
+__global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
+                                                               int nseg, unsigned zero) {
+  constexpr int LPS = 32 / SPLIT;  // lanes per frame-part
+  constexpr int SEG = LPS * 4;     // bytes of a frame one warp owns
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane / LPS, li = lane % LPS;
+  const int seg = blockIdx.x * 4 + warp;
+  if (seg >= nseg) return;
+  const int cnt0 = (n + SPLIT - 1) / SPLIT;          // frames of part 0 (the largest part)
+  const int cnt = (n - part + SPLIT - 1) / SPLIT;    // frames of this part
+  const int Q = (cnt0 + 3) >> 2;
+  const unsigned pad = pad_high<SPLIT>(part) ? 0xFFFFFFFFu : 0u;
+  // surplus of 255-pads over 0-pads (-1, 0 or +1), taken out of S arithmetically
+  int n0 = 0, n255 = 0;
+#pragma unroll
+  for (int p = 0; p < SPLIT; ++p) {
+    const int c = 4 * G - (n - p + SPLIT - 1) / SPLIT;
+    if (pad_high<SPLIT>(p)) n255 += c;
+    else n0 += c;
+  }
+  const int delta = n255 - n0;
+  // frame i of this part starts (SPLIT*i + part) * m bytes into the clip; slot (g, r) holds i = r*Q + g
+  // (`zero` is 0: it gives every row its own copy of the stride, or the compiler shares g * stride between the
+  // rows and goes back to 64-bit adds on the ALU pipe)
+  unsigned gstride[4];
+  const uint8_t* rowbase[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    rowbase[r] = frames + (long long)seg * SEG + li * 4 + ((long long)SPLIT * (r * Q) + part) * m;
+    gstride[r] = (unsigned)(SPLIT * m) + (unsigned)r * zero;
+  }
+  unsigned d[4 * G];
+  static_for<0, G>([&](auto gi) {
+    constexpr int g = decltype(gi)::value;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const bool ok = (r < 3 && g < GFULL) ? true : (g < Q && r * Q + g < cnt);
+      d[4 * g + r] = pad;
+      if (ok) d[4 * g + r] = ldg_strided<g>(rowbase[r], gstride[r]);
+    }
+  });
+  transpose_groups<G>(d);
+  const unsigned res = sad_median<SPLIT, G, SS>(d, n, delta);
+  if (part == 0) reinterpret_cast<unsigned*>(out + (long long)seg * SEG)[li] = res;
+}
+
+}  // namespace msad
+}  // namespace vu

@@ -27,6 +27,7 @@
 // vu_masked_temporal_mean: tools/unscreen/bg_offline.py:106-125 as integer
 // sums and counts per pixel, one float64 divide at the end.
 #include "vu_common.cuh"
+#include "vu_median_sad.cuh"
 
 namespace vu {
 namespace {
@@ -140,247 +141,10 @@ __global__ void __launch_bounds__(MTHREADS, 1) median_kernel(const uint8_t* __re
   }
 }
 
-// ---- register-resident SAD search ------------------------------------------
-__device__ __forceinline__ unsigned sad_acc(unsigned a, unsigned b, unsigned c) {
-  unsigned d;
-  asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
-  return d;
-}
-
-// frames of one element are split over SPLIT lane groups ("parts").  Parts on
-// the low side (part < SPLIT/2) pad their unused slots with 0, parts on the
-// high side with 255, and the surplus frames go to the sides alternately, so
-// the padded multiset keeps the data's middle order statistics.
-template <int SPLIT>
-__device__ __forceinline__ void part_frames(int n, int part, int& f_begin, int& f_cnt) {
-  const int base = n / SPLIT, rem = n % SPLIT;
-  if (SPLIT == 4) {
-    // surplus order: parts 0, 2, 1, 3
-    const int c0 = base + (rem > 0), c1 = base + (rem > 2), c2 = base + (rem > 1), c3 = base;
-    f_cnt = part == 0 ? c0 : (part == 1 ? c1 : (part == 2 ? c2 : c3));
-    f_begin = part == 0 ? 0 : (part == 1 ? c0 : (part == 2 ? c0 + c1 : c0 + c1 + c2));
-  } else {
-    f_cnt = base + (part < rem ? 1 : 0);
-    f_begin = part * base + min(part, rem);
-  }
-}
-
-// 4x4 byte transposes: d[4g+j] <- 4 consecutive frame slots of element j
-template <int G>
-__device__ __forceinline__ void transpose_groups(unsigned (&d)[4 * G]) {
-#pragma unroll
-  for (int g = 0; g < G; ++g) {
-    const unsigned a = d[4 * g], b = d[4 * g + 1], c = d[4 * g + 2], e = d[4 * g + 3];
-    const unsigned ab_lo = __byte_perm(a, b, 0x5140), ab_hi = __byte_perm(a, b, 0x7362);
-    const unsigned ce_lo = __byte_perm(c, e, 0x5140), ce_hi = __byte_perm(c, e, 0x7362);
-    d[4 * g] = __byte_perm(ab_lo, ce_lo, 0x5410);
-    d[4 * g + 1] = __byte_perm(ab_lo, ce_lo, 0x7632);
-    d[4 * g + 2] = __byte_perm(ab_hi, ce_hi, 0x5410);
-    d[4 * g + 3] = __byte_perm(ab_hi, ce_hi, 0x7632);
-  }
-}
-
-// The median minimises the convex S(m) = sum_f |x_f - m| (one VABSDIFF4.ACC per
-// 4 frames per probe).  Fibonacci search over m = 0..255 needs 12 evaluations
-// of S per element (each round re-uses one of its two probes).  For odd n one
-// high-side pad "floats" (it is overwritten with the probe itself and so adds
-// nothing): the minimiser is unique and is the median.  For even n the
-// minimisers form the plateau [x_lo, x_hi] of the two middle order statistics;
-// its ends are found by probing outwards (S(m) == S_min is monotone on either
-// side), a few linear steps first, binary search for pathological plateaus.
-template <int SPLIT, int G>
-__device__ __forceinline__ unsigned sad_search(const unsigned (&d)[4 * G], int n, int part) {
-  constexpr int LPS = 32 / SPLIT;
-  constexpr unsigned INF = 0x7fffffffu;
-  constexpr unsigned FULL = 0xffffffffu;
-  const unsigned fmask = ((n & 1) && part == SPLIT - 1) ? 0xFF000000u : 0u;
-  // idx = m + 1 (the search runs on indices 1..376; m > 255 evaluates to +inf)
-  auto evalS = [&](const int(&idx)[4], unsigned(&S)[4]) {
-    unsigned q[4], s[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      q[j] = (unsigned)min(max(idx[j] - 1, 0), 255) * 0x01010101u;
-      s[j] = 0;
-    }
-#pragma unroll
-    for (int g = 0; g < G - 1; ++g) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s[j] = sad_acc(d[4 * g + j], q[j], s[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const unsigned w = (d[4 * (G - 1) + j] & ~fmask) | (q[j] & fmask);
-      s[j] = sad_acc(w, q[j], s[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int o = LPS; o < 32; o <<= 1) s[j] += __shfl_xor_sync(FULL, s[j], o);
-      S[j] = (idx[j] < 1 || idx[j] > 256) ? INF : s[j];
-    }
-  };
-  int a[4] = {0, 0, 0, 0};
-  unsigned S1[4], S2[4];
-  int fa = 233, fb = 144, fc = 89;  // F(k-1), F(k-2), F(k-3) for k = 14
-  {
-    int i1[4], i2[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { i1[j] = fb; i2[j] = fa; }
-    evalS(i1, S1);
-    evalS(i2, S2);
-  }
-#pragma unroll 1
-  for (int k = 14; k >= 5; --k) {
-    int nidx[4];
-    bool left[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      left[j] = S1[j] <= S2[j];
-      if (left[j]) {
-        S2[j] = S1[j];
-        nidx[j] = a[j] + fc;
-      } else {
-        a[j] += fb;
-        S1[j] = S2[j];
-        nidx[j] = a[j] + fb;
-      }
-    }
-    unsigned Sn[4];
-    evalS(nidx, Sn);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (left[j]) S1[j] = Sn[j];
-      else S2[j] = Sn[j];
-    }
-    const int t = fb - fc;
-    fa = fb; fb = fc; fc = t;
-  }
-  int lo[4], hi[4];
-  unsigned Smin[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const bool left = S1[j] <= S2[j];
-    lo[j] = hi[j] = (left ? a[j] + fb : a[j] + fa) - 1;
-    Smin[j] = left ? S1[j] : S2[j];
-  }
-  if (!(n & 1)) {
-    bool actL[4], actR[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { actL[j] = lo[j] > 0; actR[j] = hi[j] < 255; }
-#pragma unroll 1
-    for (int it = 0; it < 3; ++it) {
-      const bool anyL = actL[0] | actL[1] | actL[2] | actL[3];
-      if (__any_sync(FULL, anyL)) {
-        int idx[4];
-        unsigned S[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = lo[j];  // m = lo - 1
-        evalS(idx, S);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (actL[j]) {
-            if (S[j] == Smin[j]) { --lo[j]; actL[j] = lo[j] > 0; }
-            else actL[j] = false;
-          }
-      }
-      const bool anyR = actR[0] | actR[1] | actR[2] | actR[3];
-      if (__any_sync(FULL, anyR)) {
-        int idx[4];
-        unsigned S[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = hi[j] + 2;  // m = hi + 1
-        evalS(idx, S);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (actR[j]) {
-            if (S[j] == Smin[j]) { ++hi[j]; actR[j] = hi[j] < 255; }
-            else actR[j] = false;
-          }
-      }
-    }
-    // plateaus longer than 3 on a side (e.g. two-valued data): binary search for the end
-    if (__any_sync(FULL, actL[0] | actL[1] | actL[2] | actL[3])) {
-      int L[4], R[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { R[j] = lo[j]; L[j] = actL[j] ? 0 : lo[j]; }
-      while (__any_sync(FULL, (L[0] < R[0]) | (L[1] < R[1]) | (L[2] < R[2]) | (L[3] < R[3]))) {
-        int idx[4];
-        unsigned S[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = ((L[j] + R[j]) >> 1) + 1;
-        evalS(idx, S);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (L[j] < R[j]) {
-            const int mid = (L[j] + R[j]) >> 1;
-            if (S[j] == Smin[j]) R[j] = mid;
-            else L[j] = mid + 1;
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) lo[j] = R[j];
-    }
-    if (__any_sync(FULL, actR[0] | actR[1] | actR[2] | actR[3])) {
-      int L[4], R[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { L[j] = hi[j]; R[j] = actR[j] ? 255 : hi[j]; }
-      while (__any_sync(FULL, (L[0] < R[0]) | (L[1] < R[1]) | (L[2] < R[2]) | (L[3] < R[3]))) {
-        int idx[4];
-        unsigned S[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) idx[j] = ((L[j] + R[j] + 1) >> 1) + 1;
-        evalS(idx, S);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (L[j] < R[j]) {
-            const int mid = (L[j] + R[j] + 1) >> 1;
-            if (S[j] == Smin[j]) L[j] = mid;
-            else R[j] = mid - 1;
-          }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) hi[j] = L[j];
-    }
-  }
-  unsigned res = 0;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) res |= (unsigned)((lo[j] + hi[j]) >> 1) << (8 * j);
-  return res;
-}
-
-// GMIN = register groups that are full for every n the variant is dispatched for (no bounds test on those loads)
-template <int SPLIT, int G, int GMIN, int CTAS>
-__global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
-                                                               int nseg) {
-  constexpr int LPS = 32 / SPLIT;  // lanes per frame-part
-  constexpr int SEG = LPS * 4;     // bytes of a frame one warp owns
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int part = lane / LPS, li = lane % LPS;
-  const int seg = blockIdx.x * 4 + warp;
-  if (seg >= nseg) return;
-  int f_begin, f_cnt;
-  part_frames<SPLIT>(n, part, f_begin, f_cnt);
-  const unsigned pad = part >= SPLIT / 2 ? 0xFFFFFFFFu : 0u;
-  const uint8_t* p = frames + (long long)seg * SEG + li * 4 + (long long)f_begin * m;
-  unsigned d[4 * G];
-#pragma unroll
-  for (int k = 0; k < 4 * GMIN; ++k) {
-    d[k] = __ldg(reinterpret_cast<const unsigned*>(p));
-    p += m;
-  }
-#pragma unroll
-  for (int k = 4 * GMIN; k < 4 * G; ++k) {
-    d[k] = (k < f_cnt) ? __ldg(reinterpret_cast<const unsigned*>(p)) : pad;
-    p += m;
-  }
-  transpose_groups<G>(d);
-  const unsigned res = sad_search<SPLIT, G>(d, n, part);
-  if (part == 0) reinterpret_cast<unsigned*>(out + (long long)seg * SEG)[li] = res;
-}
-
-template <int SPLIT, int G, int GMIN, int CTAS>
+// ---- register-resident SAD search: vu_median_sad.cuh ------------------------
+template <int SPLIT, int G, int GFULL, int SS, int CTAS>
 int launch_median_sad(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream) {
-  median_sad_kernel<SPLIT, G, GMIN, CTAS><<<(unsigned)((nseg + 3) / 4), 128, 0, S(stream)>>>(frames, out, n, m, (int)nseg);
+  msad::median_sad_kernel<SPLIT, G, GFULL, SS, CTAS><<<(unsigned)((nseg + 3) / 4), 128, 0, S(stream)>>>(frames, out, n, m, (int)nseg, 0u);
   note_launch();
   return record_cuda(cudaGetLastError());
 }
@@ -487,8 +251,9 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
   if (n < 1 || n > 65535) return VU_ERR_UNSUPPORTED;
   if (m == 0) return VU_OK;
   // path: 0 = SAD search, half-warp split (n <= 304); 1 = SAD search, quarter-warp split (n <= 608);
-  //       2 = shared-memory histograms with 16-bit counters
-  const int path = n <= 304 ? 0 : (n <= 608 ? 1 : 2);
+  //       2 = shared-memory histograms with 16-bit counters.  The SAD kernels keep the frame stride in 32 bits.
+  const bool fits32 = m < (1ll << 30);
+  const int path = (n <= 304 && fits32) ? 0 : ((n <= 608 && fits32) ? 1 : 2);
   const int seg = path == 0 ? 64 : (path == 1 ? 32 : 64);
   const int align = path == 2 ? 2 : 4;
   // vector paths need element-aligned frame rows
@@ -497,17 +262,19 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
   if (nseg > 0x7fffffff) return VU_ERR_UNSUPPORTED;
   if (nseg > 0) {
     int e;
-    // G = register groups of 4 frames per lane: the smallest variant that holds ceil(n / SPLIT) frames;
-    // GMIN = groups every lane fills for the whole n-range of the variant
+    // <SPLIT, G, GFULL, SS, CTAs/SM>: G = register groups of 4 frames per lane, the smallest variant that holds
+    // ceil(n / SPLIT) frames; GFULL = groups whose first three rows are real frames over the whole n-range of the
+    // variant; SS = stride of the four sample groups of the estimate (all real frames over the n-range)
     if (path == 0) {
-      if (n <= 80) e = launch_median_sad<2, 10, 0, 4>(frames, n, m, nseg, out, stream);
-      else if (n <= 152) e = launch_median_sad<2, 19, 10, 4>(frames, n, m, nseg, out, stream);
-      else if (n <= 232) e = launch_median_sad<2, 29, 19, 2>(frames, n, m, nseg, out, stream);
-      else e = launch_median_sad<2, 38, 29, 2>(frames, n, m, nseg, out, stream);
+      if (n <= 80) e = launch_median_sad<2, 10, 0, 0, 4>(frames, n, m, nseg, out, stream);
+      else if (n <= 152) e = launch_median_sad<2, 19, 11, 2, 4>(frames, n, m, nseg, out, stream);
+      else if (n <= 232) e = launch_median_sad<2, 29, 20, 5, 2>(frames, n, m, nseg, out, stream);
+      else e = launch_median_sad<2, 38, 30, 8, 2>(frames, n, m, nseg, out, stream);
     } else if (path == 1) {
-      e = n <= 464 ? launch_median_sad<4, 29, 19, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<4, 38, 29, 2>(frames, n, m, nseg, out, stream);
+      e = n <= 464 ? launch_median_sad<4, 29, 20, 5, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<4, 38, 30, 8, 2>(frames, n, m, nseg, out, stream);
+    } else {
+      e = launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
     }
-    else e = launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
     if (e) return e;
   }
   const int64_t first = nseg * seg;
