@@ -36,6 +36,7 @@
 // order statistics where they are; when the two pad counts differ by one (odd
 // n) the surplus pad is taken out of S arithmetically (S += delta * m).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -348,6 +349,213 @@ __global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __
   transpose_groups<G>(d);
   const unsigned res = sad_median<SPLIT, G, SS>(d, n, delta);
   if (part == 0) reinterpret_cast<unsigned*>(out + (long long)seg * SEG)[li] = res;
+}
+
+
+// ---- persistent tile variant: the next tile streams into shared memory while the current one is searched ----
+//
+// Measured on the B200 (tools/ldgsts_ubench.cu): fetching "one row per frame" runs at 2.8 TB/s when a warp fetches
+// 64-byte rows on its own, 5.9 TB/s with 128-byte rows and 7.2 TB/s when the 8 warps of a CTA fetch 512-byte rows
+// together: the width that is contiguous per request decides the memory throughput, not the bytes in flight.
+//
+// A CTA of TILE_WARPS warps walks tiles of TILE_WARPS adjacent segments (8 warps, SPLIT 2: 512 bytes of every frame).  Every warp
+// still owns one segment and a private shared-memory buffer of 4G slots x 128 bytes (slot k = 4g + r holds the SEG
+// bytes of part 0's frame, then part 1's, ...: lane l reads its word at l*4 + k*128, conflict-free), but the copies
+// are dealt by frame: warp w copies the frames of the groups g = w, w+8, ... for ALL eight segments, one cp.async.cg
+// instruction (16 bytes per lane) per 512-byte frame row.  Per tile: wait for the copies, barrier, move the buffer
+// to registers (LDS with immediate offsets), transpose, barrier, issue the copies of the NEXT tile, search.  The
+// loads of a tile are in flight during the whole search of the previous one.  Pad slots are written once at kernel
+// start and never copied over.  Needs 16-byte aligned frame rows (frames % 16 == 0, m % 16 == 0).
+__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int SPLIT, int G, int SS, int TILE_WARPS, int CTAS>
+__global__ void __launch_bounds__(TILE_WARPS * 32, CTAS) median_sad_tile_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n,
+                                                                             long long m, int ntiles, unsigned zero) {
+  extern __shared__ __align__(128) uint8_t smem_tile[];
+  constexpr int LPS = 32 / SPLIT;            // lanes per frame-part
+  constexpr int SEG = LPS * 4;               // bytes of a frame one warp owns
+  constexpr int TILE = TILE_WARPS * SEG;     // bytes of a frame one CTA owns
+  constexpr int CPR = SEG / 16;              // 16-byte chunks per segment row
+  constexpr int CPT = TILE / 16;             // chunks per tile row
+  constexpr int RPI = 32 / CPT;              // tile rows per copy instruction
+  constexpr int IPG = 4 * SPLIT / RPI;       // copy instructions per group of four slots
+  static_assert(RPI >= 1 && RPI <= 4 * SPLIT, "a copy instruction must stay within one group");
+  constexpr int BUF = 4 * G * 128;           // bytes of one warp's buffer
+  constexpr int T = (G + TILE_WARPS - 1) / TILE_WARPS;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane / LPS, li = lane % LPS;
+  const int cnt0 = (n + SPLIT - 1) / SPLIT;
+  const int Q = (cnt0 + 3) >> 2;
+  int n0 = 0, n255 = 0;
+#pragma unroll
+  for (int p = 0; p < SPLIT; ++p) {
+    const int c = 4 * G - (n - p + SPLIT - 1) / SPLIT;
+    if (pad_high<SPLIT>(p)) n255 += c;
+    else n0 += c;
+  }
+  const int delta = n255 - n0;
+  uint8_t* buf = smem_tile + warp * BUF;
+  {
+    // pads: chunk c of a 128-byte slot belongs to part c / CPR
+    const unsigned v = pad_high<SPLIT>((lane & 7) / CPR) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+    for (int g = 0; g < G; ++g) *reinterpret_cast<uint4*>(buf + g * 512 + lane * 16) = make_uint4(v, v, v, v);
+  }
+  // copy role of this lane: tile row ri of the instruction, chunk ci of the row = chunk wc of warp wd's segment.
+  // Instruction ii (0..IPG-1) of a group copies the rows j = ii*RPI + ri of the group's 4*SPLIT rows: slot row
+  // r = j / SPLIT = r_ct(ii) + r_lane, part p = j % SPLIT = p_ct(ii) + p_lane
+  const int ri = lane / CPT, ci = lane % CPT;
+  const int wd = ci / CPR, wc = ci % CPR;
+  const int r_lane = RPI > SPLIT ? ri / SPLIT : 0;
+  const int p_lane = RPI > SPLIT ? ri % SPLIT : ri;
+  const unsigned dst0 = (unsigned)__cvta_generic_to_shared(smem_tile) + wd * BUF + wc * 16 + r_lane * 128 + p_lane * SEG + warp * 512;
+  const unsigned m32 = (unsigned)m + zero;
+  const uint8_t* rowbase[IPG];
+  int tlim[IPG];   // this warp copies the groups g = warp + TILE_WARPS t, t < tlim[ii], with instruction ii
+#pragma unroll
+  for (int ii = 0; ii < IPG; ++ii) {
+    const int r = (RPI > SPLIT ? ii * (RPI / SPLIT) : (ii * RPI) / SPLIT) + r_lane;
+    const int p_ct = RPI > SPLIT ? 0 : (ii * RPI) % SPLIT;
+    const int p = p_ct + p_lane;
+    rowbase[ii] = frames + ci * 16 + ((long long)SPLIT * (r * Q + warp) + p_lane) * m;   // p_ct goes into the immediate
+    const int glim = min(Q, (n - p + SPLIT - 1) / SPLIT - r * Q);   // groups g < glim of (slot row r, part p) hold real frames
+    tlim[ii] = glim > warp ? (glim - warp + TILE_WARPS - 1) / TILE_WARPS : 0;
+  }
+  auto issue = [&](int tile) {
+    const long long toff = (long long)tile * TILE;
+    static_for<0, T>([&](auto ti) {
+      constexpr int t = decltype(ti)::value;
+      static_for<0, IPG>([&](auto iii) {
+        constexpr int ii = decltype(iii)::value;
+        constexpr int r_ct = RPI > SPLIT ? ii * (RPI / SPLIT) : (ii * RPI) / SPLIT;
+        constexpr int p_ct = RPI > SPLIT ? 0 : (ii * RPI) % SPLIT;
+        if (t < tlim[ii]) {
+          unsigned long long addr;
+          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(m32), "n"(TILE_WARPS * SPLIT * t + p_ct), "l"(rowbase[ii] + toff));
+          cp_async16(dst0 + t * (TILE_WARPS * 512) + r_ct * 128 + p_ct * SEG, reinterpret_cast<const void*>(addr));
+        }
+      });
+    });
+    cp_async_commit();
+  };
+  int tile = blockIdx.x;
+  if (tile < ntiles) issue(tile);
+  for (; tile < ntiles; tile += gridDim.x) {
+    cp_async_wait_all();
+    __syncthreads();   // the copies of every warp have landed (and, first time round, the pads)
+    unsigned d[4 * G];
+#pragma unroll
+    for (int k = 0; k < 4 * G; ++k) d[k] = *reinterpret_cast<const unsigned*>(buf + lane * 4 + k * 128);
+    transpose_groups<G>(d);   // consumes every load
+    __syncthreads();   // every warp has emptied its buffer
+    if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
+    const unsigned res = sad_median<SPLIT, G, SS>(d, n, delta);
+    if (part == 0) reinterpret_cast<unsigned*>(out + ((long long)tile * TILE_WARPS + warp) * SEG)[li] = res;
+  }
+}
+
+// ---- TMA variant of the tile kernel -----------------------------------------------------------------------------
+//
+// Same tiles and the same search, but the tile is fetched by the TMA unit: the clip is described to it as a 2-D
+// uint8 tensor [n frames][m bytes], and SPLIT boxes of {TILE bytes x 4G frames} (cp.async.bulk.tensor.2d, one elected
+// thread, completion counted in bytes on an mbarrier) bring "TILE contiguous bytes of every frame" into shared
+// memory as rows of TILE bytes: full 128-byte lines per request, no address arithmetic and no load instructions in
+// the warps.  Frames past the end of the clip are zero-filled by the unit: pads are all 0 here and leave S through
+// delta = -(number of pads).  The warps are only loosely coupled: a warp waits for the tile on the mbarrier, moves its
+// segment to registers and transposes, bumps a counter and goes searching; the warp that bumps it last knows the
+// buffer is free and launches the fetch of the next tile, which then lands while everybody searches.
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void* tmap, int c0, int c1, unsigned mbar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tmap),
+               "r"(c0), "r"(c1), "r"(mbar)
+               : "memory");
+}
+
+// GQ: groups g < GQ are below Q = ceil(ceil(n/SPLIT)/4) for every n the variant is dispatched for
+template <int SPLIT, int G, int GQ, int SS, int WARPS, int CTAS>
+__global__ void __launch_bounds__(WARPS * 32, CTAS) median_sad_tma_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ out, int n,
+                                                                          int ntiles) {
+  extern __shared__ __align__(128) uint8_t smem_tma[];
+  constexpr int LPS = 32 / SPLIT;
+  constexpr int SEG = LPS * 4;
+  constexpr int TILE = WARPS * SEG;          // bytes of a frame one CTA owns = pitch of the rows in shared memory
+  constexpr int ROWS = SPLIT * 4 * G;        // rows of the buffer (frames, the last ones past the clip)
+  constexpr unsigned BOX_BYTES = 4 * G * TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane / LPS, li = lane % LPS;
+  const int cnt0 = (n + SPLIT - 1) / SPLIT;
+  const int Q = (cnt0 + 3) >> 2;
+  const int delta = -(ROWS - n);
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem_tma + ROWS * TILE);
+  unsigned* count_p = reinterpret_cast<unsigned*>(mbar_p + 1);
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(mbar_p);
+  const unsigned sdata = (unsigned)__cvta_generic_to_shared(smem_tma);
+  auto fetch = [&](int tile) {   // one thread
+    mbar_expect_tx(mbar, SPLIT * BOX_BYTES);
+#pragma unroll
+    for (int b = 0; b < SPLIT; ++b) tma_load_2d(sdata + b * BOX_BYTES, &tmap, tile * TILE, b * 4 * G, mbar);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(mbar, 1);
+    *count_p = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  int tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < ntiles) fetch(tile);
+  // slot (g, r) of this lane: frame SPLIT*(r*Q + g) + part, row pitch TILE
+  const uint8_t* rowaddr[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) rowaddr[r] = smem_tma + (SPLIT * (r * Q) + part) * TILE + warp * SEG + li * 4;
+  unsigned parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    mbar_wait(mbar, parity);
+    parity ^= 1;
+    unsigned d[4 * G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        d[4 * g + r] = 0;
+        if (g < GQ || g < Q) d[4 * g + r] = *reinterpret_cast<const unsigned*>(rowaddr[r] + g * (SPLIT * TILE));
+      }
+    }
+    transpose_groups<G>(d);   // consumes every load
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const unsigned old = atomicAdd(count_p, 1u);
+      if (old % WARPS == WARPS - 1 && tile + (int)gridDim.x < ntiles) {
+        __threadfence_block();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        fetch(tile + gridDim.x);
+      }
+    }
+    const unsigned res = sad_median<SPLIT, G, SS>(d, n, delta);
+    if (part == 0) reinterpret_cast<unsigned*>(out + ((long long)tile * WARPS + warp) * SEG)[li] = res;
+  }
 }
 
 }  // namespace msad

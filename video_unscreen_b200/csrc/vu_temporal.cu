@@ -26,6 +26,8 @@
 //
 // vu_masked_temporal_mean: tools/unscreen/bg_offline.py:106-125 as integer
 // sums and counts per pixel, one float64 divide at the end.
+#include <cstdlib>
+
 #include "vu_common.cuh"
 #include "vu_median_sad.cuh"
 
@@ -149,6 +151,72 @@ int launch_median_sad(const uint8_t* frames, int n, int64_t m, int64_t nseg, uin
   return record_cuda(cudaGetLastError());
 }
 
+constexpr int TILE_WARPS = 2, TILE_CTAS = 4;   // warps per tile CTA (= segments per tile), CTAs per SM
+template <int SPLIT, int G, int SS>
+int launch_median_sad_tile(const uint8_t* frames, int n, int64_t m, int64_t ntiles, uint8_t* out, vu_stream_t stream) {
+  constexpr int SMEM = TILE_WARPS * 4 * G * 128;
+  auto kernel = msad::median_sad_tile_kernel<SPLIT, G, SS, TILE_WARPS, TILE_CTAS>;
+  static bool configured = false;
+  if (!configured) {
+    int e = record_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (e) return e;
+    configured = true;
+  }
+  const int64_t cap = (int64_t)device_sms() * TILE_CTAS;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+  kernel<<<grid, TILE_WARPS * 32, SMEM, S(stream)>>>(frames, out, n, m, (int)ntiles, 0u);
+  note_launch();
+  return record_cuda(cudaGetLastError());
+}
+
+// TMA tile kernels: the clip as a 2-D uint8 tensor [n][m], boxes of {TILE bytes, 4G frames}
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+constexpr int TMA_WARPS = 4, TMA_CTAS = 2;
+template <int SPLIT, int G, int GQ, int SS>
+int launch_median_sad_tma(const uint8_t* frames, int n, int64_t m, int64_t ntiles, uint8_t* out, vu_stream_t stream) {
+  constexpr int TILE = TMA_WARPS * (128 / SPLIT);
+  constexpr int SMEM = SPLIT * 4 * G * TILE + 16;
+  static_assert(TILE <= 256 && 4 * G <= 256, "TMA box limits");
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return VU_ERR_UNSUPPORTED;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)m};
+  const cuuint32_t box[2] = {(cuuint32_t)TILE, (cuuint32_t)(4 * G)};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return VU_ERR_UNSUPPORTED;
+  auto kernel = msad::median_sad_tma_kernel<SPLIT, G, GQ, SS, TMA_WARPS, TMA_CTAS>;
+  static bool configured = false;
+  if (!configured) {
+    int e = record_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (e) return e;
+    configured = true;
+  }
+  const int64_t cap = (int64_t)device_sms() * TMA_CTAS;
+  const int grid = (int)(ntiles < cap ? ntiles : cap);
+  kernel<<<grid, TMA_WARPS * 32, SMEM, S(stream)>>>(tmap, out, n, (int)ntiles);
+  note_launch();
+  return record_cuda(cudaGetLastError());
+}
+
 // elements that do not fill a whole segment (and unaligned inputs): one CTA
 // per element, 256-bin shared histogram
 __global__ void __launch_bounds__(256) median_tail_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
@@ -246,6 +314,12 @@ int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t
 
 using namespace vu;
 
+// development switch (VU_MEDIAN_MODE): 0 = TMA tile kernels, 1 = cp.async tile kernels, 2 = direct kernels only
+static const int g_median_mode = [] {
+  const char* e = getenv("VU_MEDIAN_MODE");
+  return e ? atoi(e) : 0;
+}();
+
 extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream) {
   VU_REQUIRE(frames && out && m >= 0);
   if (n < 1 || n > 65535) return VU_ERR_UNSUPPORTED;
@@ -260,12 +334,43 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
   const bool ok = (reinterpret_cast<uintptr_t>(frames) % align == 0) && (reinterpret_cast<uintptr_t>(out) % align == 0) && (m % align == 0);
   int64_t nseg = ok ? m / seg : 0;
   if (nseg > 0x7fffffff) return VU_ERR_UNSUPPORTED;
+  int64_t tiled = 0;   // bytes of every frame done by the tile kernels (frames / out are advanced past them)
   if (nseg > 0) {
     int e;
     // <SPLIT, G, GFULL, SS, CTAs/SM>: G = register groups of 4 frames per lane, the smallest variant that holds
     // ceil(n / SPLIT) frames; GFULL = groups whose first three rows are real frames over the whole n-range of the
     // variant; SS = stride of the four sample groups of the estimate (all real frames over the n-range)
-    if (path == 0) {
+    // 16-byte aligned rows: persistent tile kernels (8 adjacent segments per CTA, next tile prefetched with cp.async
+    // while the current one is searched); the segments that do not fill a tile go to the direct kernels below
+    const bool al16 = (reinterpret_cast<uintptr_t>(frames) % 16 == 0) && (m % 16 == 0);
+    if (al16 && path != 2 && n > 80) {
+      const int tw = (g_median_mode == 1) ? TILE_WARPS : TMA_WARPS;
+      const int64_t ntiles = nseg / tw;
+      if (ntiles > 0 && g_median_mode != 2) {
+        if (g_median_mode == 1) {
+          if (n <= 152) e = launch_median_sad_tile<2, 19, 2>(frames, n, m, ntiles, out, stream);
+          else if (n <= 232) e = launch_median_sad_tile<2, 29, 5>(frames, n, m, ntiles, out, stream);
+          else if (n <= 304) e = launch_median_sad_tile<2, 38, 8>(frames, n, m, ntiles, out, stream);
+          else if (n <= 464) e = launch_median_sad_tile<4, 29, 5>(frames, n, m, ntiles, out, stream);
+          else e = launch_median_sad_tile<4, 38, 8>(frames, n, m, ntiles, out, stream);
+        } else {
+          if (n <= 152) e = launch_median_sad_tma<2, 19, 11, 2>(frames, n, m, ntiles, out, stream);
+          else if (n <= 232) e = launch_median_sad_tma<2, 29, 20, 5>(frames, n, m, ntiles, out, stream);
+          else if (n <= 304) e = launch_median_sad_tma<2, 38, 30, 8>(frames, n, m, ntiles, out, stream);
+          else if (n <= 464) e = launch_median_sad_tma<4, 29, 20, 5>(frames, n, m, ntiles, out, stream);
+          else e = launch_median_sad_tma<4, 38, 30, 8>(frames, n, m, ntiles, out, stream);
+        }
+        if (e) return e;
+        const int64_t done = ntiles * tw;
+        frames += done * seg;
+        out += done * seg;
+        nseg -= done;
+        tiled = done * seg;
+      }
+    }
+    if (nseg == 0) {
+      e = VU_OK;
+    } else if (path == 0) {
       if (n <= 80) e = launch_median_sad<2, 10, 0, 0, 4>(frames, n, m, nseg, out, stream);
       else if (n <= 152) e = launch_median_sad<2, 19, 11, 2, 4>(frames, n, m, nseg, out, stream);
       else if (n <= 232) e = launch_median_sad<2, 29, 20, 5, 2>(frames, n, m, nseg, out, stream);
@@ -277,10 +382,11 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
     }
     if (e) return e;
   }
-  const int64_t first = nseg * seg;
-  if (first < m) {
-    if (m - first > 0x7fffffff) return VU_ERR_UNSUPPORTED;
-    median_tail_kernel<<<(unsigned)(m - first), 256, 0, S(stream)>>>(frames, out, n, m, first);
+  const int64_t first = nseg * seg;   // relative to the advanced pointers
+  const int64_t rem = m - tiled;      // m stays the frame stride
+  if (first < rem) {
+    if (rem - first > 0x7fffffff) return VU_ERR_UNSUPPORTED;
+    median_tail_kernel<<<(unsigned)(rem - first), 256, 0, S(stream)>>>(frames, out, n, m, first);
     note_launch();
     return record_cuda(cudaGetLastError());
   }
