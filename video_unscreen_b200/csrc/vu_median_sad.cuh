@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) median_sad_tma_kernel(const 
   auto fetch = [&](int tile) {   // one thread
     mbar_expect_tx(mbar, SPLIT * BOX_BYTES);
 #pragma unroll
-    for (int b = 0; b < SPLIT; ++b) tma_load_2d(sdata + b * BOX_BYTES, &tmap, tile * TILE, b * 4 * G, mbar);
+    for (int b = 0; b < SPLIT; ++b) tma_load_2d(sdata + b * BOX_BYTES, &tmap, tile * (TILE > 256 ? TILE / 4 : TILE), b * 4 * G, mbar);
   };
   if (threadIdx.x == 0) {
     mbar_init(mbar, 1);

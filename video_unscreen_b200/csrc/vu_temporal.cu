@@ -187,20 +187,20 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-constexpr int TMA_WARPS = 4, TMA_CTAS = 2;
-template <int SPLIT, int G, int GQ, int SS>
+template <int SPLIT, int G, int GQ, int SS, int TMA_WARPS, int TMA_CTAS>
 int launch_median_sad_tma(const uint8_t* frames, int n, int64_t m, int64_t ntiles, uint8_t* out, vu_stream_t stream) {
   constexpr int TILE = TMA_WARPS * (128 / SPLIT);
   constexpr int SMEM = SPLIT * 4 * G * TILE + 16;
-  static_assert(TILE <= 256 && 4 * G <= 256, "TMA box limits");
+  constexpr bool U32 = TILE > 256;   // boxes are at most 256 elements wide: wide tiles are described in 32-bit words
+  static_assert(TILE <= 1024 && 4 * G <= 256, "TMA box limits");
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return VU_ERR_UNSUPPORTED;
   CUtensorMap tmap;
-  const cuuint64_t dims[2] = {(cuuint64_t)m, (cuuint64_t)n};
+  const cuuint64_t dims[2] = {(cuuint64_t)(U32 ? m / 4 : m), (cuuint64_t)n};
   const cuuint64_t strides[1] = {(cuuint64_t)m};
-  const cuuint32_t box[2] = {(cuuint32_t)TILE, (cuuint32_t)(4 * G)};
+  const cuuint32_t box[2] = {(cuuint32_t)(U32 ? TILE / 4 : TILE), (cuuint32_t)(4 * G)};
   const cuuint32_t estr[2] = {1, 1};
-  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  if (enc(&tmap, U32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return VU_ERR_UNSUPPORTED;
   auto kernel = msad::median_sad_tma_kernel<SPLIT, G, GQ, SS, TMA_WARPS, TMA_CTAS>;
@@ -320,6 +320,11 @@ static const int g_median_mode = [] {
   return e ? atoi(e) : 0;
 }();
 
+static const int g_median_cfg = [] {
+  const char* e = getenv("VU_MEDIAN_CFG");
+  return e ? atoi(e) : 0;
+}();
+
 extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream) {
   VU_REQUIRE(frames && out && m >= 0);
   if (n < 1 || n > 65535) return VU_ERR_UNSUPPORTED;
@@ -344,7 +349,7 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
     // while the current one is searched); the segments that do not fill a tile go to the direct kernels below
     const bool al16 = (reinterpret_cast<uintptr_t>(frames) % 16 == 0) && (m % 16 == 0);
     if (al16 && path != 2 && n > 80) {
-      const int tw = (g_median_mode == 1) ? TILE_WARPS : TMA_WARPS;
+      const int tw = (g_median_mode == 1) ? TILE_WARPS : 8;
       const int64_t ntiles = nseg / tw;
       if (ntiles > 0 && g_median_mode != 2) {
         if (g_median_mode == 1) {
@@ -354,11 +359,13 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
           else if (n <= 464) e = launch_median_sad_tile<4, 29, 5>(frames, n, m, ntiles, out, stream);
           else e = launch_median_sad_tile<4, 38, 8>(frames, n, m, ntiles, out, stream);
         } else {
-          if (n <= 152) e = launch_median_sad_tma<2, 19, 11, 2>(frames, n, m, ntiles, out, stream);
-          else if (n <= 232) e = launch_median_sad_tma<2, 29, 20, 5>(frames, n, m, ntiles, out, stream);
-          else if (n <= 304) e = launch_median_sad_tma<2, 38, 30, 8>(frames, n, m, ntiles, out, stream);
-          else if (n <= 464) e = launch_median_sad_tma<4, 29, 20, 5>(frames, n, m, ntiles, out, stream);
-          else e = launch_median_sad_tma<4, 38, 30, 8>(frames, n, m, ntiles, out, stream);
+          // <SPLIT, G, GQ, SS, warps per CTA (= segments per tile), CTAs per SM>
+          if (n <= 152) e = g_median_cfg == 1 ? launch_median_sad_tma<2, 19, 11, 2, 8, 2>(frames, n, m, ntiles, out, stream)
+                                              : launch_median_sad_tma<2, 19, 11, 2, 8, 1>(frames, n, m, ntiles, out, stream);
+          else if (n <= 232) e = launch_median_sad_tma<2, 29, 20, 5, 8, 1>(frames, n, m, ntiles, out, stream);
+          else if (n <= 304) e = launch_median_sad_tma<2, 38, 30, 8, 8, 1>(frames, n, m, ntiles, out, stream);
+          else if (n <= 464) e = launch_median_sad_tma<4, 29, 20, 5, 8, 1>(frames, n, m, ntiles, out, stream);
+          else e = launch_median_sad_tma<4, 38, 30, 8, 8, 1>(frames, n, m, ntiles, out, stream);
         }
         if (e) return e;
         const int64_t done = ntiles * tw;
