@@ -321,7 +321,17 @@ def test_temporal_median_concentrated(vu, n):
     frames[:, 8:, ::17] = base[None, 8:, ::17] + rng.integers(-40, 41, (n, h - 8, len(range(0, w, 17)), 3))  # wide noise
     frames[:, 12:, 5] = np.where(rng.integers(0, 2, (n, h - 12, 3)) > 0, base[None, 12:, 5] + 1, base[None, 12:, 5])  # two adjacent values
     frames = np.clip(frames, 0, 255).astype(np.uint8)
-    assert np.array_equal(vu.U.temporal_median(frames), R.temporal_median(frames))
+    want = R.temporal_median(frames)
+    assert np.array_equal(vu.U.temporal_median(frames), want)          # 16-byte aligned: TMA tile kernels
+    # the same clip 4 bytes off a 16-byte boundary: direct register kernels (no TMA, no 16-byte requests)
+    flat = torch.empty(frames.size + 16, dtype=torch.uint8, device="cuda")
+    off = flat[4:4 + frames.size].view(frames.shape)
+    off.copy_(torch.from_numpy(frames))
+    assert off.data_ptr() % 16 == 4
+    assert np.array_equal(vu.ops.temporal_median(off).cpu().numpy(), want)
+    # frame size not a multiple of 16 bytes (15 x 100 x 3 = 4500): direct kernels, then the byte tail
+    sub = np.ascontiguousarray(frames[:, :15, :100])
+    assert np.array_equal(vu.U.temporal_median(sub), R.temporal_median(sub))
 
 
 def test_temporal_median_properties_full_size(vu):

@@ -7,9 +7,9 @@
 // element, and the ALU pipe (64 lanes/clk/SM) is what bounds this kernel.  The
 // design goal is therefore the smallest number of probes:
 //
-//   stage A  every frame-part estimates the median from 16 of its frames
-//            (spread over the whole clip) by bisection on the slope of S:
-//            8 steps x 8 instructions per element;
+//   stage A  the lower median of 16 frames spread over the whole clip is the
+//            estimate (bisection on the slope of S, 8 steps x 8 instructions;
+//            every frame-part does it for its share of the lane's elements);
 //   stage B  Fibonacci search of the 20 values around the estimate on ALL
 //            frames: 6 probes.  The bracket ends keep their S values, so the
 //            search ends knowing S at both neighbours of the minimiser: a
@@ -52,6 +52,8 @@ __device__ __forceinline__ unsigned sad_acc(unsigned a, unsigned b, unsigned c) 
 }
 
 // 4x4 byte transposes: d[4g+j] <- byte j of the four registers of group g
+// (tried: the same transposition with IDP.4A one-hot byte extraction + IMAD shifts to get it off the ALU pipe:
+// 28 instead of 8 instructions per group, and the kernel got slower with every group moved over)
 template <int G>
 __device__ __forceinline__ void transpose_groups(unsigned (&d)[4 * G]) {
 #pragma unroll
@@ -184,27 +186,41 @@ __device__ __forceinline__ unsigned sad_median(const unsigned (&d)[4 * G], int n
   unsigned smin[4], sl[4], sr[4];
   bool full = (SS == 0);
   if (SS > 0) {
-    // ---- stage A: lower median of 16 frames of this part, bisection on the slope of S ----
-    int est[4] = {0, 0, 0, 0};
+    // ---- stage A: every part estimates 4/SPLIT of the lane's elements as the lower median of 16 of ITS frames
+    // (bisection on the slope of S), then the parts swap their estimates ----
+    constexpr int EPP = 4 / SPLIT;   // elements per part
+    const int part = (threadIdx.x & 31) / (32 / SPLIT);
+    unsigned smp[EPP][4];
+#pragma unroll
+    for (int e = 0; e < EPP; ++e)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        unsigned v = d[4 * (t * SS) + e];
+#pragma unroll
+        for (int p = 1; p < SPLIT; ++p) v = (part == p) ? d[4 * (t * SS) + p * EPP + e] : v;
+        smp[e][t] = v;
+      }
+    int est[EPP];
+#pragma unroll
+    for (int e = 0; e < EPP; ++e) est[e] = 0;
 #pragma unroll 1
     for (int bit = 128; bit > 0; bit >>= 1) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const unsigned q1 = (unsigned)(est[j] | bit) * 0x01010101u, q0 = q1 - 0x01010101u;
+      for (int e = 0; e < EPP; ++e) {
+        const unsigned q1 = (unsigned)(est[e] | bit) * 0x01010101u, q0 = q1 - 0x01010101u;
         unsigned s0 = 0, s1 = 0;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          s0 = sad_acc(d[4 * (t * SS) + j], q0, s0);
-          s1 = sad_acc(d[4 * (t * SS) + j], q1, s1);
+          s0 = sad_acc(smp[e][t], q0, s0);
+          s1 = sad_acc(smp[e][t], q1, s1);
         }
-        if (s1 < s0) est[j] |= bit;
+        if (s1 < s0) est[e] |= bit;
       }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-#pragma unroll
-      for (int o = 32 / SPLIT; o < 32; o <<= 1) est[j] += __shfl_xor_sync(FULL, est[j], o);
-      a[j] = min(max((est[j] + SPLIT / 2) / SPLIT - 10, -1), 235);   // interior a+1 .. a+20 within 0..255
+      const int c = __shfl_sync(FULL, est[j % EPP], (j / EPP) * (32 / SPLIT) + (threadIdx.x & (32 / SPLIT - 1)));
+      a[j] = min(max(c - 10, -1), 235);   // interior a+1 .. a+20 within 0..255
     }
     // ---- stage B: the 20 values around the estimate ----
     fib_search<SPLIT, G, false>(d, delta, 8, 13, 8, 5, a, r, smin, sl, sr);
@@ -352,119 +368,15 @@ __global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __
 }
 
 
-// ---- persistent tile variant: the next tile streams into shared memory while the current one is searched ----
+// ---- persistent tile kernel: TMA fetches the next tile while the current one is searched ---------------------------
 //
-// Measured on the B200 (tools/ldgsts_ubench.cu): fetching "one row per frame" runs at 2.8 TB/s when a warp fetches
-// 64-byte rows on its own, 5.9 TB/s with 128-byte rows and 7.2 TB/s when the 8 warps of a CTA fetch 512-byte rows
-// together: the width that is contiguous per request decides the memory throughput, not the bytes in flight.
-//
-// A CTA of TILE_WARPS warps walks tiles of TILE_WARPS adjacent segments (8 warps, SPLIT 2: 512 bytes of every frame).  Every warp
-// still owns one segment and a private shared-memory buffer of 4G slots x 128 bytes (slot k = 4g + r holds the SEG
-// bytes of part 0's frame, then part 1's, ...: lane l reads its word at l*4 + k*128, conflict-free), but the copies
-// are dealt by frame: warp w copies the frames of the groups g = w, w+8, ... for ALL eight segments, one cp.async.cg
-// instruction (16 bytes per lane) per 512-byte frame row.  Per tile: wait for the copies, barrier, move the buffer
-// to registers (LDS with immediate offsets), transpose, barrier, issue the copies of the NEXT tile, search.  The
-// loads of a tile are in flight during the whole search of the previous one.  Pad slots are written once at kernel
-// start and never copied over.  Needs 16-byte aligned frame rows (frames % 16 == 0, m % 16 == 0).
-__device__ __forceinline__ void cp_async16(unsigned smem_addr, const void* gptr) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <int SPLIT, int G, int SS, int TILE_WARPS, int CTAS>
-__global__ void __launch_bounds__(TILE_WARPS * 32, CTAS) median_sad_tile_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n,
-                                                                             long long m, int ntiles, unsigned zero) {
-  extern __shared__ __align__(128) uint8_t smem_tile[];
-  constexpr int LPS = 32 / SPLIT;            // lanes per frame-part
-  constexpr int SEG = LPS * 4;               // bytes of a frame one warp owns
-  constexpr int TILE = TILE_WARPS * SEG;     // bytes of a frame one CTA owns
-  constexpr int CPR = SEG / 16;              // 16-byte chunks per segment row
-  constexpr int CPT = TILE / 16;             // chunks per tile row
-  constexpr int RPI = 32 / CPT;              // tile rows per copy instruction
-  constexpr int IPG = 4 * SPLIT / RPI;       // copy instructions per group of four slots
-  static_assert(RPI >= 1 && RPI <= 4 * SPLIT, "a copy instruction must stay within one group");
-  constexpr int BUF = 4 * G * 128;           // bytes of one warp's buffer
-  constexpr int T = (G + TILE_WARPS - 1) / TILE_WARPS;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int part = lane / LPS, li = lane % LPS;
-  const int cnt0 = (n + SPLIT - 1) / SPLIT;
-  const int Q = (cnt0 + 3) >> 2;
-  int n0 = 0, n255 = 0;
-#pragma unroll
-  for (int p = 0; p < SPLIT; ++p) {
-    const int c = 4 * G - (n - p + SPLIT - 1) / SPLIT;
-    if (pad_high<SPLIT>(p)) n255 += c;
-    else n0 += c;
-  }
-  const int delta = n255 - n0;
-  uint8_t* buf = smem_tile + warp * BUF;
-  {
-    // pads: chunk c of a 128-byte slot belongs to part c / CPR
-    const unsigned v = pad_high<SPLIT>((lane & 7) / CPR) ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-    for (int g = 0; g < G; ++g) *reinterpret_cast<uint4*>(buf + g * 512 + lane * 16) = make_uint4(v, v, v, v);
-  }
-  // copy role of this lane: tile row ri of the instruction, chunk ci of the row = chunk wc of warp wd's segment.
-  // Instruction ii (0..IPG-1) of a group copies the rows j = ii*RPI + ri of the group's 4*SPLIT rows: slot row
-  // r = j / SPLIT = r_ct(ii) + r_lane, part p = j % SPLIT = p_ct(ii) + p_lane
-  const int ri = lane / CPT, ci = lane % CPT;
-  const int wd = ci / CPR, wc = ci % CPR;
-  const int r_lane = RPI > SPLIT ? ri / SPLIT : 0;
-  const int p_lane = RPI > SPLIT ? ri % SPLIT : ri;
-  const unsigned dst0 = (unsigned)__cvta_generic_to_shared(smem_tile) + wd * BUF + wc * 16 + r_lane * 128 + p_lane * SEG + warp * 512;
-  const unsigned m32 = (unsigned)m + zero;
-  const uint8_t* rowbase[IPG];
-  int tlim[IPG];   // this warp copies the groups g = warp + TILE_WARPS t, t < tlim[ii], with instruction ii
-#pragma unroll
-  for (int ii = 0; ii < IPG; ++ii) {
-    const int r = (RPI > SPLIT ? ii * (RPI / SPLIT) : (ii * RPI) / SPLIT) + r_lane;
-    const int p_ct = RPI > SPLIT ? 0 : (ii * RPI) % SPLIT;
-    const int p = p_ct + p_lane;
-    rowbase[ii] = frames + ci * 16 + ((long long)SPLIT * (r * Q + warp) + p_lane) * m;   // p_ct goes into the immediate
-    const int glim = min(Q, (n - p + SPLIT - 1) / SPLIT - r * Q);   // groups g < glim of (slot row r, part p) hold real frames
-    tlim[ii] = glim > warp ? (glim - warp + TILE_WARPS - 1) / TILE_WARPS : 0;
-  }
-  auto issue = [&](int tile) {
-    const long long toff = (long long)tile * TILE;
-    static_for<0, T>([&](auto ti) {
-      constexpr int t = decltype(ti)::value;
-      static_for<0, IPG>([&](auto iii) {
-        constexpr int ii = decltype(iii)::value;
-        constexpr int r_ct = RPI > SPLIT ? ii * (RPI / SPLIT) : (ii * RPI) / SPLIT;
-        constexpr int p_ct = RPI > SPLIT ? 0 : (ii * RPI) % SPLIT;
-        if (t < tlim[ii]) {
-          unsigned long long addr;
-          asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(addr) : "r"(m32), "n"(TILE_WARPS * SPLIT * t + p_ct), "l"(rowbase[ii] + toff));
-          cp_async16(dst0 + t * (TILE_WARPS * 512) + r_ct * 128 + p_ct * SEG, reinterpret_cast<const void*>(addr));
-        }
-      });
-    });
-    cp_async_commit();
-  };
-  int tile = blockIdx.x;
-  if (tile < ntiles) issue(tile);
-  for (; tile < ntiles; tile += gridDim.x) {
-    cp_async_wait_all();
-    __syncthreads();   // the copies of every warp have landed (and, first time round, the pads)
-    unsigned d[4 * G];
-#pragma unroll
-    for (int k = 0; k < 4 * G; ++k) d[k] = *reinterpret_cast<const unsigned*>(buf + lane * 4 + k * 128);
-    transpose_groups<G>(d);   // consumes every load
-    __syncthreads();   // every warp has emptied its buffer
-    if (tile + (int)gridDim.x < ntiles) issue(tile + gridDim.x);
-    const unsigned res = sad_median<SPLIT, G, SS>(d, n, delta);
-    if (part == 0) reinterpret_cast<unsigned*>(out + ((long long)tile * TILE_WARPS + warp) * SEG)[li] = res;
-  }
-}
-
-// ---- TMA variant of the tile kernel -----------------------------------------------------------------------------
-//
-// Same tiles and the same search, but the tile is fetched by the TMA unit: the clip is described to it as a 2-D
-// uint8 tensor [n frames][m bytes], and SPLIT boxes of {TILE bytes x 4G frames} (cp.async.bulk.tensor.2d, one elected
-// thread, completion counted in bytes on an mbarrier) bring "TILE contiguous bytes of every frame" into shared
-// memory as rows of TILE bytes: full 128-byte lines per request, no address arithmetic and no load instructions in
-// the warps.  Frames past the end of the clip are zero-filled by the unit: pads are all 0 here and leave S through
+// Measured on the B200 (tools/ldgsts_ubench.cu, fetch only): "one row per frame" streams at 2.8 TB/s when a warp
+// fetches 64-byte rows on its own, at 5.9 TB/s with 128-byte rows and at 7.2 TB/s with 512-byte rows: requests must
+// cover whole 128-byte lines, and the direct kernel above (64 bytes per frame and warp) cannot get there.  Here a CTA
+// of WARPS warps owns tiles of WARPS adjacent segments (8 warps, SPLIT 2: 512 bytes of every frame).  The clip is
+// described to the TMA unit as a 2-D tensor [n frames][m bytes], and SPLIT boxes of {TILE bytes x 4G frames}
+// (cp.async.bulk.tensor.2d, one elected thread, completion counted in bytes on an mbarrier) bring the tile into
+// shared memory as rows of TILE bytes: no address arithmetic and no load instructions in the warps.  Frames past the end of the clip are zero-filled by the unit: pads are all 0 here and leave S through
 // delta = -(number of pads).  The warps are only loosely coupled: a warp waits for the tile on the mbarrier, moves its
 // segment to registers and transposes, bumps a counter and goes searching; the warp that bumps it last knows the
 // buffer is free and launches the fetch of the next tile, which then lands while everybody searches.

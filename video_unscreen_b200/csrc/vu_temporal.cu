@@ -151,24 +151,6 @@ int launch_median_sad(const uint8_t* frames, int n, int64_t m, int64_t nseg, uin
   return record_cuda(cudaGetLastError());
 }
 
-constexpr int TILE_WARPS = 2, TILE_CTAS = 4;   // warps per tile CTA (= segments per tile), CTAs per SM
-template <int SPLIT, int G, int SS>
-int launch_median_sad_tile(const uint8_t* frames, int n, int64_t m, int64_t ntiles, uint8_t* out, vu_stream_t stream) {
-  constexpr int SMEM = TILE_WARPS * 4 * G * 128;
-  auto kernel = msad::median_sad_tile_kernel<SPLIT, G, SS, TILE_WARPS, TILE_CTAS>;
-  static bool configured = false;
-  if (!configured) {
-    int e = record_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    if (e) return e;
-    configured = true;
-  }
-  const int64_t cap = (int64_t)device_sms() * TILE_CTAS;
-  const int grid = (int)(ntiles < cap ? ntiles : cap);
-  kernel<<<grid, TILE_WARPS * 32, SMEM, S(stream)>>>(frames, out, n, m, (int)ntiles, 0u);
-  note_launch();
-  return record_cuda(cudaGetLastError());
-}
-
 // TMA tile kernels: the clip as a 2-D uint8 tensor [n][m], boxes of {TILE bytes, 4G frames}
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -314,15 +296,10 @@ int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t
 
 using namespace vu;
 
-// development switch (VU_MEDIAN_MODE): 0 = TMA tile kernels, 1 = cp.async tile kernels, 2 = direct kernels only
-static const int g_median_mode = [] {
-  const char* e = getenv("VU_MEDIAN_MODE");
-  return e ? atoi(e) : 0;
-}();
-
-static const int g_median_cfg = [] {
-  const char* e = getenv("VU_MEDIAN_CFG");
-  return e ? atoi(e) : 0;
+// VU_MEDIAN_DIRECT=1 keeps the TMA tile kernels out (tests run the direct kernels on aligned clips this way)
+static const bool g_median_direct = [] {
+  const char* e = getenv("VU_MEDIAN_DIRECT");
+  return e && atoi(e) != 0;
 }();
 
 extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream) {
@@ -345,34 +322,25 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
     // <SPLIT, G, GFULL, SS, CTAs/SM>: G = register groups of 4 frames per lane, the smallest variant that holds
     // ceil(n / SPLIT) frames; GFULL = groups whose first three rows are real frames over the whole n-range of the
     // variant; SS = stride of the four sample groups of the estimate (all real frames over the n-range)
-    // 16-byte aligned rows: persistent tile kernels (8 adjacent segments per CTA, next tile prefetched with cp.async
-    // while the current one is searched); the segments that do not fill a tile go to the direct kernels below
+    // 16-byte aligned frame rows: persistent TMA tile kernels (8 adjacent segments per CTA, the next tile is fetched
+    // while the current one is searched); segments that do not fill a tile go to the direct kernels below.
+    // <SPLIT, G, GQ, SS, warps per CTA (= segments per tile), CTAs per SM>
     const bool al16 = (reinterpret_cast<uintptr_t>(frames) % 16 == 0) && (m % 16 == 0);
-    if (al16 && path != 2 && n > 80) {
-      const int tw = (g_median_mode == 1) ? TILE_WARPS : 8;
-      const int64_t ntiles = nseg / tw;
-      if (ntiles > 0 && g_median_mode != 2) {
-        if (g_median_mode == 1) {
-          if (n <= 152) e = launch_median_sad_tile<2, 19, 2>(frames, n, m, ntiles, out, stream);
-          else if (n <= 232) e = launch_median_sad_tile<2, 29, 5>(frames, n, m, ntiles, out, stream);
-          else if (n <= 304) e = launch_median_sad_tile<2, 38, 8>(frames, n, m, ntiles, out, stream);
-          else if (n <= 464) e = launch_median_sad_tile<4, 29, 5>(frames, n, m, ntiles, out, stream);
-          else e = launch_median_sad_tile<4, 38, 8>(frames, n, m, ntiles, out, stream);
-        } else {
-          // <SPLIT, G, GQ, SS, warps per CTA (= segments per tile), CTAs per SM>
-          if (n <= 152) e = g_median_cfg == 1 ? launch_median_sad_tma<2, 19, 11, 2, 8, 2>(frames, n, m, ntiles, out, stream)
-                                              : launch_median_sad_tma<2, 19, 11, 2, 8, 1>(frames, n, m, ntiles, out, stream);
-          else if (n <= 232) e = launch_median_sad_tma<2, 29, 20, 5, 8, 1>(frames, n, m, ntiles, out, stream);
-          else if (n <= 304) e = launch_median_sad_tma<2, 38, 30, 8, 8, 1>(frames, n, m, ntiles, out, stream);
-          else if (n <= 464) e = launch_median_sad_tma<4, 29, 20, 5, 8, 1>(frames, n, m, ntiles, out, stream);
-          else e = launch_median_sad_tma<4, 38, 30, 8, 8, 1>(frames, n, m, ntiles, out, stream);
-        }
-        if (e) return e;
-        const int64_t done = ntiles * tw;
+    const int64_t ntiles = nseg / 8;
+    if (al16 && path != 2 && n > 80 && ntiles > 0 && !g_median_direct) {
+      if (n <= 152) e = launch_median_sad_tma<2, 19, 11, 2, 8, 2>(frames, n, m, ntiles, out, stream);
+      else if (n <= 232) e = launch_median_sad_tma<2, 29, 20, 5, 8, 1>(frames, n, m, ntiles, out, stream);
+      else if (n <= 304) e = launch_median_sad_tma<2, 38, 30, 8, 8, 1>(frames, n, m, ntiles, out, stream);
+      else if (n <= 464) e = launch_median_sad_tma<4, 29, 20, 5, 8, 1>(frames, n, m, ntiles, out, stream);
+      else e = launch_median_sad_tma<4, 38, 30, 8, 8, 1>(frames, n, m, ntiles, out, stream);
+      if (e == VU_OK) {
+        const int64_t done = ntiles * 8;
         frames += done * seg;
         out += done * seg;
         nseg -= done;
         tiled = done * seg;
+      } else if (e != VU_ERR_UNSUPPORTED) {   // no tensor-map encoder in this driver: the direct kernels do everything
+        return e;
       }
     }
     if (nseg == 0) {
