@@ -52,7 +52,8 @@ def measured_traffic(workload):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(workload)
+            v = json.load(open(p)).get(workload)
+            return int(v) if v is not None else None
         except Exception:
             pass
     return None
@@ -129,7 +130,7 @@ def run_reference_arm(args, wl):
 # --------------------------------------------------------------------------
 
 class ClockSampler(threading.Thread):
-    def __init__(self, index, period=0.01):
+    def __init__(self, index, period=0.001):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -319,7 +320,7 @@ def run_gpu_arm(args, wl):
                        "clip_bytes": n * m, "l2": "inputs (1.87 GB at 1080p) larger than the 126 MB L2; no flush needed",
                        "sharding": "one clip (spatial tile set) per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "vu::median_sad_kernel<2,38,29,2> (VABSDIFF4 Fibonacci search)", "algorithmic_bytes_per_launch": algo_bytes,
+                         "traffic": traffic, "kernel": "vu::msad::median_sad_tma_kernel<2,38,30,8,8,1> (TMA tiles, VABSDIFF4 estimate + windowed Fibonacci search)", "algorithmic_bytes_per_launch": algo_bytes,
                          "launch_ms": kernel_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
@@ -332,7 +333,7 @@ def run_gpu_arm(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="median_1080p", choices=sorted(WORKLOADS))
