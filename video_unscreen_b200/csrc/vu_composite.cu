@@ -131,6 +131,74 @@ __global__ void __launch_bounds__(THREADS) blend_kernel(const uint8_t* __restric
   }
 }
 
+// The same blends at 16 pixels (48 bytes) per thread with 128-bit streaming loads / stores.  The float64 division
+// alpha/255 and 1 - alpha/255 (and COMPOSITE's a > 0.9 -> 1) are tabulated per CTA for the 256 possible alphas with
+// the very operations of the per-pixel kernel above, so the results are identical; uint8 -> float64 is one exact DADD
+// (2^52 + x, minus 2^52) and the truncating cast one DADD.RZ (x + 2^52: the low word is trunc(x)), which leaves six
+// float64 pipe operations per output byte and nothing on the slow conversion unit.
+__device__ __forceinline__ double u8_to_f64(unsigned x) { return __dsub_rn(__hiloint2double(0x43300000, (int)x), 4503599627370496.0); }
+__device__ __forceinline__ int f64_trunc_nonneg(double x) { return __double2loint(__dadd_rz(x, 4503599627370496.0)); }
+
+template <int MODE, int AC>
+__global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
+                                                          int64_t ngroups, int64_t bg_groups, uint4* __restrict__ out) {
+  __shared__ double mtab[256], otab[256];
+  for (int a = threadIdx.x; a < 256; a += THREADS) {
+    double m = __ddiv_rn((double)a, 255.0);
+    if (MODE == VU_BLEND_COMPOSITE && m > 0.9) m = 1.0;
+    mtab[a] = m;
+    otab[a] = __dsub_rn(1.0, m);
+  }
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    uint4 f[3], q[3], av[3], o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f[k] = ldg_stream16(fg + 3 * g + k);
+    if (MODE != VU_BLEND_NAIVE) {
+      const int64_t gb = g % bg_groups;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) q[k] = (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k);
+    }
+    if (AC == 3) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) av[k] = ldg_stream16(alpha + 3 * g + k);
+    } else {
+      av[0] = ldg_stream16(alpha + g);
+    }
+    const unsigned* fw = reinterpret_cast<const unsigned*>(f);
+    const unsigned* qw = reinterpret_cast<const unsigned*>(q);
+    const unsigned* aw = reinterpret_cast<const unsigned*>(av);
+    unsigned* ow = reinterpret_cast<unsigned*>(o);
+#pragma unroll
+    for (int w = 0; w < 12; ++w) {
+      unsigned r4 = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = 4 * w + b;                       // byte of the 48
+        const int ai = AC == 3 ? i : i / 3;            // its alpha byte
+        const unsigned a = (aw[ai >> 2] >> (8 * (ai & 3))) & 255u;
+        const double m = mtab[a];
+        const double c = u8_to_f64((fw[w] >> (8 * b)) & 255u);
+        double r;
+        if (MODE == VU_BLEND_NAIVE) {
+          r = __dmul_rn(c, m);
+        } else {
+          const double qq = u8_to_f64((qw[w] >> (8 * b)) & 255u);
+          if (MODE == VU_BLEND_COMPOSITE) r = __dadd_rn(c, __dmul_rn(qq, otab[a]));
+          else r = __dadd_rn(__dmul_rn(c, m), __dmul_rn(qq, otab[a]));   // FUSE == REPLACE (products commute)
+        }
+        int v = f64_trunc_nonneg(r);
+        if (MODE == VU_BLEND_COMPOSITE) v = min(v, 255);
+        r4 |= (unsigned)v << (8 * b);
+      }
+      ow[w] = r4;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, o[k]);
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) fuse_bg_kernel(const unsigned* __restrict__ bg, const unsigned* __restrict__ always, int64_t nwords,
                                                           int64_t always_words, float beta, float omb, unsigned* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -225,6 +293,28 @@ extern "C" int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int a
   VU_REQUIRE_VEC(npix, fg, alpha, bg, out);
   if (mode != VU_BLEND_NAIVE && bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
   if (npix == 0) return VU_OK;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool wide = npix % 16 == 0 && (mode == VU_BLEND_NAIVE || bg_npix % 16 == 0) && al16(fg) && al16(alpha) && al16(out) && (!bg || al16(bg));
+  if (wide) {
+    const int64_t ng = npix / 16, bgg = (mode == VU_BLEND_NAIVE) ? 1 : bg_npix / 16;
+    const int grid = grid_for(ng, THREADS, 8);
+#define LAUNCH16(M)                                                                                                          \
+  do {                                                                                                                       \
+    if (alpha_channels == 1)                                                                                                 \
+      blend16_kernel<M, 1><<<grid, THREADS, 0, S(stream)>>>(reinterpret_cast<const uint4*>(fg), reinterpret_cast<const uint4*>(alpha), \
+                                                            reinterpret_cast<const uint4*>(bg), ng, bgg, reinterpret_cast<uint4*>(out)); \
+    else                                                                                                                     \
+      blend16_kernel<M, 3><<<grid, THREADS, 0, S(stream)>>>(reinterpret_cast<const uint4*>(fg), reinterpret_cast<const uint4*>(alpha), \
+                                                            reinterpret_cast<const uint4*>(bg), ng, bgg, reinterpret_cast<uint4*>(out)); \
+  } while (0)
+    switch (mode) {
+      case VU_BLEND_NAIVE: LAUNCH16(VU_BLEND_NAIVE); break;
+      case VU_BLEND_COMPOSITE: LAUNCH16(VU_BLEND_COMPOSITE); break;
+      default: LAUNCH16(VU_BLEND_REPLACE); break;   // FUSE and REPLACE are the same arithmetic
+    }
+#undef LAUNCH16
+    VU_RETURN_LAUNCH();
+  }
   const int64_t ng = npix / 4, bgg = (mode == VU_BLEND_NAIVE) ? 1 : bg_npix / 4;
   const int grid = grid_for(ng, THREADS, 8);
 #define LAUNCH(M)                                                                                        \
