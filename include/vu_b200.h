@@ -207,6 +207,11 @@ int vu_fuse_bg(const uint8_t* bg, const uint8_t* bg_always, int64_t npix, int64_
 /* bg.py:85-88 == bg_offline.py:154-157: g = BGR2GRAY(|frame-bg|); g[g>thr]=255 */
 int vu_bgdiff_gray(const uint8_t* frame, const uint8_t* bg, int64_t npix, int64_t bg_npix, int thr, uint8_t* gray,
                    vu_stream_t stream);
+/* bg.py:85-92 == bg_offline.py:154-160 in one pass over n frames: out = mask * (dilate_mask(g, 4, 2) // 255) with
+ * g = BGR2GRAY(|frame - bg|), g[g > thr] = 255.  bg is one [h,w,3] image (bg_frames == 1) or one per frame
+ * (bg_frames == n).  Needs w % 4 == 0 and 4-byte aligned pointers. */
+int vu_bgdiff_gate(const uint8_t* frames, const uint8_t* bg, const uint8_t* masks, int n, int h, int w, int bg_frames,
+                   int thr, uint8_t* out, vu_stream_t stream);
 /* bg.py:92 == bg_offline.py:160: out = mask * (g // 255) (uint8 wrap-free) */
 int vu_gate(const uint8_t* mask, const uint8_t* g, int64_t count, uint8_t* out, vu_stream_t stream);
 /* bg.py:74-76: >128 -> 255 else 0 */

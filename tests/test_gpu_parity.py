@@ -269,6 +269,29 @@ def test_blend_all_alpha_values(vu):
     assert np.array_equal(U.get_fg(fg, al, bg), R.get_fg(fg, al, bg))
 
 
+@pytest.mark.parametrize("shape,thr", [((70, 128), 25), ((64, 120), 25), ((131, 244), 10), ((9, 12), 25), ((200, 500), 254), ((200, 500), 255),
+                                       ((65, 124), 0)])
+def test_bgdiff_gate_fused(vu, shape, thr):
+    """the fused, bit-packed gate (vu_bgdiff_gate) against the oracle's bg.py:85-92 restatement: tile seams (120 x 64
+    output tiles), image borders, thresholds at the ends of the range, per-frame and shared backgrounds."""
+    h, w = shape
+    rng = np.random.default_rng(h * 1000 + w + thr)
+    n = 3
+    bg = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    frames = np.clip(bg.astype(np.int16) + rng.integers(-20, 21, (n, h, w, 3)), 0, 255).astype(np.uint8)
+    hot = rng.random((n, h, w)) < 0.01                     # sparse large differences: isolated dilation footprints
+    frames[hot] = 255 - bg[hot]
+    frames[:, 0, 0] = 255; bg[:, 0, 0] = 0                 # gray == 255 exactly, in a corner
+    frames[:, -1, -1] = 0; bg[:, -1, -1] = 255
+    masks = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    got = vu.ops.bgdiff_gate(torch.from_numpy(frames).cuda(), torch.from_numpy(bg).cuda(), torch.from_numpy(masks).cuda(), thr).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got[i], R.bgdiff_gate(frames[i], bg[i], masks[i], thr)), i
+    got1 = vu.ops.bgdiff_gate(torch.from_numpy(frames).cuda(), torch.from_numpy(bg[0]).cuda(), torch.from_numpy(masks).cuda(), thr).cpu().numpy()
+    for i in range(n):
+        assert np.array_equal(got1[i], R.bgdiff_gate(frames[i], bg[0], masks[i], thr)), i
+
+
 # ---- temporal ----------------------------------------------------------------------------------
 
 def test_temporal_golden(vu, golden):

@@ -129,8 +129,10 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=16):
     tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     fg = torch.empty_like(frames)
     for s, e in _chunks(n, chunk):
-        g = ops.dilate(ops.bgdiff_gray(frames[s:e], bg, thr), 4, 2)
-        a = ops.gate(masks[s:e], g)
+        if ops.bgdiff_gate_supported(frames[s:e], bg, masks[s:e]):
+            a = ops.bgdiff_gate(frames[s:e], bg, masks[s:e], thr)
+        else:
+            a = ops.gate(masks[s:e], ops.dilate(ops.bgdiff_gray(frames[s:e], bg, thr), 4, 2))
         alpha[s:e] = a
         tri[s:e] = trimap_clip(a, trimap_agent, chunk=chunk)
         fg[s:e] = ops.get_fg(frames[s:e], a, bg, _lib.PATCH_ALPHA_EQ0)

@@ -285,6 +285,22 @@ def gate(mask, g):
     return out
 
 
+def bgdiff_gate_supported(frames, bg, masks):
+    return frames.shape[-2] % 4 == 0 and all(t.data_ptr() % 4 == 0 for t in (frames, bg, masks))
+
+
+def bgdiff_gate(frames, bg, masks, thr):
+    """mask * (dilate_mask(g, 4, 2) // 255), g = thresholded BGR2GRAY(|frame - bg|), fused and bit-packed
+    (tools/unscreen/bg.py:85-92 == bg_offline.py:154-160); frames [N,H,W,3] or [H,W,3], bg [H,W,3] or [N,H,W,3]."""
+    frames, bg, masks = _img(frames), _img(bg), _dev(masks)
+    h, w = frames.shape[-3], frames.shape[-2]
+    n = frames.numel() // (h * w * 3)
+    nb = bg.numel() // (h * w * 3)
+    out = torch.empty_like(masks)
+    check(lib().vu_bgdiff_gate(_p(frames), _p(bg), _p(masks), n, h, w, nb, int(thr), _p(out), _stream()))
+    return out
+
+
 def sub_wrap(a, b):
     a, b = _dev(a), _dev(b)
     out = torch.empty_like(a)

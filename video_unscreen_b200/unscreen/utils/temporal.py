@@ -38,7 +38,9 @@ def bgdiff_gate(frame, bgimg, mask, thr=25):
     f, as_np = to_dev(frame)
     b, _ = to_dev(bgimg)
     m, _ = to_dev(mask)
-    g = ops.bgdiff_gray(f, b, thr)
+    if ops.bgdiff_gate_supported(f, b, m):
+        return back(ops.bgdiff_gate(f, b, m, thr), as_np)
+    g = ops.bgdiff_gray(f, b, thr)    # widths that are not a multiple of 4: the unfused kernels
     g = ops.dilate(g, 4, 2)
     return back(ops.gate(m, g), as_np)
 
