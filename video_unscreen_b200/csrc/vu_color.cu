@@ -29,16 +29,16 @@ struct Bgr2Hsv {
 
 struct Hsv2Bgr {
   const uint8_t* src; uint8_t* dst;
-  __device__ void px(int64_t p, const HsvTab&) const {
-    int b, g, r; hsv2bgr_px(src[3 * p], src[3 * p + 1], src[3 * p + 2], b, g, r);
+  __device__ void px(int64_t p, const HsvTab& t) const {
+    int b, g, r; hsv2bgr_px(src[3 * p], src[3 * p + 1], src[3 * p + 2], t, b, g, r);
     dst[3 * p] = b; dst[3 * p + 1] = g; dst[3 * p + 2] = r;
   }
-  __device__ void px4(int64_t g, const HsvTab&) const {
+  __device__ void px4(int64_t g, const HsvTab& t) const {
     const unsigned* s4 = reinterpret_cast<const unsigned*>(src) + 3 * g;
     int c[12], o[12];
     unpack12(__ldg(s4), __ldg(s4 + 1), __ldg(s4 + 2), c);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) hsv2bgr_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+    for (int i = 0; i < 4; ++i) hsv2bgr_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], t, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
     unsigned w0, w1, w2; pack12(o, w0, w1, w2);
     unsigned* d4 = reinterpret_cast<unsigned*>(dst) + 3 * g;
     d4[0] = w0; d4[1] = w1; d4[2] = w2;

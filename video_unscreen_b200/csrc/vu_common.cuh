@@ -50,11 +50,25 @@ __device__ __forceinline__ void stg_stream16(void* p, const uint4& v) {
 struct HsvTab {
   int sdiv[256];
   int hdiv[256];
+  // HSV2BGR, per hue byte: the sector of cv2's float formula and the factor f (odd sectors) / 1 - f (even sectors)
+  float hfac[256];
+  unsigned char hsec[256];
 };
 __device__ __forceinline__ void hsv_tab_init(HsvTab& t) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     t.sdiv[i] = i ? (2 * 1044480 + i) / (2 * i) : 0;
     t.hdiv[i] = i ? (2 * 122880 + i) / (2 * i) : 0;
+    // h *= 6/180; h = fmod(h, 6); sector = floor(h); f = h - sector   (SURVEY.md A.5), hue bytes >= 180 wrap
+    float h = __fmul_rn((float)i, 6.0f / 180.0f);
+    h = fmodf(h, 6.0f);
+    int sec = (int)floorf(h);
+    h = __fsub_rn(h, (float)sec);
+    if ((unsigned)sec >= 6u) {
+      sec = 0;
+      h = 0.f;
+    }
+    t.hsec[i] = (unsigned char)sec;
+    t.hfac[i] = (sec & 1) ? h : __fsub_rn(1.f, h);
   }
 }
 __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const HsvTab& t, int& h, int& s, int& v) {
@@ -67,43 +81,32 @@ __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const HsvTab& t,
   h = hh < 0 ? hh + 180 : hh;
 }
 
+// uint8 <-> float32 without the conversion unit (16 lanes/clk/SM against 64 for an FADD): 2^23 + i has i in its
+// mantissa, and x + 2^23 rounded toward zero has trunc(x) there (0 <= x < 2^23)
+__device__ __forceinline__ float u8_to_f32(int i) { return __fadd_rn(__int_as_float(0x4B000000 | i), -8388608.0f); }
+__device__ __forceinline__ int f32_trunc_nonneg(float x) { return __float_as_int(__fadd_rz(x, 8388608.0f)) & 0x007FFFFF; }
+
 // ---- cv2 BGR2GRAY (uint8): 15-bit coefficients, SURVEY A.4 ----
 __device__ __forceinline__ int bgr2gray_px(int b, int g, int r) { return (3735 * b + 19235 * g + 9798 * r + 16384) >> 15; }
 
 // ---- cv2 HSV2BGR (uint8), float32 formula with the truncating cast of the
-// whole-image SIMD path, SURVEY A.5 ----
-__device__ __forceinline__ void hsv2bgr_px(int hi, int si, int vi, int& b, int& g, int& r) {
-  const float v = __fmul_rn((float)vi, 1.0f / 255.0f);
-  float bf, gf, rf;
-  if (si == 0) {
-    bf = gf = rf = v;
-  } else {
-    const float s = __fmul_rn((float)si, 1.0f / 255.0f);
-    float h = __fmul_rn((float)hi, 6.0f / 180.0f);
-    h = fmodf(h, 6.0f);
-    int sec = (int)floorf(h);
-    h = __fsub_rn(h, (float)sec);
-    if ((unsigned)sec >= 6u) {
-      sec = 0;
-      h = 0.f;
-    }
-    const float t0 = v;
-    const float t1 = __fmul_rn(v, __fsub_rn(1.f, s));
-    const float t2 = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, h)));
-    const float t3 = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, __fsub_rn(1.f, h))));
-    // sector_data = {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}}
-    switch (sec) {
-      case 0: bf = t1; gf = t3; rf = t0; break;
-      case 1: bf = t1; gf = t0; rf = t2; break;
-      case 2: bf = t3; gf = t0; rf = t1; break;
-      case 3: bf = t0; gf = t2; rf = t1; break;
-      case 4: bf = t0; gf = t1; rf = t3; break;
-      default: bf = t2; gf = t1; rf = t0; break;
-    }
-  }
-  b = min(255, max(0, (int)__fmul_rn(bf, 255.f)));
-  g = min(255, max(0, (int)__fmul_rn(gf, 255.f)));
-  r = min(255, max(0, (int)__fmul_rn(rf, 255.f)));
+// whole-image SIMD path, SURVEY A.5:  tab = {v, v(1-s), v(1-s f), v(1-s(1-f))},
+// (b,g,r) = tab[sector_data[sector]], sector_data = {{1,3,0},{1,0,2},{3,0,1},{0,2,1},{0,1,3},{2,1,0}}.
+// Sector and f come from the per-hue table; only one of v(1-s f) / v(1-s(1-f)) is used by a sector (odd / even).
+// s == 0 needs no branch: every entry is then v * (1 - 0) = v exactly. ----
+__device__ __forceinline__ void hsv2bgr_px(int hi, int si, int vi, const HsvTab& t, int& b, int& g, int& r) {
+  const float v = __fmul_rn(u8_to_f32(vi), 1.0f / 255.0f);
+  const float s = __fmul_rn(u8_to_f32(si), 1.0f / 255.0f);
+  const int sec = t.hsec[hi];
+  const float p = __fmul_rn(v, __fsub_rn(1.f, s));
+  const float x = __fmul_rn(v, __fsub_rn(1.f, __fmul_rn(s, t.hfac[hi])));
+  // sector: 0 (p,x,v)  1 (p,v,x)  2 (x,v,p)  3 (v,x,p)  4 (v,p,x)  5 (x,p,v)
+  const float bf = sec < 2 ? p : ((sec == 2 || sec == 5) ? x : v);
+  const float gf = (sec == 1 || sec == 2) ? v : ((sec == 0 || sec == 3) ? x : p);
+  const float rf = (sec == 0 || sec == 5) ? v : ((sec == 1 || sec == 4) ? x : p);
+  b = min(255, f32_trunc_nonneg(__fmul_rn(bf, 255.f)));
+  g = min(255, f32_trunc_nonneg(__fmul_rn(gf, 255.f)));
+  r = min(255, f32_trunc_nonneg(__fmul_rn(rf, 255.f)));
 }
 
 // unpack / pack 4 BGR pixels held in three little-endian words

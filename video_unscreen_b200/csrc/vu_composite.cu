@@ -14,37 +14,59 @@ namespace {
 
 constexpr int THREADS = 256;
 
-__device__ __forceinline__ int trunc_clamp255(float x) { return (int)fminf(fmaxf(x, 0.f), 255.f); }
+__device__ __forceinline__ int trunc_clamp255(float x) { return f32_trunc_nonneg(fminf(fmaxf(x, 0.f), 255.f)); }
 
-// 4 pixels per thread; alpha word holds the 4 alphas
-template <int PATCH, bool WRITE_BG>
+// 4 pixels per thread; alpha word holds the 4 alphas.
+// BGMODE: how the background repeats under the frames (no 64-bit modulo in the pixel loop):
+//   0  bg as large as the input            1  bg is ONE 4-pixel group (constant colour)
+//   2  the input is gridDim.y repetitions of bg (a clip over one background image): g runs over one repetition
+//   3  anything else: g % bg_groups
+template <int PATCH, bool WRITE_BG, int BGMODE>
 __global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restrict__ frame, const uint8_t* __restrict__ alpha,
                                                          const uint8_t* __restrict__ bg, int64_t ngroups, int64_t bg_groups,
                                                          uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
   __shared__ HsvTab tab;
+  __shared__ float ktab[256];   // 1 - alpha/255. for every alpha byte
   hsv_tab_init(tab);
+  for (int a = threadIdx.x; a < 256; a += blockDim.x) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+  const int64_t rep = BGMODE == 2 ? (int64_t)blockIdx.y * bg_groups : 0;   // first group of this repetition
+  const int64_t gend = BGMODE == 2 ? bg_groups : ngroups;
+  int q0[12];
+  if (BGMODE == 1) {
+    const unsigned* b4 = reinterpret_cast<const unsigned*>(bg);
+    unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q0);
+  }
+  for (int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gl < gend; gl += stride) {
+    const int64_t g = rep + gl;
     const unsigned* f4 = reinterpret_cast<const unsigned*>(frame) + 3 * g;
-    const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * (g % bg_groups);
     int c[12], q[12], o[12];
     unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
-    unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
+    if (BGMODE == 1) {
+#pragma unroll
+      for (int i = 0; i < 12; ++i) q[i] = q0[i];
+    } else {
+      const int64_t gb = BGMODE == 0 ? g : (BGMODE == 2 ? gl : g % bg_groups);
+      const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * gb;
+      unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
+    }
     const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int a = (aw >> (8 * i)) & 255;
       const bool patch = (PATCH == VU_PATCH_ALPHA_LT128) ? (a < 128) : (PATCH == VU_PATCH_ALPHA_EQ0 ? (a == 0) : false);
-      if (patch) { q[3 * i] = c[3 * i]; q[3 * i + 1] = c[3 * i + 1]; q[3 * i + 2] = c[3 * i + 2]; }
+      q[3 * i] = patch ? c[3 * i] : q[3 * i];
+      q[3 * i + 1] = patch ? c[3 * i + 1] : q[3 * i + 1];
+      q[3 * i + 2] = patch ? c[3 * i + 2] : q[3 * i + 2];
       int ih, is, iv, bh, bs, bv;
       bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
       bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bv);
-      const float k = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));   // 1 - alpha/255.
-      const int fh = trunc_clamp255(__fsub_rn((float)ih, __fmul_rn(k, (float)bh)));
-      const int fs = trunc_clamp255(__fsub_rn((float)is, __fmul_rn(k, (float)bs)));
-      const int fv = trunc_clamp255(__fsub_rn((float)iv, __fmul_rn(k, (float)bv)));
-      hsv2bgr_px(fh, fs, fv, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      const float k = ktab[a];   // 1 - alpha/255.
+      const int fh = trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
+      const int fs = trunc_clamp255(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
+      const int fv = trunc_clamp255(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bv))));
+      hsv2bgr_px(fh, fs, fv, tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
     }
     unsigned w0, w1, w2;
     pack12(o, w0, w1, w2);
@@ -61,7 +83,9 @@ __global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restri
 __global__ void __launch_bounds__(THREADS) get_bg_kernel(const uint8_t* __restrict__ alpha, const uint8_t* __restrict__ bg, int64_t ngroups,
                                                          uint8_t* __restrict__ out) {
   __shared__ HsvTab tab;
+  __shared__ float ktab[256];
   hsv_tab_init(tab);
+  for (int a = threadIdx.x; a < 256; a += blockDim.x) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
@@ -74,9 +98,9 @@ __global__ void __launch_bounds__(THREADS) get_bg_kernel(const uint8_t* __restri
       const int a = (aw >> (8 * i)) & 255;
       int bh, bs, bv;
       bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bv);
-      const float k = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
-      hsv2bgr_px(trunc_clamp255(__fmul_rn(k, (float)bh)), trunc_clamp255(__fmul_rn(k, (float)bs)), trunc_clamp255(__fmul_rn(k, (float)bv)),
-                 o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      const float k = ktab[a];
+      hsv2bgr_px(trunc_clamp255(__fmul_rn(k, u8_to_f32(bh))), trunc_clamp255(__fmul_rn(k, u8_to_f32(bs))),
+                 trunc_clamp255(__fmul_rn(k, u8_to_f32(bv))), tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
     }
     unsigned w0, w1, w2;
     pack12(o, w0, w1, w2);
@@ -261,8 +285,26 @@ extern "C" int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8
   if (bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
   if (npix == 0) return VU_OK;
   const int64_t ng = npix / 4, bgg = bg_npix / 4;
-  const int grid = grid_for(ng, THREADS, 8);
-#define LAUNCH(P, W) get_fg_kernel<P, W><<<grid, THREADS, 0, S(stream)>>>(frame, alpha, bg, ng, bgg, fg_out, bg_out)
+  int mode = 3;
+  dim3 grid(grid_for(ng, THREADS, 8));
+  if (bgg == ng) mode = 0;
+  else if (bgg == 1) mode = 1;
+  else if (ng % bgg == 0 && ng / bgg <= 65535) {
+    mode = 2;
+    const int64_t reps = ng / bgg;
+    int64_t gx = ((int64_t)device_sms() * 8 + reps - 1) / reps;
+    const int64_t need = (bgg + THREADS - 1) / THREADS;
+    if (gx > need) gx = need;
+    grid = dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)reps);
+  }
+#define LAUNCH3(P, W, M) get_fg_kernel<P, W, M><<<grid, THREADS, 0, S(stream)>>>(frame, alpha, bg, ng, bgg, fg_out, bg_out)
+#define LAUNCH(P, W)                      \
+  do {                                    \
+    if (mode == 0) LAUNCH3(P, W, 0);      \
+    else if (mode == 1) LAUNCH3(P, W, 1); \
+    else if (mode == 2) LAUNCH3(P, W, 2); \
+    else LAUNCH3(P, W, 3);                \
+  } while (0)
   if (bg_out) {
     if (patch_mode == VU_PATCH_NONE) LAUNCH(VU_PATCH_NONE, true);
     else if (patch_mode == VU_PATCH_ALPHA_LT128) LAUNCH(VU_PATCH_ALPHA_LT128, true);
@@ -273,6 +315,7 @@ extern "C" int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8
     else LAUNCH(VU_PATCH_ALPHA_EQ0, false);
   }
 #undef LAUNCH
+#undef LAUNCH3
   VU_RETURN_LAUNCH();
 }
 
