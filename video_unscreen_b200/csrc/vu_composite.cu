@@ -41,6 +41,22 @@ __global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restri
   for (int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gl < gend; gl += stride) {
     const int64_t g = rep + gl;
     const unsigned* f4 = reinterpret_cast<const unsigned*>(frame) + 3 * g;
+    const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
+    if (PATCH != VU_PATCH_NONE) {
+      // a patched pixel has bg == frame, hence fg = HSV2BGR(hsv - (1 - a/255) * hsv): with the alpha == 0 patch that is
+      // HSV2BGR(0,0,0) = black.  Whole warps of such pixels (everything outside the matte) skip the arithmetic, and the
+      // loads too when the patched background is not asked for.
+      const bool allzero = PATCH == VU_PATCH_ALPHA_EQ0 && aw == 0u;
+      if (__all_sync(__activemask(), allzero)) {
+        unsigned* d4 = reinterpret_cast<unsigned*>(fg_out) + 3 * g;
+        d4[0] = 0u; d4[1] = 0u; d4[2] = 0u;
+        if (WRITE_BG) {
+          unsigned* e4 = reinterpret_cast<unsigned*>(bg_out) + 3 * g;
+          e4[0] = __ldg(f4); e4[1] = __ldg(f4 + 1); e4[2] = __ldg(f4 + 2);
+        }
+        continue;
+      }
+    }
     int c[12], q[12], o[12];
     unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
     if (BGMODE == 1) {
@@ -51,7 +67,6 @@ __global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restri
       const unsigned* b4 = reinterpret_cast<const unsigned*>(bg) + 3 * gb;
       unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
     }
-    const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int a = (aw >> (8 * i)) & 255;
