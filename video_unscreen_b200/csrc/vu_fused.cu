@@ -22,6 +22,7 @@
 //  vu_fuzzy_count      is_pixel_inrange (bg colour) + fuzzy area + the two
 //                      counts of trimap/agent.py:90-94 in one pass.
 #include "vu_common.cuh"
+#include "vu_cross_march.cuh"
 
 namespace vu {
 namespace {
@@ -240,6 +241,25 @@ extern "C" int vu_cross_chain_u8(const uint8_t* src, uint8_t* dst, int n, int h,
   }
   if (total > CC_MAXPASS) return VU_ERR_UNSUPPORTED;
   if (n == 0) return VU_OK;
+  if (n > 65535) return VU_ERR_UNSUPPORTED;
+  // the chains the reference runs go to the register-marching kernels (vu_cross_march.cuh); anything else to the
+  // generic shared-memory kernel below
+  {
+    unsigned emask = 0;
+    int k = 0;
+    for (int i = 0; i < nseg; ++i)
+      for (int j = 0; j < iters[i]; ++j, ++k)
+        if (ops[i] == VU_ERODE) emask |= 1u << k;
+    const auto* st = reinterpret_cast<const unsigned long long*>(stats2);
+    const unsigned all = total > 0 ? (1u << total) - 1u : 0u;
+#define VU_MARCH(NP, EM) \
+  if (total == NP && emask == (EM)) return march::launch<NP, (EM), 0>(src, dst, n, h, w, st, thr_ratio, S(stream));
+    VU_MARCH(8, 0x3Cu)   // colour filter postprocess: dilate 2, erode 2, erode 2, dilate 2
+    VU_MARCH(1, 0x0u) VU_MARCH(2, 0x0u) VU_MARCH(3, 0x0u) VU_MARCH(4, 0x0u) VU_MARCH(5, 0x0u)
+    VU_MARCH(1, 0x1u) VU_MARCH(2, 0x3u) VU_MARCH(3, 0x7u) VU_MARCH(4, 0xFu) VU_MARCH(5, 0x1Fu)
+#undef VU_MARCH
+    (void)all;
+  }
   dim3 grid((w + CC_TW - 1) / CC_TW, (h + CC_TH - 1) / CC_TH, n);
   const size_t smem = 2 * sizeof(uint2) * make_geo(total).cells;
   cross_chain_kernel<0><<<grid, CC_THREADS, smem, S(stream)>>>(src, dst, h, w, ch, reinterpret_cast<const unsigned long long*>(stats2), thr_ratio,
@@ -252,6 +272,15 @@ extern "C" int vu_trimap_core_u8(const uint8_t* src, uint8_t* dst, int n, int h,
   VU_REQUIRE(src && dst && n >= 0 && h > 0 && w > 0 && iters >= 0);
   if (iters > CC_MAXPASS) return VU_ERR_UNSUPPORTED;
   if (n == 0) return VU_OK;
+  if (n > 65535) return VU_ERR_UNSUPPORTED;
+  switch (iters) {   // register-marching kernels for the usual radii
+    case 1: return march::launch<1, 0u, 1>(src, dst, n, h, w, nullptr, 0.0, S(stream));
+    case 2: return march::launch<2, 0u, 1>(src, dst, n, h, w, nullptr, 0.0, S(stream));
+    case 3: return march::launch<3, 0u, 1>(src, dst, n, h, w, nullptr, 0.0, S(stream));
+    case 4: return march::launch<4, 0u, 1>(src, dst, n, h, w, nullptr, 0.0, S(stream));
+    case 5: return march::launch<5, 0u, 1>(src, dst, n, h, w, nullptr, 0.0, S(stream));
+    default: break;
+  }
   Chain ch{1, {VU_DILATE, 0, 0, 0}, {iters, 0, 0, 0}};
   dim3 grid((w + CC_TW - 1) / CC_TW, (h + CC_TH - 1) / CC_TH, n);
   const size_t smem = 4 * sizeof(uint2) * make_geo(iters).cells;
