@@ -425,16 +425,19 @@ __device__ __forceinline__ AxisC up_axis(int d, int dst, int src, bool reset) {
   return a;
 }
 
-constexpr int RU_TW = 128, RU_TH = 64;   // dst tile; 256 threads = 32 column groups x 8 row lanes
-constexpr int RU_SMAX = 6144;            // staged source bytes per tile (covers down-scales up to ~1.4x as well)
+constexpr int RU_TW = 128, RU_TH = 64;   // dst tile; 256 threads = 32 column groups (4 pixels) x 8 runs of 8 consecutive rows
+constexpr int RU_RUN = RU_TH / 8;
+// cv2's fixed-point bilinear: row[x] = S[y][x0]*a0 + S[y][x1]*a1;
+// dst = (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.  A thread owns 4 destination columns and walks down 8
+// consecutive destination rows: the horizontal pass of a source row is computed once and kept in registers for all the
+// destination rows that use it (up-scaling: most consecutive rows share their source rows).  Source taps come through
+// the read-only path: the low-resolution maps are L2 / L1 resident.
 // MODE 0: plain   MODE 1: snap (0<v<255 -> 128), then 128 where flags[n]==0 && fuzzy
 template <int MODE>
 __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst, int dh, int dw,
                                                        const uint8_t* __restrict__ fuzzy, const uint8_t* __restrict__ flags,
                                                        const uint8_t* __restrict__ alt_src, const uint8_t* __restrict__ alt_flags) {
   __shared__ AxisC ytab[RU_TH];
-  __shared__ uint8_t stile[RU_SMAX];
-  __shared__ int sbox[4];  // sx0, sy0, scols, srows of the staged source window
   const int n = blockIdx.z;
   const int ty0 = blockIdx.y * RU_TH, tx0 = blockIdx.x * RU_TW;
   if (threadIdx.x < RU_TH && ty0 + threadIdx.x < dh) ytab[threadIdx.x] = up_axis(ty0 + threadIdx.x, dh, sh, false);
@@ -443,37 +446,52 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
   AxisC xa[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) xa[k] = up_axis(min(x + k, dw - 1), dw, sw, true);
-  if (threadIdx.x == 0) {
-    const AxisC xl = up_axis(tx0, dw, sw, true), xr = up_axis(min(tx0 + RU_TW - 1, dw - 1), dw, sw, true);
-    const AxisC yt = up_axis(ty0, dh, sh, false), yb = up_axis(min(ty0 + RU_TH - 1, dh - 1), dh, sh, false);
-    sbox[0] = xl.i0; sbox[1] = yt.i0; sbox[2] = xr.i1 - xl.i0 + 1; sbox[3] = yb.i1 - yt.i0 + 1;
-  }
-  __syncthreads();
-  const uint8_t* s = src + (int64_t)n * sh * sw;
-  const int sx0 = sbox[0], sy0 = sbox[1], scols = sbox[2], srows = sbox[3];
-  const bool staged = scols * srows <= RU_SMAX;
-  const bool use_alt = alt_flags && alt_flags[n] != 0;
-  if (staged && !use_alt) {
-    for (int i = threadIdx.x; i < scols * srows; i += FT) {
-      const int r = i / scols, c = i - r * scols;
-      stile[i] = __ldg(s + (int64_t)(sy0 + r) * sw + sx0 + c);
-    }
-  }
   __syncthreads();
   if (x >= dw) return;
+  const uint8_t* s = src + (int64_t)n * sh * sw;
   uint8_t* d = dst + (int64_t)n * dh * dw;
+  const bool use_alt = alt_flags && alt_flags[n] != 0;
   const bool ens = (MODE == 1) && fuzzy && flags && flags[n] == 0;
   const bool vec = (dw & 3) == 0 && x + 3 < dw && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
-  for (int r = ry; r < RU_TH; r += 8) {
+  auto hrow = [&](int sy, int (&R)[4]) {   // horizontal pass of source row sy, >> 4 as the vertical pass wants it
+    const uint8_t* r = s + (int64_t)sy * sw;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) R[k] = ((int)__ldg(r + xa[k].i0) * xa[k].w0 + (int)__ldg(r + xa[k].i1) * xa[k].w1) >> 4;
+  };
+  int R0[4], R1[4];
+  int y0c = -1, y1c = -1;   // source rows held in R0 / R1
+#pragma unroll 1
+  for (int rr = 0; rr < RU_RUN; ++rr) {
+    const int r = ry * RU_RUN + rr;
     const int y = ty0 + r;
     if (y >= dh) break;
     unsigned word = 0;
     if (use_alt) {
+      if (vec) word = __ldg(reinterpret_cast<const unsigned*>(alt_src + ((int64_t)n * dh + y) * dw + x));
+      else
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (x + k < dw) word |= (unsigned)__ldg(alt_src + ((int64_t)n * dh + y) * dw + x + k) << (8 * k);
+        for (int k = 0; k < 4; ++k)
+          if (x + k < dw) word |= (unsigned)__ldg(alt_src + ((int64_t)n * dh + y) * dw + x + k) << (8 * k);
     } else {
       const AxisC ya = ytab[r];
+      if (ya.i0 != y0c) {
+        if (ya.i0 == y1c) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) R0[k] = R1[k];
+        } else {
+          hrow(ya.i0, R0);
+        }
+        y0c = ya.i0;
+      }
+      if (ya.i1 != y1c) {
+        if (ya.i1 == y0c) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) R1[k] = R0[k];
+        } else {
+          hrow(ya.i1, R1);
+        }
+        y1c = ya.i1;
+      }
       unsigned fz = 0;
       if (ens) {
         if (vec) fz = __ldg(reinterpret_cast<const unsigned*>(fuzzy + ((int64_t)n * dh + y) * dw + x));
@@ -485,19 +503,7 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
       }
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        int s00, s01, s10, s11;
-        if (staged) {
-          const uint8_t* r0 = stile + (ya.i0 - sy0) * scols - sx0;
-          const uint8_t* r1 = stile + (ya.i1 - sy0) * scols - sx0;
-          s00 = r0[xa[k].i0]; s01 = r0[xa[k].i1]; s10 = r1[xa[k].i0]; s11 = r1[xa[k].i1];
-        } else {
-          const uint8_t* r0 = s + (int64_t)ya.i0 * sw;
-          const uint8_t* r1 = s + (int64_t)ya.i1 * sw;
-          s00 = __ldg(r0 + xa[k].i0); s01 = __ldg(r0 + xa[k].i1); s10 = __ldg(r1 + xa[k].i0); s11 = __ldg(r1 + xa[k].i1);
-        }
-        const int R0 = s00 * xa[k].w0 + s01 * xa[k].w1;
-        const int R1 = s10 * xa[k].w0 + s11 * xa[k].w1;
-        int v = (((ya.w0 * (R0 >> 4)) >> 16) + ((ya.w1 * (R1 >> 4)) >> 16) + 2) >> 2;
+        int v = (((ya.w0 * R0[k]) >> 16) + ((ya.w1 * R1[k]) >> 16) + 2) >> 2;
         v = min(255, max(0, v));
         if (MODE == 1) {
           if (v > 0 && v < 255) v = 128;
@@ -507,8 +513,9 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
       }
     }
     uint8_t* o = d + (int64_t)y * dw + x;
-    if (vec) *reinterpret_cast<unsigned*>(o) = word;
-    else {
+    if (vec) {
+      *reinterpret_cast<unsigned*>(o) = word;
+    } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (x + k < dw) o[k] = (uint8_t)(word >> (8 * k));
