@@ -401,6 +401,60 @@ __global__ void __launch_bounds__(FT) cf_lowres_kernel(const uint8_t* __restrict
   warp_block_atomic2(sum, cnt, stats2 + 2 * n);
 }
 
+// S = 2, 16 full-resolution columns per thread (w % 16 == 0, 16-byte aligned rows): 128-bit loads, eight outputs,
+// all the loads of a thread in flight before the first conversion
+__global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
+                                                             int tw, const uint8_t* __restrict__ lut3d, uint8_t* __restrict__ alpha_lo,
+                                                             unsigned long long* __restrict__ stats2) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int per_row = tw / 8;
+  const int64_t items = (int64_t)th * per_row;
+  const uint8_t* fr = frames + (int64_t)n * h * w * 3;
+  const uint8_t* mk = masks + (int64_t)n * h * w;
+  uint8_t* out = alpha_lo + (int64_t)n * th * tw;
+  unsigned long long sum = 0, cnt = 0;
+  for (int64_t it = (int64_t)blockIdx.x * FT + threadIdx.x; it < items; it += (int64_t)gridDim.x * FT) {
+    const int y = (int)(it / per_row), xg = (int)(it - (int64_t)y * per_row);
+    uint4 fv[2][3], mv[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint4* p = reinterpret_cast<const uint4*>(fr + ((int64_t)(2 * y + r) * w + 16 * xg) * 3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fv[r][k] = ldg_stream16(p + k);
+      mv[r] = ldg_stream16(mk + (int64_t)(2 * y + r) * w + 16 * xg);
+    }
+    unsigned res[2] = {0u, 0u};
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {   // output o: full-resolution columns 2o, 2o+1 of both rows
+      int acc0 = 0, acc1 = 0, acc2 = 0, macc = 0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const unsigned* fw = reinterpret_cast<const unsigned*>(fv[r]);
+        const unsigned* mw = reinterpret_cast<const unsigned*>(&mv[r]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int q = 2 * o + k;   // pixel of the 16
+          const int b0 = 3 * q, b1 = 3 * q + 1, b2 = 3 * q + 2;
+          const int B = (fw[b0 >> 2] >> (8 * (b0 & 3))) & 255, G = (fw[b1 >> 2] >> (8 * (b1 & 3))) & 255, R = (fw[b2 >> 2] >> (8 * (b2 & 3))) & 255;
+          int hh, ss, vv;
+          bgr2hsv_px(B, G, R, tab, hh, ss, vv);
+          acc0 += hh; acc1 += ss; acc2 += vv;
+          macc += (mw[q >> 2] >> (8 * (q & 3))) & 255;
+        }
+      }
+      const int hh = (acc0 + 2) >> 2, ss = (acc1 + 2) >> 2, vv = (acc2 + 2) >> 2, mm = (macc + 2) >> 2;
+      const unsigned a = __ldg(lut3d + ((hh << 16) | (ss << 8) | vv));
+      if (a > 128 && mm > 0) { sum += a; ++cnt; }
+      res[o >> 2] |= a << (8 * (o & 3));
+    }
+    *reinterpret_cast<uint2*>(out + (int64_t)y * tw + 8 * xg) = make_uint2(res[0], res[1]);
+  }
+  warp_block_atomic2(sum, cnt, stats2 + 2 * n);
+}
+
 struct AxisC {
   int i0, i1, w0, w1;
 };
@@ -567,9 +621,14 @@ __global__ void __launch_bounds__(FT) fuzzy_count_kernel(const uint8_t* __restri
   unsigned* o4 = reinterpret_cast<unsigned*>(fuzzy) + (int64_t)n * ngroups;
   unsigned long long nf = 0, np = 0;
   for (int64_t g = (int64_t)blockIdx.x * FT + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * FT) {
+    const unsigned aw = __ldg(a4 + g);
+    // fuzzy = (alpha > 0) && in-range: a warp whose 128 pixels are all outside the matte neither loads nor converts the frame
+    if (__all_sync(__activemask(), aw == 0u)) {
+      o4[g] = 0u;
+      continue;
+    }
     int c[12];
     unpack12(__ldg(f4 + 3 * g), __ldg(f4 + 3 * g + 1), __ldg(f4 + 3 * g + 2), c);
-    const unsigned aw = __ldg(a4 + g);
     unsigned w = 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -631,7 +690,10 @@ extern "C" int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, 
   int e = record_cuda(cudaMemsetAsync(stats2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
   if (e) return e;
   auto* st = reinterpret_cast<unsigned long long*>(stats2);
-  if (s == 2) cf_lowres_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 2)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
+  const bool wide = s == 2 && (w % 16 == 0) && (tw % 8 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && ((reinterpret_cast<uintptr_t>(alpha_lo) & 7) == 0);
+  if (wide) cf_lowres2_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 8)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
+  else if (s == 2) cf_lowres_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 2)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   else cf_lowres_kernel<4><<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   VU_RETURN_LAUNCH();
 }
