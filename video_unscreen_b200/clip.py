@@ -16,6 +16,25 @@ from .unscreen.utils.fgfuncs import bgr2hsv_pixel
 from .unscreen.utils.imgprocess import get_target_size
 
 
+class Graphed:
+    """A clip pipeline captured as ONE CUDA graph: ``Graphed(fn)`` runs ``fn()`` once eagerly (warm-up: kernel
+    attributes, allocator), captures a second run, and every ``replay()`` relaunches the whole launch sequence
+    (about a hundred kernels for a 300-frame clip) with a single driver call.  The captured kernels read and write
+    the very tensors ``fn`` closed over: refill those in place between replays.  ``result`` is what ``fn`` returned
+    during capture (tensors owned by the graph's memory pool, overwritten by every replay)."""
+
+    def __init__(self, fn):
+        fn()
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fn()
+
+    def replay(self):
+        self.graph.replay()
+        return self.result
+
+
 def _chunks(n, chunk):
     for s in range(0, n, chunk):
         yield s, min(n, s + chunk)
@@ -90,18 +109,22 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
     return tri
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16):
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None, bg_tile=None):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
     stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
-    bgimg[alpha<128] = frame[...] -> get_fg.  Returns alpha, trimap, fg, bg."""
+    bgimg[alpha<128] = frame[...] -> get_fg.  Returns alpha, trimap, fg, bg.
+    ``bg_color`` ((3,) BGR, host) / ``bg_tile`` ([1,4,3] device) default to the agent's background colour; pass them
+    in when the call is captured into a CUDA graph (fetching them synchronises)."""
     n, h, w, _ = frames.shape
     dev = frames.device
     alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     fg = torch.empty_like(frames)
     bgo = torch.empty_like(frames)
-    bg_color = cf_agent.bg_color_bgr()
-    bg_tile = torch.from_numpy(np.tile(bg_color, (1, 4, 1))).to(dev)     # constant background: a 4-pixel periodic image
+    if bg_color is None:
+        bg_color = cf_agent.bg_color_bgr()
+    if bg_tile is None:
+        bg_tile = torch.from_numpy(np.tile(bg_color, (1, 4, 1))).to(dev)     # constant background: a 4-pixel periodic image
     for s, e in _chunks(n, chunk):
         a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk)
         alpha[s:e] = a
