@@ -116,12 +116,13 @@ __global__ void __launch_bounds__(WARPS * 32) cross_march_kernel(const uint8_t* 
   const bool all_in = px >= 0 && px + 3 < w;
   const bool writer = lane >= HG && lane < 32 - HG && px < w;
   const int T = (Y1 - Y0) + 2 * NP;
-  auto one = [&](auto ph, int t) {
-    constexpr int PH = decltype(ph)::value;
+  // the row of step t: loaded PF steps ahead (a step is a long dependent chain of shuffles and min/max: without the
+  // look-ahead every step would start with a full L2 round trip)
+  constexpr int PF = 4;
+  auto load_row = [&](int t) -> unsigned {
     const int y_in = Y0 - NP + t;
     unsigned word = 0;
-    const bool row_in = (unsigned)y_in < (unsigned)h;
-    if (row_in && px + 3 >= 0 && px < w) {
+    if (t < T && (unsigned)y_in < (unsigned)h && px + 3 >= 0 && px < w) {
       const uint8_t* p = src + frame + (int64_t)y_in * w + px;
       if (all_in && vec) {
         word = __ldg(reinterpret_cast<const unsigned*>(p));
@@ -131,6 +132,15 @@ __global__ void __launch_bounds__(WARPS * 32) cross_march_kernel(const uint8_t* 
           if ((unsigned)(px + k) < (unsigned)w) word |= (unsigned)__ldg(p + k) << (8 * k);
       }
     }
+    return word;
+  };
+  unsigned q[PF];
+#pragma unroll
+  for (int i = 0; i < PF; ++i) q[i] = load_row(i);
+  auto one = [&](auto ph, int t, unsigned word) {
+    constexpr int PH = decltype(ph)::value;
+    const int y_in = Y0 - NP + t;
+    const bool row_in = (unsigned)y_in < (unsigned)h;
     if (MODE == 0 && ithr > 0) {
       unsigned r = 0;
 #pragma unroll
@@ -173,9 +183,15 @@ __global__ void __launch_bounds__(WARPS * 32) cross_march_kernel(const uint8_t* 
       }
     }
   };
-  for (int t = 0; t < T; t += 2) {
-    one(std::integral_constant<int, 0>{}, t);
-    if (t + 1 < T) one(std::integral_constant<int, 1>{}, t + 1);
+  static_assert(PF == 4, "the loop below is unrolled over the look-ahead queue");
+  for (int t = 0; t < T; t += 4) {
+    const unsigned w0 = q[0], w1 = q[1], w2 = q[2], w3 = q[3];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) q[i] = load_row(t + PF + i);
+    one(std::integral_constant<int, 0>{}, t, w0);
+    if (t + 1 < T) one(std::integral_constant<int, 1>{}, t + 1, w1);
+    if (t + 2 < T) one(std::integral_constant<int, 0>{}, t + 2, w2);
+    if (t + 3 < T) one(std::integral_constant<int, 1>{}, t + 3, w3);
   }
 }
 

@@ -458,9 +458,11 @@ __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __re
 struct AxisC {
   int i0, i1, w0, w1;
 };
-__device__ __forceinline__ AxisC up_axis(int d, int dst, int src, bool reset) {
+__device__ __forceinline__ double up_scale(int dst, int src) {
   const double inv_scale = (double)dst / (double)src;
-  const double scale = 1.0 / inv_scale;
+  return 1.0 / inv_scale;
+}
+__device__ __forceinline__ AxisC up_axis(int d, double scale, int src, bool reset) {
   float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
   int i0 = (int)floorf(f);
   float fr = __fsub_rn(f, (float)i0);
@@ -479,7 +481,7 @@ __device__ __forceinline__ AxisC up_axis(int d, int dst, int src, bool reset) {
   return a;
 }
 
-constexpr int RU_TW = 128, RU_TH = 64;   // dst tile; 256 threads = 32 column groups (4 pixels) x 8 runs of 8 consecutive rows
+constexpr int RU_TW = 128, RU_TH = 128;   // dst tile; 256 threads = 32 column groups (4 pixels) x 8 runs of 16 consecutive rows
 constexpr int RU_RUN = RU_TH / 8;
 // cv2's fixed-point bilinear: row[x] = S[y][x0]*a0 + S[y][x1]*a1;
 // dst = (((b0*(R0>>4))>>16) + ((b1*(R1>>4))>>16) + 2) >> 2.  A thread owns 4 destination columns and walks down 8
@@ -494,12 +496,13 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
   __shared__ AxisC ytab[RU_TH];
   const int n = blockIdx.z;
   const int ty0 = blockIdx.y * RU_TH, tx0 = blockIdx.x * RU_TW;
-  if (threadIdx.x < RU_TH && ty0 + threadIdx.x < dh) ytab[threadIdx.x] = up_axis(ty0 + threadIdx.x, dh, sh, false);
+  const double ysc = up_scale(dh, sh), xsc = up_scale(dw, sw);
+  if (threadIdx.x < RU_TH && ty0 + threadIdx.x < dh) ytab[threadIdx.x] = up_axis(ty0 + threadIdx.x, ysc, sh, false);
   const int gx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int x = tx0 + 4 * gx;
   AxisC xa[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) xa[k] = up_axis(min(x + k, dw - 1), dw, sw, true);
+  for (int k = 0; k < 4; ++k) xa[k] = up_axis(min(x + k, dw - 1), xsc, sw, true);
   __syncthreads();
   if (x >= dw) return;
   const uint8_t* s = src + (int64_t)n * sh * sw;
