@@ -115,8 +115,18 @@ def main():
         def step():
             return clip.green_clip(fr, sg, cf, ta, chunk=8, bg_color=col, bg_tile=tile)
         ms, launches = timed(step, max(2, args.steps // 2), warmup=1)
+        a_d, t_d, f_d, b_d = [x[1].cpu().numpy() for x in (step() if not GRAPH else clip.green_clip(fr, sg, cf, ta, chunk=8, bg_color=col, bg_tile=tile))]
+        lb, lf, bgh = cf.tables()
+        t0 = time.perf_counter()
+        a_o, _, _ = R.cf_forward_predict(fr_h[1], sg_h[1], lb, lf, bgh, 960)
+        t_o = R.generate_trimap_withbg(a_o, fr_h[1], col, 960)
+        b_o = R.patch_bg(np.broadcast_to(col, fr_h[1].shape), fr_h[1], a_o, "lt128")
+        f_o = R.get_fg(fr_h[1], a_o, b_o)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(a_d, a_o) and np.array_equal(t_d, t_o) and np.array_equal(b_d, b_o) and np.array_equal(f_d, f_o)
         report("green_4k", "BASELINE configs[2]: cf predict -> trimap -> patched bg -> get_fg at 4K (CNN stages skipped), 48 frames", n, ms, launches,
-               n * 12 * h * w, float("nan"), "not timed on the CPU (the 1080p row covers the same functions)", peak)
+               n * 12 * h * w, 1 / dt, "oracle cf_forward_predict + generate_trimap_withbg + patch + get_fg on 1 frame (numpy, 1 thread); alpha, trimap, "
+               "bg, fg bit-exact", peak)
         del fr, sg
 
     if want("replace_1080p"):
@@ -150,8 +160,25 @@ def main():
         def step():
             return clip.bgstep_clip(fr, masks, ta, chunk=8)
         ms, launches = timed(step, max(2, args.steps // 2), warmup=1)
+        bg_d, a_d, t_d, f_d = clip.bgstep_clip(fr, masks, ta, chunk=8)
+        i = n // 2
+        frame_h, mask_h, bg_h = fr[i].cpu().numpy(), masks[i].cpu().numpy(), bg_d.cpu().numpy()
+        rows = 64                                             # the oracle median on a strip, scaled (np.partition over 120 frames)
+        strip = fr[:, :rows].cpu().numpy()
+        t0 = time.perf_counter()
+        med_o = R.temporal_median(strip)
+        dt_med = (time.perf_counter() - t0) * (h / rows)
+        assert np.array_equal(med_o, bg_h[:rows])
+        t0 = time.perf_counter()
+        a_o = R.bgdiff_gate(frame_h, bg_h, mask_h, 25)
+        t_o = R.generate_trimap(a_o, 960)
+        f_o = R.get_fg(frame_h, a_o, R.patch_bg(bg_h, frame_h, a_o, "eq0"))
+        dt = time.perf_counter() - t0
+        assert np.array_equal(a_d[i].cpu().numpy(), a_o) and np.array_equal(t_d[i].cpu().numpy(), t_o) and np.array_equal(f_d[i].cpu().numpy(), f_o)
         report("bgstep_4k", "BASELINE configs[4] on one GPU tile: temporal median + difference gate + trimap + get_fg at 4K, 120 frames", n, ms, launches,
-               n * 12 * h * w + 6 * h * w, float("nan"), "not timed on the CPU", peak)
+               n * 12 * h * w + 6 * h * w, n / (dt_med + n * dt),
+               "oracle temporal_median on a 64-row strip (scaled to the frame) + bgdiff_gate + generate_trimap + patch + get_fg on 1 frame "
+               "(numpy, 1 thread); background, alpha, trimap, fg bit-exact", peak)
 
 
 if __name__ == "__main__":
