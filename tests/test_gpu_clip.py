@@ -95,3 +95,30 @@ def test_bgstep_and_replace_clip(env):
     out = env.clip.replace_clip(dev(fg), dev(alpha), dev(newbg)).cpu().numpy()
     for i in range(n):
         assert np.array_equal(out[i], R.replace_blend(fg[i], alpha[i], newbg)), i
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_equals_whole(env, world):
+    """SURVEY section 8e on one GPU, shards run one after the other: frame-range shards of the per-frame stages and
+    row-tile shards of the temporal median (video_unscreen_b200.shard) give exactly the whole-clip results."""
+    from video_unscreen_b200 import shard
+    n, h, w = 24, 96, 160
+    frames, masks, _ = synth.bgstep_clip(n, h, w, seed=6)
+    f_d, m_d = dev(frames), dev(masks)
+    ta = env.TA(input_long_side=80)
+    whole_bg, whole_alpha, whole_tri, whole_fg = env.clip.bgstep_clip(f_d, m_d, ta, thr=25, chunk=5)
+    # temporal median by row tiles (no halo: every pixel is independent)
+    tiles = [env.ops.temporal_median(f_d[:, r0:r1].contiguous()) for r0, r1, _, _ in shard.row_tiles(h, world)]
+    assert torch.equal(torch.cat(tiles, 0), whole_bg)
+    # per-frame stages by frame range, background shared
+    alphas, tris, fgs = [], [], []
+    for s, e in shard.frame_ranges(n, world, align=1):
+        if e == s:
+            continue
+        a = env.ops.bgdiff_gate(f_d[s:e], whole_bg, m_d[s:e], 25)
+        alphas.append(a)
+        tris.append(env.clip.trimap_clip(a, ta, chunk=4))
+        fgs.append(env.ops.get_fg(f_d[s:e], a, whole_bg, 2))
+    assert torch.equal(torch.cat(alphas, 0), whole_alpha)
+    assert torch.equal(torch.cat(tris, 0), whole_tri)
+    assert torch.equal(torch.cat(fgs, 0), whole_fg)

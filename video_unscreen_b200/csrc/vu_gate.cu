@@ -54,36 +54,63 @@ __global__ void __launch_bounds__(GT_THREADS) bgdiff_gate_kernel(const uint8_t* 
   const int px = X0 - 4 + 4 * lane;                 // first of this lane's 4 staged pixels
   const int teff = thr < 254 ? thr : 254;           // gray > thr || gray == 255
   // ---- B = (gray(|frame - bg|) > thr), one bit per pixel, 0 outside the image ----
-  for (int r = warp; r < GT_ROWS; r += GT_THREADS / 32) {
-    const int gy = Y0 - 4 + r;
-    unsigned nib = 0;
-    if ((unsigned)gy < (unsigned)h && px + 3 >= 0 && px < w) {
-      const int64_t o = ((int64_t)gy * w + px) * 3;
-      if (px >= 0 && px + 3 < w) {
+  // 4 pixels = 3 words.  |frame - bg| of 4 bytes is one VABSDIFF4; BGR2GRAY's 15-bit coefficients are split into bytes
+  // (3735 = 14*256 + 151, 19235 = 75*256 + 35, 9798 = 38*256 + 70), so that the weighted sum of a pixel is two IDP.4A over
+  // the word that holds its three bytes (a PRMT gathers the two pixels that straddle words): 6 instructions per pixel
+  // instead of ~20.  A warp takes its rows three at a time so that 18 loads per lane are in flight.
+  const bool lane_full = px >= 0 && px + 3 < w;
+  const bool lane_any = px + 3 >= 0 && px < w;
+  constexpr unsigned WH = 14u | (75u << 8) | (38u << 16), WL = 151u | (35u << 8) | (70u << 16);
+  const unsigned limit = ((unsigned)teff + 1u) << 15;   // gray > teff  <=>  weighted sum + 16384 >= (teff + 1) << 15
+  constexpr int NW = GT_THREADS / 32, RB = 3;
+  for (int r0 = warp; r0 < GT_ROWS; r0 += NW * RB) {
+    unsigned fw[RB][3], bw[RB][3];
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      const int r = r0 + j * NW, gy = Y0 - 4 + r;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fw[j][k] = bw[j][k] = 0u;
+      if (r < GT_ROWS && (unsigned)gy < (unsigned)h && lane_full) {
+        const int64_t o = ((int64_t)gy * w + px) * 3;
         const unsigned* f4 = reinterpret_cast<const unsigned*>(fr + o);
         const unsigned* b4 = reinterpret_cast<const unsigned*>(bgp + o);
-        int c[12], q[12];
-        unpack12(__ldg(f4), __ldg(f4 + 1), __ldg(f4 + 2), c);
-        unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int y = bgr2gray_px(abs(c[3 * k] - q[3 * k]), abs(c[3 * k + 1] - q[3 * k + 1]), abs(c[3 * k + 2] - q[3 * k + 2]));
-          nib |= (unsigned)(y > teff) << k;
-        }
-      } else {
-        for (int k = 0; k < 4; ++k) {
-          const int x = px + k;
-          if (x < 0 || x >= w) continue;
-          const uint8_t* f = fr + o + 3 * k;
-          const uint8_t* b = bgp + o + 3 * k;
-          const int y = bgr2gray_px(abs((int)__ldg(f) - (int)__ldg(b)), abs((int)__ldg(f + 1) - (int)__ldg(b + 1)),
-                                    abs((int)__ldg(f + 2) - (int)__ldg(b + 2)));
-          nib |= (unsigned)(y > teff) << k;
-        }
+        for (int k = 0; k < 3; ++k) { fw[j][k] = __ldg(f4 + k); bw[j][k] = __ldg(b4 + k); }
       }
     }
-    const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
-    if ((lane & 7) == 0) B[r][lane >> 3] = word;
+#pragma unroll
+    for (int j = 0; j < RB; ++j) {
+      const int r = r0 + j * NW, gy = Y0 - 4 + r;
+      if (r >= GT_ROWS) break;   // warp-uniform
+      unsigned nib = 0;
+      if ((unsigned)gy < (unsigned)h) {
+        if (lane_full) {
+          const unsigned d0 = __vabsdiffu4(fw[j][0], bw[j][0]), d1 = __vabsdiffu4(fw[j][1], bw[j][1]), d2 = __vabsdiffu4(fw[j][2], bw[j][2]);
+          const unsigned ps[4] = {d0,                             // B G R x
+                                  __byte_perm(d0, d1, 0x0543),    // d0.3 d1.0 d1.1 x
+                                  __byte_perm(d1, d2, 0x0432),    // d1.2 d1.3 d2.0 x
+                                  d2 >> 8};                       // d2.1 d2.2 d2.3 0
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const unsigned num = __dp4a(ps[k], WH, 0u) * 256u + __dp4a(ps[k], WL, 16384u);
+            nib |= (unsigned)(num >= limit) << k;
+          }
+        } else if (lane_any) {   // the group straddles the image border: pixel by pixel
+          const int64_t o = ((int64_t)gy * w + px) * 3;
+          for (int k = 0; k < 4; ++k) {
+            const int x = px + k;
+            if (x < 0 || x >= w) continue;
+            const uint8_t* f = fr + o + 3 * k;
+            const uint8_t* b = bgp + o + 3 * k;
+            const int y = bgr2gray_px(abs((int)__ldg(f) - (int)__ldg(b)), abs((int)__ldg(f + 1) - (int)__ldg(b + 1)),
+                                      abs((int)__ldg(f + 2) - (int)__ldg(b + 2)));
+            nib |= (unsigned)(y > teff) << k;
+          }
+        }
+      }
+      const unsigned word = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
+      if ((lane & 7) == 0) B[r][lane >> 3] = word;
+    }
   }
   __syncthreads();
   // in-image mask of a staged word (bit i = pixel X0 - 4 + 32 j + i)
