@@ -648,6 +648,58 @@ __global__ void __launch_bounds__(FT) fuzzy_count_kernel(const uint8_t* __restri
   warp_block_atomic2(nf, np, counts2 + 2 * n);
 }
 
+// the same at 16 pixels per thread (npix % 16 == 0, 16-byte aligned): 128-bit loads keep enough bytes in flight for
+// a streaming kernel (4-byte loads, one per thread at a time, cap it near 1.2 TB/s whatever the arithmetic)
+__global__ void __launch_bounds__(FT) fuzzy_count16_kernel(const uint4* __restrict__ frames, const uint4* __restrict__ alpha, int64_t ngroups, int lo0,
+                                                           int lo1, int lo2, int hi0, int hi1, int hi2, uint4* __restrict__ fuzzy,
+                                                           unsigned long long* __restrict__ counts2) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int n = blockIdx.y;
+  const uint4* f16 = frames + (int64_t)n * ngroups * 3;
+  const uint4* a16 = alpha + (int64_t)n * ngroups;
+  uint4* o16 = fuzzy + (int64_t)n * ngroups;
+  unsigned long long nf = 0, np = 0;
+  for (int64_t g = (int64_t)blockIdx.x * FT + threadIdx.x; g < ngroups; g += (int64_t)gridDim.x * FT) {
+    const uint4 av = ldg_stream16(a16 + g);
+    if ((av.x | av.y | av.z | av.w) == 0u) {   // 16 pixels outside the matte: neither load nor convert the frame
+      o16[g] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
+    }
+    uint4 fv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(f16 + 3 * g + k);
+    const unsigned* fw = reinterpret_cast<const unsigned*>(fv);
+    const unsigned aw[4] = {av.x, av.y, av.z, av.w};
+    unsigned ow[4];
+    unsigned cf = 0, cp = 0;
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4) {
+      unsigned w = 0;
+      if (aw[w4] != 0u) {
+        int c[12];
+        unpack12(fw[3 * w4], fw[3 * w4 + 1], fw[3 * w4 + 2], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int hh, ss, vv;
+          bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, hh, ss, vv);
+          const bool in = (hh >= lo0) & (hh <= hi0) & (ss >= lo1) & (ss <= hi1) & (vv >= lo2) & (vv <= hi2);
+          const bool pos = ((aw[w4] >> (8 * i)) & 255u) != 0;
+          cp += pos;
+          cf += pos && in;
+          w |= (unsigned)(pos && in) << (8 * i);
+        }
+      }
+      ow[w4] = w;
+    }
+    nf += cf;
+    np += cp;
+    o16[g] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+  warp_block_atomic2(nf, np, counts2 + 2 * n);
+}
+
 // nearest down-scale of the trimap source mask with the ensemble clearing fused:
 // out[y][x] = (flags[n] == 0 && fuzzy[sy][sx]) ? 0 : mask[sy][sx]
 __global__ void __launch_bounds__(FT) trimap_src_lo_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ fuzzy,
@@ -664,6 +716,40 @@ __global__ void __launch_bounds__(FT) trimap_src_lo_kernel(const uint8_t* __rest
     int v = __ldg(mask + si);
     if (ens && __ldg(fuzzy + si)) v = 0;
     out[(int64_t)n * total + i] = (uint8_t)v;
+  }
+}
+
+// exact integer scales S = 2, 4 (w == S*tw, h == S*th, tw % 4 == 0): floor(x * S) == S*x, four outputs per thread from
+// one 8- or 16-byte load of the source row (and of the fuzzy row), no float64 coordinates
+template <int SC>
+__global__ void __launch_bounds__(FT) trimap_src_lo_int_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ fuzzy,
+                                                               const uint8_t* __restrict__ flags, int h, int w, int th, int tw,
+                                                               uint8_t* __restrict__ out) {
+  const int n = blockIdx.y;
+  const bool ens = fuzzy && flags && flags[n] == 0;
+  const int gpr = tw / 4;   // 4-output groups per row
+  const int64_t total = (int64_t)th * gpr;
+  auto pick = [](const uint8_t* p) -> unsigned {   // bytes 0, S, 2S, 3S of the 4S bytes at p
+    if (SC == 2) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+      return __byte_perm(v.x, v.y, 0x6420);
+    } else {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+      return (v.x & 255u) | ((v.y & 255u) << 8) | ((v.z & 255u) << 16) | (v.w << 24);
+    }
+  };
+  for (int64_t i = (int64_t)blockIdx.x * FT + threadIdx.x; i < total; i += (int64_t)gridDim.x * FT) {
+    const int y = (int)(i / gpr), xg = (int)(i - (int64_t)y * gpr);
+    const int64_t si = ((int64_t)n * h + (int64_t)SC * y) * w + (int64_t)4 * SC * xg;
+    unsigned v = pick(mask + si);
+    if (ens) {
+      const unsigned f = pick(fuzzy + si);
+      // zero the bytes whose fuzzy byte is non-zero
+      const unsigned nz = ((f & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | f;          // bit 7 of every non-zero byte
+      const unsigned keep = ~(((nz >> 7) & 0x01010101u) * 255u);
+      v &= keep;
+    }
+    *reinterpret_cast<unsigned*>(out + ((int64_t)n * th + y) * tw + 4 * xg) = v;
   }
 }
 
@@ -738,8 +824,15 @@ extern "C" int vu_fuzzy_count(const uint8_t* frames, const uint8_t* alpha, int n
   int e = record_cuda(cudaMemsetAsync(counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
   if (e) return e;
   if (npix == 0) return VU_OK;
-  fuzzy_count_kernel<<<frame_grid(n, npix / 4), FT, 0, S(stream)>>>(frames, alpha, npix / 4, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], fuzzy01,
-                                                                    reinterpret_cast<unsigned long long*>(counts2));
+  const bool wide = npix % 16 == 0 && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) && ((reinterpret_cast<uintptr_t>(alpha) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(fuzzy01) & 15) == 0);
+  if (wide)
+    fuzzy_count16_kernel<<<frame_grid(n, npix / 16), FT, 0, S(stream)>>>(reinterpret_cast<const uint4*>(frames), reinterpret_cast<const uint4*>(alpha),
+                                                                         npix / 16, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2],
+                                                                         reinterpret_cast<uint4*>(fuzzy01), reinterpret_cast<unsigned long long*>(counts2));
+  else
+    fuzzy_count_kernel<<<frame_grid(n, npix / 4), FT, 0, S(stream)>>>(frames, alpha, npix / 4, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], fuzzy01,
+                                                                      reinterpret_cast<unsigned long long*>(counts2));
   VU_RETURN_LAUNCH();
 }
 
@@ -748,6 +841,14 @@ extern "C" int vu_trimap_src_lo(const uint8_t* mask, const uint8_t* fuzzy, const
   VU_REQUIRE(mask && out && n >= 0 && h > 0 && w > 0 && th > 0 && tw > 0);
   VU_REQUIRE((fuzzy == nullptr) == (flags == nullptr));
   if (n == 0) return VU_OK;
-  trimap_src_lo_kernel<<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, out);
+  const int sc = (w == 2 * tw && h == 2 * th) ? 2 : ((w == 4 * tw && h == 4 * th) ? 4 : 0);
+  const bool al = ((reinterpret_cast<uintptr_t>(mask) & 15) == 0) && (!fuzzy || (reinterpret_cast<uintptr_t>(fuzzy) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+  if (sc != 0 && tw % 4 == 0 && al) {   // w is then a multiple of 16 (or 8): the wide loads are aligned
+    if (sc == 2) trimap_src_lo_int_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 4)), FT, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, out);
+    else trimap_src_lo_int_kernel<4><<<frame_grid(n, (int64_t)th * (tw / 4)), FT, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, out);
+  } else {
+    trimap_src_lo_kernel<<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, out);
+  }
   VU_RETURN_LAUNCH();
 }
