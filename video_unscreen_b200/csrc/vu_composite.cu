@@ -95,6 +95,92 @@ __global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restri
   }
 }
 
+// get_fg at 16 pixels per thread: 128-bit streaming loads / stores (enough bytes in flight per thread for HBM), the
+// alpha == 0 early-out per thread.  Same arithmetic as get_fg_kernel, one 4-pixel group at a time.
+// groups16 = 16-pixel groups of the input; bg as in get_fg_kernel (BGMODE 0, 1, 2), counted in 16-pixel groups too.
+template <int PATCH, bool WRITE_BG, int BGMODE>
+__global__ void __launch_bounds__(THREADS) get_fg16_kernel(const uint4* __restrict__ frame, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
+                                                           int64_t ngroups, int64_t bg_groups, uint4* __restrict__ fg_out, uint4* __restrict__ bg_out) {
+  __shared__ HsvTab tab;
+  __shared__ float ktab[256];   // 1 - alpha/255. for every alpha byte
+  hsv_tab_init(tab);
+  for (int a = threadIdx.x; a < 256; a += blockDim.x) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t rep = BGMODE == 2 ? (int64_t)blockIdx.y * bg_groups : 0;
+  const int64_t gend = BGMODE == 2 ? bg_groups : ngroups;
+  int q0[12];
+  if (BGMODE == 1) {
+    const unsigned* b4 = reinterpret_cast<const unsigned*>(bg);
+    unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q0);
+  }
+  for (int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gl < gend; gl += stride) {
+    const int64_t g = rep + gl;
+    const uint4 av = ldg_stream16(alpha + g);
+    uint4 fv[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frame + 3 * g + k);
+    if (PATCH == VU_PATCH_ALPHA_EQ0 && (av.x | av.y | av.z | av.w) == 0u) {
+      // every pixel patched with itself: fg = HSV2BGR(hsv - 1.0 * hsv) = black
+#pragma unroll
+      for (int k = 0; k < 3; ++k) stg_stream16(fg_out + 3 * g + k, make_uint4(0u, 0u, 0u, 0u));
+      if (WRITE_BG) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) stg_stream16(bg_out + 3 * g + k, fv[k]);
+      }
+      continue;
+    }
+    uint4 qv[3];
+    if (BGMODE != 1) {
+      const int64_t gb = BGMODE == 0 ? g : gl;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) qv[k] = BGMODE == 0 ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k);
+    }
+    const unsigned* fw = reinterpret_cast<const unsigned*>(fv);
+    const unsigned* qw = reinterpret_cast<const unsigned*>(qv);
+    const unsigned aws[4] = {av.x, av.y, av.z, av.w};
+    uint4 ov[3], bv[3];
+    unsigned* ow = reinterpret_cast<unsigned*>(ov);
+    unsigned* bw = reinterpret_cast<unsigned*>(bv);
+#pragma unroll
+    for (int s4 = 0; s4 < 4; ++s4) {
+      int c[12], q[12], o[12];
+      unpack12(fw[3 * s4], fw[3 * s4 + 1], fw[3 * s4 + 2], c);
+      if (BGMODE == 1) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) q[i] = q0[i];
+      } else {
+        unpack12(qw[3 * s4], qw[3 * s4 + 1], qw[3 * s4 + 2], q);
+      }
+      const unsigned aw = aws[s4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int a = (aw >> (8 * i)) & 255;
+        const bool patch = (PATCH == VU_PATCH_ALPHA_LT128) ? (a < 128) : (PATCH == VU_PATCH_ALPHA_EQ0 ? (a == 0) : false);
+        q[3 * i] = patch ? c[3 * i] : q[3 * i];
+        q[3 * i + 1] = patch ? c[3 * i + 1] : q[3 * i + 1];
+        q[3 * i + 2] = patch ? c[3 * i + 2] : q[3 * i + 2];
+        int ih, is, iv, bh, bs, bvv;
+        bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
+        bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bvv);
+        const float k = ktab[a];   // 1 - alpha/255.
+        const int fh = trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
+        const int fs = trunc_clamp255(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
+        const int fv2 = trunc_clamp255(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bvv))));
+        hsv2bgr_px(fh, fs, fv2, tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+      }
+      pack12(o, ow[3 * s4], ow[3 * s4 + 1], ow[3 * s4 + 2]);
+      if (WRITE_BG) pack12(q, bw[3 * s4], bw[3 * s4 + 1], bw[3 * s4 + 2]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) stg_stream16(fg_out + 3 * g + k, ov[k]);
+    if (WRITE_BG) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) stg_stream16(bg_out + 3 * g + k, bv[k]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) get_bg_kernel(const uint8_t* __restrict__ alpha, const uint8_t* __restrict__ bg, int64_t ngroups,
                                                          uint8_t* __restrict__ out) {
   __shared__ HsvTab tab;
@@ -315,7 +401,30 @@ extern "C" int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8
     if (gx > need) gx = need;
     grid = dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)reps);
   }
-#define LAUNCH3(P, W, M) get_fg_kernel<P, W, M><<<grid, THREADS, 0, S(stream)>>>(frame, alpha, bg, ng, bgg, fg_out, bg_out)
+  // 16 pixels per thread whenever the sizes and alignments allow (BGMODE 3 has no wide variant)
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool wide = mode != 3 && npix % 16 == 0 && (mode == 1 || bg_npix % 16 == 0) && a16(frame) && a16(alpha) && a16(fg_out) && a16(bg_out) &&
+                    (mode == 1 || a16(bg));
+  const int64_t ng16 = ng / 4, bgg16 = mode == 1 ? 1 : bgg / 4;
+  if (wide) {
+    grid = dim3(grid_for(ng16, THREADS, 8));
+    if (mode == 2) {
+      const int64_t reps = ng16 / bgg16;
+      int64_t gx = ((int64_t)device_sms() * 8 + reps - 1) / reps;
+      const int64_t need = (bgg16 + THREADS - 1) / THREADS;
+      if (gx > need) gx = need;
+      grid = dim3((unsigned)(gx < 1 ? 1 : gx), (unsigned)reps);
+    }
+  }
+#define LAUNCH3(P, W, M)                                                                                                                  \
+  do {                                                                                                                                    \
+    if (wide && M != 3)                                                                                                                   \
+      get_fg16_kernel<P, W, (M == 3 ? 0 : M)><<<grid, THREADS, 0, S(stream)>>>(reinterpret_cast<const uint4*>(frame), reinterpret_cast<const uint4*>(alpha), \
+                                                                               reinterpret_cast<const uint4*>(bg), ng16, bgg16,          \
+                                                                               reinterpret_cast<uint4*>(fg_out), reinterpret_cast<uint4*>(bg_out)); \
+    else                                                                                                                                  \
+      get_fg_kernel<P, W, M><<<grid, THREADS, 0, S(stream)>>>(frame, alpha, bg, ng, bgg, fg_out, bg_out);                                 \
+  } while (0)
 #define LAUNCH(P, W)                      \
   do {                                    \
     if (mode == 0) LAUNCH3(P, W, 0);      \
