@@ -109,10 +109,12 @@ __global__ void __launch_bounds__(THREADS) get_fg16_kernel(const uint4* __restri
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t rep = BGMODE == 2 ? (int64_t)blockIdx.y * bg_groups : 0;
   const int64_t gend = BGMODE == 2 ? bg_groups : ngroups;
-  int q0[12];
+  int q0[12], h0[4], s0[4], v0[4];   // BGMODE 1: the constant background group and its HSV, converted once
   if (BGMODE == 1) {
     const unsigned* b4 = reinterpret_cast<const unsigned*>(bg);
     unpack12(__ldg(b4), __ldg(b4 + 1), __ldg(b4 + 2), q0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bgr2hsv_px(q0[3 * i], q0[3 * i + 1], q0[3 * i + 2], tab, h0[i], s0[i], v0[i]);
   }
   for (int64_t gl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gl < gend; gl += stride) {
     const int64_t g = rep + gl;
@@ -162,7 +164,13 @@ __global__ void __launch_bounds__(THREADS) get_fg16_kernel(const uint4* __restri
         q[3 * i + 2] = patch ? c[3 * i + 2] : q[3 * i + 2];
         int ih, is, iv, bh, bs, bvv;
         bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
-        bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bvv);
+        if (BGMODE == 1) {   // a patched pixel's background IS the frame pixel: no second conversion
+          bh = patch ? ih : h0[i];
+          bs = patch ? is : s0[i];
+          bvv = patch ? iv : v0[i];
+        } else {
+          bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bvv);
+        }
         const float k = ktab[a];   // 1 - alpha/255.
         const int fh = trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
         const int fs = trunc_clamp255(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
