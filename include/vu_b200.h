@@ -224,6 +224,11 @@ int vu_sub_wrap_u8(const uint8_t* a, const uint8_t* b, int64_t count, uint8_t* o
  * section 8 a23; oracle np.median(stack,0).astype(u8)): even n ->
  * (sorted[n/2-1] + sorted[n/2]) >> 1.  1 <= n <= 65535. */
 int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream);
+/* the same with caller-provided scratch memory (device, vu_temporal_median_workspace_bytes(n, m) bytes; 0 for
+ * n <= 608): clips of more than 608 frames then take the estimate + streaming-refine path instead of histograms */
+size_t vu_temporal_median_workspace_bytes(int n, int64_t m);
+int vu_temporal_median_u8_ws(const uint8_t* frames, int n, int64_t m, uint8_t* out, void* workspace,
+                             size_t workspace_bytes, vu_stream_t stream);
 /* masked temporal mean, bg_offline.py:106-125.  masks are the ALREADY DILATED
  * single-channel masks [n][h*w] (dilate_mask(mask,3,2) is a vu_morph_u8 call).
  * bg_out[h*w*3], mask_always_out[h*w] (255 where count <= min_count). */

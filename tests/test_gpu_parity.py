@@ -326,7 +326,8 @@ def test_temporal_median_vs_oracle(vu, n):
     assert np.array_equal(vu.U.temporal_median(gaps), R.temporal_median(gaps))
 
 
-@pytest.mark.parametrize("n", [81, 82, 83, 152, 153, 232, 233, 240, 241, 299, 300, 303, 304, 305, 306, 307, 464, 465, 607, 608])
+@pytest.mark.parametrize("n", [81, 82, 83, 152, 153, 232, 233, 240, 241, 299, 300, 303, 304, 305, 306, 307, 464, 465, 607, 608,
+                               609, 610, 912, 913, 1000, 1217, 2000])
 def test_temporal_median_concentrated(vu, n):
     """background-like data (the estimate + windowed search path of vu_median_sad.cuh): static background with small
     temporal noise, occluded for a contiguous run of frames, including backgrounds at the ends of the uint8 range;

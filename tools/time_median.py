@@ -16,7 +16,7 @@ def timeit(frames, tag):
 h, w = 1080, 1920
 g = torch.Generator(device=dev).manual_seed(0)
 base = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device=dev, generator=g).to(torch.int16)
-for n in (300, 299, 152, 600, 1000):
+for n in (300, 299, 152, 600, 1000, 2000):
     noise = torch.randint(-6, 7, (n, h, w, 3), dtype=torch.int16, device=dev, generator=g)
     frames = (base[None] + noise).clamp_(0, 255).to(torch.uint8); del noise
     timeit(frames, f"noise6 n={n}")

@@ -73,6 +73,8 @@ SIGNATURES = {
     "vu_binarise": (_i, [_p, _i64, _i, _p, _p]),
     "vu_sub_wrap_u8": (_i, [_p, _p, _i64, _p, _p]),
     "vu_temporal_median_u8": (_i, [_p, _i, _i64, _p, _p]),
+    "vu_temporal_median_workspace_bytes": (ctypes.c_size_t, [_i, _i64]),
+    "vu_temporal_median_u8_ws": (_i, [_p, _i, _i64, _p, _p, ctypes.c_size_t, _p]),
     "vu_masked_temporal_mean": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),
 }
 

@@ -470,5 +470,122 @@ __global__ void __launch_bounds__(WARPS * 32, CTAS) median_sad_tma_kernel(const 
   }
 }
 
+// ---- n > 608: estimate on a subsample, then ONE streaming pass that proves it ---------------------------------------
+//
+// More frames than the registers of a warp can hold.  Pass 1 is the tile kernel above on every s-th frame (a tensor
+// map with row pitch s*m: at most 304 frames), which leaves the subsample's median in `out`.  Pass 2 (this kernel)
+// streams ALL frames once, TMA chunk by chunk through a ring of shared-memory stages, and accumulates S(m) at the
+// eight values m = e-4 .. e+3 around the estimate e of every element: 8 VABSDIFF4 + 2 PRMT per input word, just
+// under what the ALU pipe can do at the HBM rate.  The minimiser of a convex function that is strictly inside the
+// probed range is the global one, so a strict interior minimum is the median (odd n), and a plateau that ends
+// inside the range gives both middle order statistics (even n).  Elements whose minimum touches the edge of the
+// range are not decided here: the segment is flagged and the histogram kernel redoes the flagged segments.
+// Frames are dealt to the two half-warps alternately; rows past the end of the clip are zero-filled by the TMA and
+// leave S arithmetically (S -= pads * m).
+constexpr int RF_WARPS = 8, RF_ROWS = 64, RF_STAGES = 4, RF_PROBES = 8;
+constexpr int RF_TILE = RF_WARPS * 64;
+constexpr int RF_STAGE_BYTES = RF_ROWS * RF_TILE;
+constexpr int RF_SMEM = RF_STAGES * RF_STAGE_BYTES + RF_STAGES * 16;
+
+__global__ void __launch_bounds__(RF_WARPS * 32, 1) median_refine_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ out,
+                                                                         uint8_t* __restrict__ flags, int n, int ntiles, int nchunks) {
+  extern __shared__ __align__(128) uint8_t smem_rf[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int part = lane >> 4, li = lane & 15;
+  uint64_t* mbar_p = reinterpret_cast<uint64_t*>(smem_rf + RF_STAGES * RF_STAGE_BYTES);
+  unsigned* count_p = reinterpret_cast<unsigned*>(mbar_p + RF_STAGES);
+  const unsigned mbar0 = (unsigned)__cvta_generic_to_shared(mbar_p);
+  const unsigned sdata = (unsigned)__cvta_generic_to_shared(smem_rf);
+  const int my_tiles = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int J = my_tiles * nchunks;   // chunks this CTA streams, in order
+  auto issue = [&](int j) {           // one thread
+    const int tile = blockIdx.x + (j / nchunks) * gridDim.x, chunk = j % nchunks, st = j % RF_STAGES;
+    mbar_expect_tx(mbar0 + 8 * st, RF_STAGE_BYTES);
+    tma_load_2d(sdata + st * RF_STAGE_BYTES, &tmap, tile * (RF_TILE / 4), chunk * RF_ROWS, mbar0 + 8 * st);
+  };
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < RF_STAGES; ++st) {
+      mbar_init(mbar0 + 8 * st, 1);
+      count_p[st] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int j = 0; j < RF_STAGES && j < J; ++j) issue(j);
+  const int delta = -(nchunks * RF_ROWS - n);   // zero rows past the clip
+  unsigned acc[RF_PROBES][4], q[RF_PROBES][4];
+  int a0[4];
+  const uint8_t* lane_row = smem_rf + part * RF_TILE + warp * 64 + li * 4;   // rows 2i + part of a stage
+  for (int j = 0; j < J; ++j) {
+    const int tile = blockIdx.x + (j / nchunks) * gridDim.x, chunk = j % nchunks, st = j % RF_STAGES;
+    const int64_t seg = (int64_t)tile * RF_WARPS + warp;
+    if (chunk == 0) {
+      const unsigned e = *reinterpret_cast<const unsigned*>(out + seg * 64 + li * 4);   // pass 1's estimates
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a0[k] = min(max((int)((e >> (8 * k)) & 255u) - 4, 0), 256 - RF_PROBES);
+#pragma unroll
+        for (int p = 0; p < RF_PROBES; ++p) {
+          q[p][k] = (unsigned)(a0[k] + p) * 0x01010101u;
+          acc[p][k] = 0u;
+        }
+      }
+    }
+    mbar_wait(mbar0 + 8 * st, (unsigned)((j / RF_STAGES) & 1));
+    const uint8_t* base = lane_row + st * RF_STAGE_BYTES;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {   // 2 x 16 rows of this part: 16 words, 4 groups
+      unsigned d[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) d[i] = *reinterpret_cast<const unsigned*>(base + (2 * (16 * h + i)) * RF_TILE);
+      transpose_groups<4>(d);
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+#pragma unroll
+        for (int p = 0; p < RF_PROBES; ++p)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) acc[p][k] = sad_acc(d[4 * g + k], q[p][k], acc[p][k]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      __threadfence_block();
+      const unsigned old = atomicAdd(count_p + st, 1u);
+      if (old % RF_WARPS == RF_WARPS - 1 && j + RF_STAGES < J) {
+        __threadfence_block();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(j + RF_STAGES);
+      }
+    }
+    if (chunk == nchunks - 1) {
+      unsigned res = 0;
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        unsigned S[RF_PROBES];
+        unsigned smin = 0xFFFFFFFFu;
+#pragma unroll
+        for (int p = 0; p < RF_PROBES; ++p) {
+          S[p] = acc[p][k] + __shfl_xor_sync(FULL, acc[p][k], 16) + (unsigned)(delta * (a0[k] + p));
+          smin = min(smin, S[p]);
+        }
+        int lo = -1, hi = -1;   // first / last probe at the minimum
+#pragma unroll
+        for (int p = 0; p < RF_PROBES; ++p)
+          if (S[p] == smin) {
+            if (lo < 0) lo = p;
+            hi = p;
+          }
+        // decided only if the minimum does not touch the edge of the probed range (or the edge of the byte range)
+        bad |= (lo == 0 && a0[k] > 0) || (hi == RF_PROBES - 1 && a0[k] + RF_PROBES - 1 < 255);
+        res |= (unsigned)((2 * a0[k] + lo + hi) >> 1) << (8 * k);
+      }
+      const bool any_bad = __any_sync(FULL, bad);
+      if (part == 0) *reinterpret_cast<unsigned*>(out + seg * 64 + li * 4) = res;
+      if (lane == 0) flags[seg] = any_bad ? 1 : 0;
+    }
+  }
+}
+
 }  // namespace msad
 }  // namespace vu

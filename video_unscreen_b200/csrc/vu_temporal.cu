@@ -56,7 +56,7 @@ __device__ __forceinline__ unsigned load_px(const uint8_t* p) {
 
 template <class P, int U>
 __global__ void __launch_bounds__(MTHREADS, 1) median_kernel(const uint8_t* __restrict__ frames, uint8_t* __restrict__ out, int n, long long m,
-                                                             int nseg) {
+                                                             int nseg, const uint8_t* __restrict__ flags) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int PX = P::PX;
   constexpr int SEG = 32 * PX;
@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(MTHREADS, 1) median_kernel(const uint8_t* __re
   const unsigned klo = (unsigned)(n - 1) >> 1, khi = (unsigned)n >> 1;
   const int nb = n / U;
   for (int seg = blockIdx.x * WARPS + warp; seg < nseg; seg += gridDim.x * WARPS) {
+    if (flags && !flags[seg]) continue;   // fix-up mode: only the segments the refine pass could not decide
 #pragma unroll 8
     for (int b = 0; b < 256; ++b) *reinterpret_cast<unsigned*>(base + b * BIN_STRIDE) = 0u;
     __syncwarp();
@@ -169,8 +170,10 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// pitch = bytes between consecutive frames of the (possibly subsampled) clip
 template <int SPLIT, int G, int GQ, int SS, int TMA_WARPS, int TMA_CTAS>
-int launch_median_sad_tma(const uint8_t* frames, int n, int64_t m, int64_t ntiles, uint8_t* out, vu_stream_t stream) {
+int launch_median_sad_tma(const uint8_t* frames, int n, int64_t m, int64_t ntiles, uint8_t* out, vu_stream_t stream, int64_t pitch = 0) {
+  if (pitch == 0) pitch = m;
   constexpr int TILE = TMA_WARPS * (128 / SPLIT);
   constexpr int SMEM = SPLIT * 4 * G * TILE + 16;
   constexpr bool U32 = TILE > 256;   // boxes are at most 256 elements wide: wide tiles are described in 32-bit words
@@ -179,7 +182,7 @@ int launch_median_sad_tma(const uint8_t* frames, int n, int64_t m, int64_t ntile
   if (!enc) return VU_ERR_UNSUPPORTED;
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)(U32 ? m / 4 : m), (cuuint64_t)n};
-  const cuuint64_t strides[1] = {(cuuint64_t)m};
+  const cuuint64_t strides[1] = {(cuuint64_t)pitch};
   const cuuint32_t box[2] = {(cuuint32_t)(U32 ? TILE / 4 : TILE), (cuuint32_t)(4 * G)};
   const cuuint32_t estr[2] = {1, 1};
   if (enc(&tmap, U32 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<uint8_t*>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(TT) masked_mean_kernel(const uint8_t* __restri
 }
 
 template <class P, int U>
-int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream) {
+int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream, const uint8_t* flags = nullptr) {
   static bool configured = false;
   if (!configured) {
     int e = record_cuda(cudaFuncSetAttribute(median_kernel<P, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, HIST_BYTES));
@@ -286,9 +289,52 @@ int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t
   int grid = device_sms();
   const int64_t need = (nseg + WARPS - 1) / WARPS;
   if (need < grid) grid = (int)need;
-  median_kernel<P, U><<<grid, MTHREADS, HIST_BYTES, S(stream)>>>(frames, out, n, m, (int)nseg);
+  median_kernel<P, U><<<grid, MTHREADS, HIST_BYTES, S(stream)>>>(frames, out, n, m, (int)nseg, flags);
   note_launch();
   return record_cuda(cudaGetLastError());
+}
+
+// n > 608 with a workspace: subsample estimate (tile kernel) + streaming refine + histogram fix-up of the undecided
+// segments.  flags = one byte per 64-byte segment.  Returns VU_ERR_UNSUPPORTED when the TMA path is not available.
+int launch_median_two_pass(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, uint8_t* flags, vu_stream_t stream) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return VU_ERR_UNSUPPORTED;
+  const int64_t ntiles = nseg / msad::RF_WARPS;
+  if (ntiles == 0 || ntiles > 0x7fffffff) return VU_ERR_UNSUPPORTED;
+  const int step = (n + 303) / 304;              // every step-th frame: at most 304 of them
+  const int nsub = (n + step - 1) / step;
+  int e;
+  if (nsub <= 152) e = launch_median_sad_tma<2, 19, 11, 2, 8, 2>(frames, nsub, m, ntiles, out, stream, (int64_t)step * m);
+  else if (nsub <= 232) e = launch_median_sad_tma<2, 29, 20, 5, 8, 1>(frames, nsub, m, ntiles, out, stream, (int64_t)step * m);
+  else e = launch_median_sad_tma<2, 38, 30, 8, 8, 1>(frames, nsub, m, ntiles, out, stream, (int64_t)step * m);
+  if (e) return e;
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)(m / 4), (cuuint64_t)n};
+  const cuuint64_t strides[1] = {(cuuint64_t)m};
+  const cuuint32_t box[2] = {(cuuint32_t)(msad::RF_TILE / 4), (cuuint32_t)msad::RF_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<uint8_t*>(frames), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return VU_ERR_UNSUPPORTED;
+  static bool configured = false;
+  if (!configured) {
+    e = record_cuda(cudaFuncSetAttribute(msad::median_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, msad::RF_SMEM));
+    if (e) return e;
+    configured = true;
+  }
+  const int nchunks = (n + msad::RF_ROWS - 1) / msad::RF_ROWS;
+  const int grid = (int)(ntiles < device_sms() ? ntiles : device_sms());
+  msad::median_refine_kernel<<<grid, msad::RF_WARPS * 32, msad::RF_SMEM, S(stream)>>>(tmap, out, flags, n, (int)ntiles, nchunks);
+  note_launch();
+  e = record_cuda(cudaGetLastError());
+  if (e) return e;
+  // segments that do not fill a tile are flagged wholesale; the histogram kernel then redoes every flagged segment
+  const int64_t done = ntiles * msad::RF_WARPS;
+  if (done < nseg) {
+    e = record_cuda(cudaMemsetAsync(flags + done, 1, (size_t)(nseg - done), S(stream)));
+    if (e) return e;
+  }
+  return launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream, flags);
 }
 
 }  // namespace
@@ -302,7 +348,14 @@ static const bool g_median_direct = [] {
   return e && atoi(e) != 0;
 }();
 
+extern "C" size_t vu_temporal_median_workspace_bytes(int n, int64_t m) { return (n > 608 && m > 0) ? (size_t)(m / 64 + 64) : 0; }
+
 extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, uint8_t* out, vu_stream_t stream) {
+  return vu_temporal_median_u8_ws(frames, n, m, out, nullptr, 0, stream);
+}
+
+extern "C" int vu_temporal_median_u8_ws(const uint8_t* frames, int n, int64_t m, uint8_t* out, void* workspace, size_t workspace_bytes,
+                                        vu_stream_t stream) {
   VU_REQUIRE(frames && out && m >= 0);
   if (n < 1 || n > 65535) return VU_ERR_UNSUPPORTED;
   if (m == 0) return VU_OK;
@@ -353,7 +406,12 @@ extern "C" int vu_temporal_median_u8(const uint8_t* frames, int n, int64_t m, ui
     } else if (path == 1) {
       e = n <= 464 ? launch_median_sad<4, 29, 20, 5, 2>(frames, n, m, nseg, out, stream) : launch_median_sad<4, 38, 30, 8, 2>(frames, n, m, nseg, out, stream);
     } else {
-      e = launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
+      // with a workspace, 16-byte aligned frame rows and a frame size the 32-bit tensor map can describe:
+      // estimate + streaming refine + histogram fix-up; otherwise histograms for everything
+      e = VU_ERR_UNSUPPORTED;
+      if (workspace && workspace_bytes >= vu_temporal_median_workspace_bytes(n, m) && al16 && m < (1ll << 32) && !g_median_direct)
+        e = launch_median_two_pass(frames, n, m, nseg, out, static_cast<uint8_t*>(workspace), stream);
+      if (e == VU_ERR_UNSUPPORTED) e = launch_median<PolU16x2, 32>(frames, n, m, nseg, out, stream);
     }
     if (e) return e;
   }

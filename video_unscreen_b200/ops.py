@@ -425,7 +425,12 @@ def temporal_median(frames, out=None):
     m = frames.numel() // n
     if out is None:
         out = torch.empty(frames.shape[1:], dtype=u8, device=frames.device)
-    check(lib().vu_temporal_median_u8(_p(frames), n, m, _p(out), _stream()))
+    ws_bytes = int(lib().vu_temporal_median_workspace_bytes(n, m))
+    if ws_bytes:
+        ws = torch.empty(ws_bytes, dtype=u8, device=frames.device)
+        check(lib().vu_temporal_median_u8_ws(_p(frames), n, m, _p(out), _p(ws), ws_bytes, _stream()))
+    else:
+        check(lib().vu_temporal_median_u8(_p(frames), n, m, _p(out), _stream()))
     return out
 
 
