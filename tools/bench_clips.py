@@ -149,6 +149,29 @@ def main():
                n * 7 * h * w + 3 * h * w, 1 / dt, "oracle replace_blend on 1 frame (numpy float64, 1 thread); output bit-exact", peak)
         del fg, al, bg, out
 
+    if want("masked_mean_1080p"):
+        n, h, w = 300, 1080, 1920
+        fr = bench.make_clip_device(n, h, w, 2, torch.device("cuda"))
+        yy = torch.arange(h, device="cuda", dtype=torch.float32)[:, None]
+        xx = torch.arange(w, device="cuda", dtype=torch.float32)[None, :]
+        masks = torch.stack([((((xx - w * (0.15 + 0.7 * t / (n - 1))) / (w * 0.12)) ** 2 + ((yy - h / 2.0) / (h * 0.45)) ** 2) <= 1.0).to(torch.uint8) * 255
+                             for t in range(n)])
+        res = [None]
+
+        def step():
+            md = ops.dilate(masks, 3, 2)                       # bg_offline.py:116
+            res[0] = ops.masked_temporal_mean(fr, md, 10)      # :117-125
+        ms, launches = timed(step, args.steps)
+        rows = 64
+        t0 = time.perf_counter()
+        bg_o, always_o = R.masked_temporal_mean(fr[:, :rows].cpu().numpy(), masks[:, :rows].cpu().numpy())
+        dt = (time.perf_counter() - t0) * (h / rows)
+        # rows near the cut see a different dilation: compare away from it
+        assert np.array_equal(res[0][0][:rows - 4].cpu().numpy(), bg_o[:rows - 4]) and np.array_equal(res[0][1][:rows - 4].cpu().numpy(), always_o[:rows - 4])
+        report("masked_mean_1080p", "overall background of bg_offline.py:106-125 (dilate(3,2) of the masks + masked temporal mean), 300 x 1080p", n, ms,
+               launches, n * 4 * h * w + 4 * h * w, n / dt, "oracle masked_temporal_mean on a 64-row strip (numpy, 1 thread), scaled; output bit-exact", peak)
+        del fr, masks
+
     if want("bgstep_4k"):
         n, h, w = 120, 2160, 3840
         fr = bench.make_clip_device(n, h, w, 1, torch.device("cuda"))

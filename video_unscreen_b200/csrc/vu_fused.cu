@@ -510,12 +510,26 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
   const bool use_alt = alt_flags && alt_flags[n] != 0;
   const bool ens = (MODE == 1) && fuzzy && flags && flags[n] == 0;
   const bool vec = (dw & 3) == 0 && x + 3 < dw && ((reinterpret_cast<uintptr_t>(dst) & 3) == 0);
-  auto hrow = [&](int sy, int (&R)[4]) {   // horizontal pass of source row sy, >> 4 as the vertical pass wants it
+  // horizontal pass of source row sy, >> 4 as the vertical pass wants it.  Returns the common value of the eight taps, or
+  // -1: where all the taps of both source rows agree the interpolation is that value exactly (the two weighted
+  // halves lose less than 2 of 4v + 2 together), which is most of a matte or a trimap
+  auto hrow = [&](int sy, int (&R)[4]) -> int {
     const uint8_t* r = s + (int64_t)sy * sw;
+    int first = 0;
+    bool same = true;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) R[k] = ((int)__ldg(r + xa[k].i0) * xa[k].w0 + (int)__ldg(r + xa[k].i1) * xa[k].w1) >> 4;
+    for (int k = 0; k < 4; ++k) {
+      const int a = (int)__ldg(r + xa[k].i0), b = (int)__ldg(r + xa[k].i1);
+      if (k == 0) first = a;
+      same = same && a == first && b == first;
+      R[k] = (a * xa[k].w0 + b * xa[k].w1) >> 4;
+    }
+    return same ? first : -1;
   };
+  // (the shortcut needs weights that sum to 2048 on both axes: true for every scale the pipelines use, checked anyway)
+  const bool xsum_ok = xa[0].w0 + xa[0].w1 == 2048 && xa[1].w0 + xa[1].w1 == 2048 && xa[2].w0 + xa[2].w1 == 2048 && xa[3].w0 + xa[3].w1 == 2048;
   int R0[4], R1[4];
+  int u0 = -1, u1 = -1;     // common tap value of the rows in R0 / R1 (or -1)
   int y0c = -1, y1c = -1;   // source rows held in R0 / R1
 #pragma unroll 1
   for (int rr = 0; rr < RU_RUN; ++rr) {
@@ -535,8 +549,9 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
         if (ya.i0 == y1c) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) R0[k] = R1[k];
+          u0 = u1;
         } else {
-          hrow(ya.i0, R0);
+          u0 = hrow(ya.i0, R0);
         }
         y0c = ya.i0;
       }
@@ -544,11 +559,13 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
         if (ya.i1 == y0c) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) R1[k] = R0[k];
+          u1 = u0;
         } else {
-          hrow(ya.i1, R1);
+          u1 = hrow(ya.i1, R1);
         }
         y1c = ya.i1;
       }
+      const bool flat = u0 >= 0 && u0 == u1 && xsum_ok && ya.w0 + ya.w1 == 2048;
       unsigned fz = 0;
       if (ens) {
         if (vec) fz = __ldg(reinterpret_cast<const unsigned*>(fuzzy + ((int64_t)n * dh + y) * dw + x));
@@ -558,15 +575,26 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
             if (x + k < dw) fz |= (unsigned)__ldg(fuzzy + ((int64_t)n * dh + y) * dw + x + k) << (8 * k);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        int v = (((ya.w0 * R0[k]) >> 16) + ((ya.w1 * R1[k]) >> 16) + 2) >> 2;
-        v = min(255, max(0, v));
-        if (MODE == 1) {
-          if (v > 0 && v < 255) v = 128;
-          if ((fz >> (8 * k)) & 255u) v = 128;
+      if (flat) {
+        int v = u0;
+        if (MODE == 1 && v > 0 && v < 255) v = 128;
+        word = (unsigned)v * 0x01010101u;
+        if (MODE == 1 && fz) {
+          const unsigned nz = ((fz & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | fz;       // bit 7 of every non-zero fuzzy byte
+          const unsigned sel = ((nz >> 7) & 0x01010101u) * 255u;
+          word = (word & ~sel) | (0x80808080u & sel);
         }
-        word |= (unsigned)v << (8 * k);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          int v = (((ya.w0 * R0[k]) >> 16) + ((ya.w1 * R1[k]) >> 16) + 2) >> 2;
+          v = min(255, max(0, v));
+          if (MODE == 1) {
+            if (v > 0 && v < 255) v = 128;
+            if ((fz >> (8 * k)) & 255u) v = 128;
+          }
+          word |= (unsigned)v << (8 * k);
+        }
       }
     }
     uint8_t* o = d + (int64_t)y * dw + x;
