@@ -308,27 +308,29 @@ __global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restric
     unsigned* ow = reinterpret_cast<unsigned*>(o);
 #pragma unroll
     for (int w = 0; w < 12; ++w) {
-      unsigned r4 = 0;
+      unsigned vb[4];
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         const int i = 4 * w + b;                       // byte of the 48
         const int ai = AC == 3 ? i : i / 3;            // its alpha byte
-        const unsigned a = (aw[ai >> 2] >> (8 * (ai & 3))) & 255u;
+        // one PRMT per byte extraction (selector 4 = a zero byte), one per pair of results: the kernel is bound by
+        // instruction issue as much as by the float64 pipe
+        const unsigned a = __byte_perm(aw[ai >> 2], 0u, 0x4440 | (ai & 3));
         const double m = mtab[a];
-        const double c = u8_to_f64((fw[w] >> (8 * b)) & 255u);
+        const double c = u8_to_f64(__byte_perm(fw[w], 0u, 0x4440 | b));
         double r;
         if (MODE == VU_BLEND_NAIVE) {
           r = __dmul_rn(c, m);
         } else {
-          const double qq = u8_to_f64((qw[w] >> (8 * b)) & 255u);
+          const double qq = u8_to_f64(__byte_perm(qw[w], 0u, 0x4440 | b));
           if (MODE == VU_BLEND_COMPOSITE) r = __dadd_rn(c, __dmul_rn(qq, otab[a]));
           else r = __dadd_rn(__dmul_rn(c, m), __dmul_rn(qq, otab[a]));   // FUSE == REPLACE (products commute)
         }
         int v = f64_trunc_nonneg(r);
         if (MODE == VU_BLEND_COMPOSITE) v = min(v, 255);
-        r4 |= (unsigned)v << (8 * b);
+        vb[b] = (unsigned)v;
       }
-      ow[w] = r4;
+      ow[w] = __byte_perm(__byte_perm(vb[0], vb[1], 0x0040), __byte_perm(vb[2], vb[3], 0x0040), 0x5410);
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, o[k]);
