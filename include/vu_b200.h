@@ -167,6 +167,17 @@ int vu_set128_unflagged(const uint8_t* a, const uint8_t* b, const uint8_t* flags
  * float32 tables (luts = [bg H,S,V, fg H,S,V][256], DEVICE): per pixel
  * bg = (lutH[h]*lutS[s])*lutV[v], same for fg, p = fg^(1/3f) / (bg^(1/3f) +
  * fg^(1/3f) + 1e-6), alpha = u8(clip(p*255)). */
+/* The training samples of the mixtures gathered on the device, order-exact (colorfiltering/agent.py:139-141,
+ * 165-167, 192-194): samples = channel[selection] in row-major order, every (len // max_samples)-th of them when
+ * there are more than max_samples, for the three channels of hsv [h,w,3] under ONE selection
+ *   selection = (mask_op == 0 ? mask < 128 : mask > 128) && prior
+ *   prior_mode 0: none   1: prior_lo < H < prior_hi   2: !(prior_lo < H < prior_hi)       (get_color_prior's interval)
+ * samples: [3][cap] bytes (cap >= 2 * max_samples); meta3 = {selected pixels, stride, samples per channel};
+ * hist256 = histogram of the H samples kept (agent.py:142-143).  workspace: vu_cf_samples_workspace_bytes(h). */
+size_t vu_cf_samples_workspace_bytes(int h);
+int vu_cf_samples(const uint8_t* hsv, const uint8_t* mask, int h, int w, int mask_op, int prior_mode, int prior_lo,
+                  int prior_hi, int max_samples, uint8_t* samples, int cap, int32_t* meta3, uint32_t* hist256,
+                  void* workspace, size_t workspace_bytes, vu_stream_t stream);
 int vu_cf_alpha_u8(const uint8_t* hsv, int64_t npix, const float* luts, uint8_t* alpha, vu_stream_t stream);
 /* the same function tabulated over every (h<180, s, v): lut3d[180][256][256] */
 int vu_cf_build_lut3d(const float* luts, uint8_t* lut3d, vu_stream_t stream);

@@ -383,3 +383,31 @@ def test_temporal_median_properties_full_size(vu):
     del frames
     const = torch.full((n, 8, 64, 3), 77, dtype=torch.uint8, device="cuda")
     assert bool((vu.ops.temporal_median(const) == 77).all())
+
+
+@pytest.mark.parametrize("mask_op,prior,invert", [(0, None, False), (1, None, False), (0, (40, 70), False), (1, (40, 70), True), (1, (0, 1), False)])
+def test_cf_samples_order_exact(vu, mask_op, prior, invert):
+    """vu_cf_samples == channel[selection][::len // max] of colorfiltering/agent.py:139-141 for the three channels, plus
+    the histogram of the hue samples (:142): same pixels, same order, same stride."""
+    rng = np.random.default_rng(11)
+    h, w, mx = 135, 240, 1000
+    hsv = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    hsv[..., 0] = rng.integers(30, 90, (h, w))
+    mask = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    mask[:, :7] = 128                                    # neither < 128 nor > 128
+    sel = (mask < 128) if mask_op == 0 else (mask > 128)
+    if prior is not None:
+        inside = (hsv[..., 0] > prior[0]) & (hsv[..., 0] < prior[1])
+        sel = sel & (~inside if invert else inside)
+    want = []
+    for c in range(3):
+        smp = hsv[..., c][sel]
+        if len(smp) > mx:
+            smp = smp[::len(smp) // mx]
+        want.append(smp)
+    got, total, hist = vu.ops.cf_samples(torch.from_numpy(hsv).cuda(), torch.from_numpy(mask).cuda(), mask_op, mx, prior=prior, invert=invert)
+    assert total == int(sel.sum())
+    assert got.shape == (3, len(want[0]))
+    for c in range(3):
+        assert np.array_equal(got[c], want[c])
+    assert np.array_equal(hist, np.histogram(want[0].astype(float), 256, [0, 256])[0])

@@ -445,6 +445,27 @@ def masked_temporal_mean(frames, masks_dilated, min_count=10):
 
 # ---- per-frame branches on the device (batched clips) --------------------------------
 
+def cf_samples(hsv_lo, mask_lo, mask_op, max_samples, prior=None, invert=False):
+    """training samples of the mixtures gathered on the device (colorfiltering/agent.py:139-141): every
+    (len // max_samples)-th selected pixel in row-major order.  selection = (mask < 128 if mask_op == 0 else mask > 128)
+    and, with ``prior`` = (lo, hi), lo < H < hi (or its negation with ``invert``).  Returns (samples [3, n] uint8 numpy,
+    number of selected pixels, histogram [256] of the H samples)."""
+    hsv_lo, mask_lo = _img(hsv_lo), _mask(mask_lo)
+    h, w = mask_lo.shape[-2:]
+    cap = 2 * int(max_samples)
+    samples = torch.empty((3, cap), dtype=u8, device=hsv_lo.device)
+    meta = torch.empty(3, dtype=torch.int32, device=hsv_lo.device)
+    hist = torch.empty(256, dtype=torch.int32, device=hsv_lo.device)
+    ws_bytes = int(lib().vu_cf_samples_workspace_bytes(h))
+    ws = torch.empty(ws_bytes, dtype=u8, device=hsv_lo.device)
+    mode = 0 if prior is None else (2 if invert else 1)
+    lo, hi = (0, 0) if prior is None else (int(prior[0]), int(prior[1]))
+    check(lib().vu_cf_samples(_p(hsv_lo), _p(mask_lo), h, w, int(mask_op), mode, lo, hi, int(max_samples), _p(samples), cap, _p(meta), _p(hist),
+                              _p(ws), ws_bytes, _stream()))
+    total, _, kept = (int(v) for v in meta.cpu())
+    return samples[:, :kept].cpu().numpy(), total, hist.cpu().numpy()
+
+
 def ratio_flags(counts2, thr):
     counts2 = _dev(counts2, torch.int64)
     n = counts2.shape[0]

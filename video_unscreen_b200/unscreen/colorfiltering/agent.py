@@ -4,8 +4,8 @@ Per-pixel evaluation (BGR2HSV, down-scale, mixture evaluation, adaptive
 threshold, d2/e2/e2/d2 morphology, up-scale) runs on the GPU.  The EM fit of
 the six 1-D mixtures stays scikit-learn on the host, exactly as in the
 reference (a tiny, order-sensitive, RNG-seeded statistical fit on <= 20k
-samples): the GPU hands it the low-resolution HSV image, the host gathers the
-row-major strided samples the reference gathers.
+samples): the GPU gathers the row-major strided samples the reference gathers
+(vu_cf_samples) and hands scikit-learn those and the hue histogram.
 """
 import cv2
 import numpy as np
@@ -170,6 +170,35 @@ class ColorFilteringAgent():
             mask = (mask & (1 - mask_by_prior).astype(bool))
         self._fit(self.fg_gmms, img_hsv, mask)
 
+    def _fit_dev(self, hsv_lo, mask_lo):
+        """one fit iteration of forward (agent.py:325-332) with the samples gathered on the device (vu_cf_samples:
+        same pixels, same order, same stride as channel[mask][::step]); only the <= 20k samples per channel, the
+        selection count and the 256-bin hue histogram come back for scikit-learn."""
+        w_bg, w_fg = self.color_prior_winsize, self.color_prior_winsize // 5
+        # get_color_prior(hsv, mask < 128, w) for both windows: same samples, same histogram, same peak
+        _, _, hist = ops.cf_samples(hsv_lo, mask_lo, 0, self.max_num_samples)
+        peak = int(np.argmax(hist))
+        bg_prior = (peak - w_bg // 2, peak + w_bg // 2)
+        fg_prior = (peak - w_fg // 2, peak + w_fg // 2)
+        # fit_bg_gmms(hsv, mask < 128, bg_prior)
+        samples, _, _ = ops.cf_samples(hsv_lo, mask_lo, 0, self.max_num_samples, prior=bg_prior)
+        self._fit_samples(self.bg_gmms, samples)
+        # fit_fg_gmms(hsv, mask > 128, fg_prior): outside the prior if that leaves enough pixels
+        samples, total, _ = ops.cf_samples(hsv_lo, mask_lo, 1, self.max_num_samples, prior=fg_prior, invert=True)
+        if not total > max(self.fg_ncomp) * 5:
+            samples, _, _ = ops.cf_samples(hsv_lo, mask_lo, 1, self.max_num_samples)
+        self._fit_samples(self.fg_gmms, samples)
+
+    def _fit_samples(self, gmms, samples):
+        for i in range(3):
+            x = samples[i].astype(float)[..., np.newaxis]
+            if self.use_opencv_gmm:
+                gmms[i].trainEM(x)
+            else:
+                gmms[i].fit(x)
+        self._is_trained = True
+        self._luts_dev = None
+
     # ---- per-pixel evaluation (device) ---------------------------------------
     def _alpha_dev(self, hsv_dev):
         if self._luts_dev is None:
@@ -217,13 +246,8 @@ class ColorFilteringAgent():
         if iters == 0:
             alpha = self._postprocess_dev(self._alpha_dev(hsv_lo), mask_lo)
         else:
-            hsv_host = hsv_lo.cpu().numpy()
             for _ in range(iters):
-                mask_host = mask_lo.cpu().numpy()
-                bg_prior = self.get_color_prior(hsv_host, mask_host < 128, self.color_prior_winsize)
-                fg_prior = self.get_color_prior(hsv_host, mask_host < 128, self.color_prior_winsize // 5)
-                self.fit_bg_gmms(hsv_host, mask_host < 128, bg_prior)
-                self.fit_fg_gmms(hsv_host, mask_host > 128, fg_prior)
+                self._fit_dev(hsv_lo, mask_lo)
                 alpha = self._postprocess_dev(self._alpha_dev(hsv_lo), mask_lo)
                 mask_lo = ops.binarise(alpha, 128)
                 no_fg, no_bg = self._degenerate(mask_lo)
