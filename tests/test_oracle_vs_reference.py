@@ -1,0 +1,93 @@
+"""Oracle == the live, unmodified reference, on fresh seeded inputs (other than the committed golden fixtures).
+
+Runs only where the reference checkout exists (the build container: /root/reference); skipped on the GPU box.
+The reference is imported under the non-invasive shim of tests/golden/make_golden.py (stub mmcv / matplotlib,
+restore np.float / np.int).  This is what pins the oracle beyond the fixtures: different sizes, seeds and parameters
+every time the file is edited, no stored outputs."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+REF_ROOT = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF_ROOT, "unscreen")), reason="reference checkout not present")
+
+from oracle import refport as R  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import load_reference
+    U, CF, TA, BA = load_reference(REF_ROOT)
+
+    class Ref:
+        pass
+    r = Ref()
+    r.U, r.CF, r.TA = U, CF, TA
+    return r
+
+
+def test_morphology_and_counts(ref):
+    rng = np.random.default_rng(77)
+    m = rng.integers(0, 256, (61, 83), dtype=np.uint8)
+    for k, n in [(3, 1), (3, 4), (4, 1), (4, 3), (5, 2), (7, 3)]:
+        assert np.array_equal(R.dilate_mask(m, k, n), ref.U.dilate_mask(m, k, n)), (k, n)
+        assert np.array_equal(R.erode_mask(m, k, n), ref.U.erode_mask(m, k, n)), (k, n)
+    assert np.array_equal(R.get_outer_boundary(m), ref.U.get_outer_boundary(m))
+    for t in (0.0, 0.3, 0.5, 0.9):
+        assert R.exist_foreground(m, t) == ref.U.exist_foreground(m, t)
+
+
+def test_inrange_and_sizes(ref):
+    rng = np.random.default_rng(78)
+    img = rng.integers(0, 256, (70, 94, 3), dtype=np.uint8)
+    bgi = np.clip(img.astype(np.int16) + rng.integers(-25, 26, img.shape), 0, 255).astype(np.uint8)
+    for col, win in [((30, 180, 60), (10, 100, 180)), ((250, 3, 7), (40, 40, 40)), ((0, 0, 0), (255, 255, 255))]:
+        c = np.array(col, np.uint8)
+        assert np.array_equal(R.is_pixel_inrange(img, c, win), ref.U.is_pixel_inrange(img, c, win))
+    assert np.array_equal(R.is_pixel_inrange(img, bgi, (20, 30, 90)), ref.U.is_pixel_inrange(img, bgi, (20, 30, 90)))
+    for h, w, L in [(1080, 1920, 960), (2160, 3840, 960), (607, 411, 300), (100, 100, 37)]:
+        assert tuple(R.get_target_size(h, w, L)) == tuple(ref.U.get_target_size(h, w, L))
+
+
+@pytest.mark.parametrize("h,w,L", [(96, 160, 80), (150, 110, 60), (128, 256, 64)])
+def test_trimap(ref, h, w, L):
+    rng = np.random.default_rng(h + w)
+    yy, xx = np.mgrid[0:h, 0:w]
+    mask = ((((xx - w / 2) / (w * 0.3)) ** 2 + ((yy - h / 2) / (h * 0.35)) ** 2) <= 1).astype(np.uint8) * 255
+    mask[rng.random((h, w)) < 0.01] = 200
+    agent = ref.TA(input_long_side=L)
+    assert np.array_equal(R.generate_trimap(mask, L), agent.forward(mask.copy()))
+    img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    img[mask == 0] = (60, 200, 40)
+    for bg in (np.array([60, 200, 40], np.uint8), np.array([10, 10, 200], np.uint8)):
+        assert np.array_equal(R.generate_trimap_withbg(mask, img, bg, L), agent.forward(mask.copy(), img.copy(), bg.copy()))
+
+
+def test_compositing(ref):
+    rng = np.random.default_rng(79)
+    h, w = 64, 96
+    fr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    bg = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    al = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    assert np.abs(R.get_fg(fr, al, bg).astype(int) - ref.U.get_fg(fr.copy(), al.copy(), bg.copy()).astype(int)).max() <= 1     # cv2's HSV2BGR
+    assert np.abs(R.get_bg(al, bg).astype(int) - ref.U.get_bg(al.copy(), bg.copy()).astype(int)).max() <= 1
+    assert np.array_equal(R.get_fg_naive(fr, al), ref.U.get_fg_naive(fr.copy(), al.copy()))
+    assert np.array_equal(R.fuse_fgbg(fr, bg, al), ref.U.fuse_fgbg(fr.copy(), bg.copy(), al.copy()))
+    assert np.array_equal(R.composite_fgbg(fr, al, bg), ref.U.composite_fgbg(fr.copy(), al.copy(), bg.copy()))
+
+
+def test_colorfilter_predict(ref):
+    from video_unscreen_b200 import synth
+    frame, seg = synth.green_frame(180, 320, t=2, n=10, seed=9)
+    agent = ref.CF(input_long_side=160)
+    np.random.seed(3)
+    agent.forward(frame.copy(), seg.copy(), 2)                       # fit on the reference side
+    alpha_ref, bg_ref, _ = agent.forward(frame.copy(), seg.copy(), 0)
+    lb, lf = R.gmm_luts_from_models(agent.bg_gmms), R.gmm_luts_from_models(agent.fg_gmms)
+    bgh = R.bg_color_hsv([g.means_[0, 0] for g in agent.bg_gmms])
+    alpha, bg, _ = R.cf_forward_predict(frame, seg, lb, lf, bgh, 160)
+    assert np.array_equal(alpha, alpha_ref)
+    assert np.abs(bg.astype(int) - bg_ref.astype(int)).max() <= 1

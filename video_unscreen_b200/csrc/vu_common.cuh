@@ -76,7 +76,10 @@ __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const HsvTab& t,
   const int mn = min(b, min(g, r));
   const int d = v - mn;
   s = (d * t.sdiv[v] + 2048) >> 12;
-  int hh = (v == r) ? (g - b) : ((v == g) ? (b - r + 2 * d) : (r - g + 4 * d));
+  // hue numerator by priority r, g, b of the maximum: x - y + k*d, selected without a (divergent) branch
+  const bool vr = v == r, vg = v == g;
+  const int x = vr ? g : (vg ? b : r), y = vr ? b : (vg ? r : g), k = vr ? 0 : (vg ? 2 : 4);
+  int hh = x - y + k * d;
   hh = (hh * t.hdiv[d] + 2048) >> 12;  // arithmetic shift on a signed value
   h = hh < 0 ? hh + 180 : hh;
 }
