@@ -122,3 +122,24 @@ def test_sharded_equals_whole(env, world):
     assert torch.equal(torch.cat(alphas, 0), whole_alpha)
     assert torch.equal(torch.cat(tris, 0), whole_tri)
     assert torch.equal(torch.cat(fgs, 0), whole_fg)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_row_tile_sharding_with_halo(env, world):
+    """BASELINE config 5's layout on one GPU, tiles run one after the other: every rank's row tile (+ 24-row halo) through
+    median, difference gate, trimap and get_fg equals the same rows of the whole-clip pipeline."""
+    n, h, w = 10, 384, 640                    # working resolution 96 x 160: scale 4, like 4K -> 540 x 960
+    frames, masks, _ = synth.bgstep_clip(n, h, w, seed=8)
+    f_d, m_d = dev(frames), dev(masks)
+    ta = env.TA(input_long_side=160)
+    bg, alpha, tri, fg = env.clip.bgstep_clip(f_d, m_d, ta, thr=25, chunk=4)
+    covered = 0
+    for rank in range(world):
+        (r0, r1), bg_t, a_t, t_t, f_t = env.clip.bgstep_clip_tile(f_d, m_d, ta, rank, world, thr=25, chunk=4, scale=4)
+        assert r0 % 4 == 0 and (r1 % 4 == 0 or r1 == h)
+        assert torch.equal(bg_t, bg[r0:r1])
+        assert torch.equal(a_t, alpha[:, r0:r1])
+        assert torch.equal(t_t, tri[:, r0:r1])
+        assert torch.equal(f_t, fg[:, r0:r1])
+        covered += r1 - r0
+    assert covered == h

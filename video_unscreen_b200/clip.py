@@ -160,3 +160,25 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=16):
         tri[s:e] = trimap_clip(a, trimap_agent, chunk=chunk)
         fg[s:e] = ops.get_fg(frames[s:e], a, bg, _lib.PATCH_ALPHA_EQ0)
     return bg, alpha, tri, fg
+
+
+BGSTEP_HALO = 24   # full-resolution rows: 6 working-resolution rows at 1/4 scale (r=5 diamond + one bilinear tap); covers dilate(4,2)
+
+
+def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=16, scale=4):
+    """bgstep_clip on this rank's ROW TILE of the clip (BASELINE config 5: spatial-tile sharding):
+    the temporal median of the tile's rows (every pixel is independent), then the per-frame stages on the tile plus a
+    halo of BGSTEP_HALO rows read from the local frames, cropped back.  ``frames`` / ``masks`` are the WHOLE frames here
+    (the caller may hold only rows [r0 - halo, r1 + halo) and pass those with the matching offsets instead).  Tile
+    boundaries are multiples of ``scale`` (frame size / working size), so the tile's down-scales sample the pixels the
+    whole frame's do: the results equal the corresponding rows of bgstep_clip on the whole clip, bit for bit.
+    Returns (r0, r1), background, alpha, trimap, fg for rows [r0, r1)."""
+    from . import shard
+    n, h, w, _ = frames.shape
+    r0, r1, ht, hb = shard.my_row_tile(h, rank, world, halo=BGSTEP_HALO, align=scale)
+    a0, a1 = r0 - ht, r1 + hb
+    ftile = frames[:, a0:a1].contiguous()
+    mtile = masks[:, a0:a1].contiguous()
+    bg_t, alpha_t, tri_t, fg_t = bgstep_clip(ftile, mtile, trimap_agent, thr=thr, chunk=chunk)
+    lo, hi = ht, ht + (r1 - r0)
+    return (r0, r1), bg_t[lo:hi], alpha_t[:, lo:hi], tri_t[:, lo:hi], fg_t[:, lo:hi]

@@ -24,17 +24,22 @@ def frame_ranges(n_frames, world, align=1):
     return out
 
 
-def row_tiles(height, world, halo=0):
+def row_tiles(height, world, halo=0, align=1):
     """[(row_start, row_stop, halo_top, halo_bottom)] per rank.  ``halo`` rows
     of neighbouring tiles are needed when a tile is later pushed through the
     stencil stages without gathering (dilate(4,2) reaches -4..+2 rows, the
-    r=5 trimap at 1/4 scale ~20 rows + bilinear taps: 24 covers both)."""
-    if world < 1 or height < 0 or halo < 0:
+    r=5 trimap at 1/4 scale ~20 rows + bilinear taps: 24 covers both).
+    Interior boundaries are multiples of ``align`` (the down-scale factor of
+    the working resolution, 4 at 4K, so that a tile's nearest / area
+    down-scale samples the same pixels as the whole frame's); halos are
+    clipped to the image."""
+    if world < 1 or height < 0 or halo < 0 or align < 1:
         raise ValueError("bad arguments")
+    units = -(-height // align)
     out, start = [], 0
     for r in range(world):
-        rows = height // world + (1 if r < height % world else 0)
-        stop = start + rows
+        u = units // world + (1 if r < units % world else 0)
+        stop = min(height, start + u * align)
         out.append((start, stop, min(halo, start), min(halo, height - stop)))
         start = stop
     return out
@@ -44,8 +49,8 @@ def my_frame_range(n_frames, rank, world, align=1):
     return frame_ranges(n_frames, world, align)[rank]
 
 
-def my_row_tile(height, rank, world, halo=0):
-    return row_tiles(height, world, halo)[rank]
+def my_row_tile(height, rank, world, halo=0, align=1):
+    return row_tiles(height, world, halo, align)[rank]
 
 
 def reduce_rows_sharded(frames, fn, rank, world, gather=False):
