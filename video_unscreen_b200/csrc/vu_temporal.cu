@@ -64,8 +64,26 @@ __global__ void __launch_bounds__(MTHREADS, 1) median_kernel(const uint8_t* __re
   unsigned char* base = smem + warp * 128 + lane * 4;
   const unsigned klo = (unsigned)(n - 1) >> 1, khi = (unsigned)n >> 1;
   const int nb = n / U;
-  for (int seg = blockIdx.x * WARPS + warp; seg < nseg; seg += gridDim.x * WARPS) {
-    if (flags && !flags[seg]) continue;   // fix-up mode: only the segments the refine pass could not decide
+  // fix-up mode (flags != nullptr): only the segments the refine pass could not decide.  A warp scans 32 flags per
+  // load and walks the set bits; without flags every segment of the warp's stride is processed.
+  const int wid = blockIdx.x * WARPS + warp, nw = gridDim.x * WARPS;
+  const int iters = flags ? (nseg + 32 * nw - 1) / (32 * nw) * 32 : (nseg + nw - 1) / nw;
+  unsigned pending = 0;
+  for (int it = 0; it < iters; ++it) {
+    int seg;
+    if (flags) {
+      if ((it & 31) == 0) {
+        const int s = ((it >> 5) * nw + wid) * 32 + lane;
+        pending = __ballot_sync(0xffffffffu, s < nseg && flags[s] != 0);
+      }
+      if (pending == 0) { it |= 31; continue; }
+      const int b = __ffs(pending) - 1;
+      pending &= pending - 1;
+      seg = ((it >> 5) * nw + wid) * 32 + b;
+    } else {
+      seg = it * nw + wid;
+      if (seg >= nseg) break;
+    }
 #pragma unroll 8
     for (int b = 0; b < 256; ++b) *reinterpret_cast<unsigned*>(base + b * BIN_STRIDE) = 0u;
     __syncwarp();
