@@ -142,6 +142,14 @@ int vu_trimap_src_lo(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* f
                      int tw, uint8_t* out, vu_stream_t stream);
 /* generate_trimap, trimap/agent.py:54-58: out = 0 where dilated < 128, else
  * 255 where eroded > 127, else 128 */
+/* The whole trimap tail (trimap/agent.py:52-60 and :97, :100) for frames that are an exact 2x or 4x of the working
+ * resolution th x tw, MORPH_ELLIPSE(3,3): nearest down-scale of mask [n,h,w] (fuzzy pixels cleared first in frames
+ * with flags[i] == 0), `iters` cross dilations / erosions, classification, bilinear up-scale, snap, fuzzy -> 128,
+ * all in bit logic (see vu_trimap_bits.cu).  fuzzy / flags may both be NULL.  workspace: vu_trimap_bits_workspace_bytes.
+ * VU_ERR_UNSUPPORTED for other scales, tw % 4 != 0, iters > 12 or pointers that are not 16-byte aligned. */
+size_t vu_trimap_bits_workspace_bytes(int n, int th, int tw);
+int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* flags, int n, int h, int w, int th, int tw,
+                   int iters, uint8_t* out, void* workspace, size_t workspace_bytes, vu_stream_t stream);
 int vu_trimap_classify(const uint8_t* dilated, const uint8_t* eroded, uint8_t* out, int64_t count,
                        vu_stream_t stream);
 /* trimap/agent.py:60: values strictly between 0 and 255 become 128 */

@@ -411,3 +411,41 @@ def test_cf_samples_order_exact(vu, mask_op, prior, invert):
     for c in range(3):
         assert np.array_equal(got[c], want[c])
     assert np.array_equal(hist, np.histogram(want[0].astype(float), 256, [0, 256])[0])
+
+
+@pytest.mark.parametrize("sc,th,tw,iters", [(2, 64, 96, 5), (4, 64, 96, 5), (2, 70, 100, 5), (4, 33, 52, 3), (2, 130, 196, 1), (4, 65, 200, 0),
+                                            (2, 9, 12, 8), (2, 67, 128, 12)])
+def test_trimap_bits_tail(vu, sc, th, tw, iters):
+    """vu_trimap_bits (nearest down -> binary cross dilation / erosion -> classification -> snapped bilinear up-scale as tap
+    logic) against the oracle's generate_trimap and the ensemble branch of generate_trimap_withbg, tile seams (96 x 64
+    working-resolution tiles), borders, grey-valued masks, fuzzy overrides, per-frame flags."""
+    h, w = sc * th, sc * tw
+    rng = np.random.default_rng(sc * 1000 + th + tw + iters)
+    n = 3
+    yy, xx = np.mgrid[0:h, 0:w]
+    masks = np.zeros((n, h, w), np.uint8)
+    for i in range(n):
+        blob = (((xx - w * (0.3 + 0.2 * i)) / (w * 0.22)) ** 2 + ((yy - h * 0.5) / (h * 0.38)) ** 2) <= 1
+        masks[i][blob] = rng.integers(100, 256, int(blob.sum()))         # grey values either side of 128
+        masks[i][rng.random((h, w)) < 0.002] = 255                        # isolated specks
+    masks[0, :, :3] = 255; masks[0, :2, :] = 255                          # touching the borders
+    masks[1, -1, :] = 255; masks[1, :, -1] = 200
+    long_side = max(th, tw)
+    want = np.stack([R.generate_trimap(masks[i], long_side, 3, iters) for i in range(n)])
+    got = vu.ops.trimap_bits(torch.from_numpy(masks).cuda(), th, tw, iters).cpu().numpy()
+    assert np.array_equal(got, want)
+    # ensemble branch (trimap/agent.py:96-100): fuzzy pixels cleared before, set to 128 after; flags pick the frames
+    fuzzy = ((rng.random((n, h, w)) < 0.05) & (masks > 0)).astype(np.uint8)
+    flags = np.array([0, 1, 0], np.uint8)
+    want2 = []
+    for i in range(n):
+        if flags[i] == 0:
+            m = masks[i].copy()
+            m[fuzzy[i] > 0] = 0
+            t = R.generate_trimap(m, long_side, 3, iters)
+            t[fuzzy[i] > 0] = 128
+        else:
+            t = R.generate_trimap(masks[i], long_side, 3, iters)
+        want2.append(t)
+    got2 = vu.ops.trimap_bits(torch.from_numpy(masks).cuda(), th, tw, iters, torch.from_numpy(fuzzy).cuda(), torch.from_numpy(flags).cuda()).cpu().numpy()
+    assert np.array_equal(got2, np.stack(want2))

@@ -70,6 +70,9 @@ def _trimap_tail(masks, agent, fuzzy=None, flags=None):
     """nearest down (+ ensemble clearing) -> dilate/erode/classify -> bilinear up + snap (+ fuzzy override)"""
     n, h, w = masks.shape
     ih, iw = get_target_size(h, w, agent.input_long_side)
+    if agent.kernelsize == 3 and ops.trimap_bits_supported(masks, ih, iw, agent.iters, fuzzy):
+        # exact 2x / 4x working resolution (1080p, 4K): the whole tail in bit logic, two launches
+        return ops.trimap_bits(masks, ih, iw, agent.iters, fuzzy, flags)
     m = ops.trimap_src_lo(masks, ih, iw, fuzzy, flags)
     if agent.kernelsize == 3 and agent.iters <= ops.CROSS_MAX_PASSES:
         tri = ops.trimap_core(m, agent.iters)

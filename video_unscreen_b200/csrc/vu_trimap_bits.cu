@@ -1,0 +1,247 @@
+// The trimap tail in bit logic, for frames that are an exact 2x or 4x of the working resolution
+// (1080p and 4K with input_long_side = 960) and MORPH_ELLIPSE(3,3) (unscreen/trimap/agent.py:35-61, 97-100):
+//
+//     m    = resize(mask, NEAREST)             m[fuzzy] = 0 first in the ensemble branch (:97)
+//     dil  = dilate_mask(m, 3, r);  ero = erode_mask(m, 3, r)
+//     t    = 128;  t[ero > 127] = 255;  t[dil < 128] = 0
+//     out  = resize(t, (W,H))  (bilinear, :59);  out[(out > 0) & (out < 255)] = 128;  out[fuzzy] = 128 (:100)
+//
+// Everything after the nearest down-scale depends on m only through B = (m >= 128): a max is < 128 iff all its taps
+// are, a min is > 127 iff all its taps are.  So t == 0 where the binary dilation of B is empty, t == 255 where the
+// binary erosion of B is full.  And for exact 2x / 4x scales the snapped bilinear up-scale of a {0,128,255} map is tap
+// logic too: cv2's fixed-point interpolation gives exactly 0 iff every tap with a non-zero weight is 0 and exactly
+// 255 iff every such tap is 255 (the smallest weight product, 1/64, still moves the result by 2; checked
+// exhaustively over all weight pairs and tap values, see tests), and the taps with non-zero weights are the 2x2
+// neighbourhood towards the pixel's quadrant, replicated at the borders.
+//
+// Kernel A: one CTA per 96 x 64 tile of the working resolution: B packed to bits straight from the full-resolution
+// mask (and fuzzy map), r cross dilations and r cross erosions on 32-pixel words in shared memory (cells outside the
+// image reset to the identity after every pass), then the four quadrant ANDs of Z = "t == 0" and F = "t == 255":
+// eight bit planes of th x ceil(tw/32) words per frame.  Kernel B: one pass over the output: four plane words per 4
+// pixels, the fuzzy override, one store.  The working-resolution trimap never exists as bytes.
+#include "vu_common.cuh"
+
+namespace vu {
+namespace {
+
+constexpr int TB_THREADS = 256;
+constexpr int TB_OW = 96, TB_OH = 64;     // output tile (working-resolution pixels)
+constexpr int TB_HX = 16;                 // staged halo columns on either side (>= passes + 1)
+constexpr int TB_MAXR = 12;               // most passes
+constexpr int TB_WORDS = (TB_OW + 2 * TB_HX) / 32;   // 4
+constexpr int TB_ROWS_MAX = TB_OH + 2 * (TB_MAXR + 1);
+
+// bytes 0, S, 2S, 3S of the 4S bytes at p
+template <int SC>
+__device__ __forceinline__ unsigned pick4(const uint8_t* p) {
+  if (SC == 2) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    return __byte_perm(v.x, v.y, 0x6420);
+  } else {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+    return (v.x & 255u) | ((v.y & 255u) << 8) | ((v.z & 255u) << 16) | (v.w << 24);
+  }
+}
+
+// plane p of frame n: planes[((p * nframes + n) * th + y) * wpr + j]
+template <int SC>
+__global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ fuzzy,
+                                                                 const uint8_t* __restrict__ flags, int h, int w, int th, int tw, int passes,
+                                                                 unsigned* __restrict__ planes, int nframes, int wpr) {
+  __shared__ unsigned Db[2][TB_ROWS_MAX][TB_WORDS], Eb[2][TB_ROWS_MAX][TB_WORDS], In[TB_ROWS_MAX][TB_WORDS];
+  __shared__ unsigned ZL[TB_ROWS_MAX][TB_WORDS], ZR[TB_ROWS_MAX][TB_WORDS], FL[TB_ROWS_MAX][TB_WORDS], FR[TB_ROWS_MAX][TB_WORDS];
+  const int n = blockIdx.z;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int halo = passes + 1;
+  const int rows = TB_OH + 2 * halo;
+  const int X0 = blockIdx.x * TB_OW - TB_HX, Y0 = blockIdx.y * TB_OH - halo;   // staged origin
+  const bool ens = fuzzy && flags && flags[n] == 0;
+  const uint8_t* mk = mask + (int64_t)n * h * w;
+  const uint8_t* fz = fuzzy ? fuzzy + (int64_t)n * h * w : nullptr;
+  // ---- B = (nearest-sampled mask >= 128, fuzzy pixels cleared), one bit per working-resolution pixel ----
+  for (int r = warp; r < rows; r += TB_THREADS / 32) {
+    const int y = Y0 + r, x = X0 + 4 * lane;
+    unsigned nib = 0, inb = 0;
+    if ((unsigned)y < (unsigned)th && x >= 0 && x < tw) {   // tw % 4 == 0: a group is inside or outside as a whole
+      const int64_t si = (int64_t)SC * y * w + (int64_t)SC * x;
+      unsigned v = pick4<SC>(mk + si);
+      if (ens) {
+        const unsigned f = pick4<SC>(fz + si);
+        const unsigned nz = ((f & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | f;   // bit 7 of every non-zero fuzzy byte
+        v &= ~(((nz >> 7) & 0x01010101u) * 255u);
+      }
+      nib = ((v >> 7) & 1u) | ((v >> 14) & 2u) | ((v >> 21) & 4u) | ((v >> 28) & 8u);   // byte >= 128
+      inb = 15u;
+    }
+    const unsigned grp = 0xFFu << (lane & 24);
+    const unsigned bw = __reduce_or_sync(grp, nib << (4 * (lane & 7)));
+    const unsigned iw = __reduce_or_sync(grp, inb << (4 * (lane & 7)));
+    if ((lane & 7) == 0) {
+      Db[0][r][lane >> 3] = bw;            // outside the image: 0, the identity of a dilation
+      Eb[0][r][lane >> 3] = bw | ~iw;      // outside the image: 1, the identity of an erosion
+      In[r][lane >> 3] = iw;
+    }
+  }
+  __syncthreads();
+  // ---- passes of the 3x3 cross on both chains ----
+  int cur = 0;
+  for (int p = 0; p < passes; ++p) {
+    for (int i = threadIdx.x; i < rows * TB_WORDS; i += TB_THREADS) {
+      const int r = i / TB_WORDS, j = i % TB_WORDS;
+      const unsigned in = In[r][j];
+      {
+        const unsigned c = Db[cur][r][j];
+        const unsigned lf = __funnelshift_l(j > 0 ? Db[cur][r][j - 1] : 0u, c, 1);                 // pixel x-1
+        const unsigned rt = __funnelshift_r(c, j < TB_WORDS - 1 ? Db[cur][r][j + 1] : 0u, 1);     // pixel x+1
+        const unsigned up = r > 0 ? Db[cur][r - 1][j] : 0u, dn = r + 1 < rows ? Db[cur][r + 1][j] : 0u;
+        Db[cur ^ 1][r][j] = (c | lf | rt | up | dn) & in;
+      }
+      {
+        const unsigned c = Eb[cur][r][j];
+        const unsigned lf = __funnelshift_l(j > 0 ? Eb[cur][r][j - 1] : 0xFFFFFFFFu, c, 1);
+        const unsigned rt = __funnelshift_r(c, j < TB_WORDS - 1 ? Eb[cur][r][j + 1] : 0xFFFFFFFFu, 1);
+        const unsigned up = r > 0 ? Eb[cur][r - 1][j] : 0xFFFFFFFFu, dn = r + 1 < rows ? Eb[cur][r + 1][j] : 0xFFFFFFFFu;
+        Eb[cur ^ 1][r][j] = (c & lf & rt & up & dn) | ~in;
+      }
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  // ---- Z = (t == 0) = no dilated bit, F = (t == 255) = eroded bit; their ANDs with the left / right neighbour,
+  //      replicated at the image border (the neighbour outside the image is the pixel itself) ----
+  for (int i = threadIdx.x; i < rows * TB_WORDS; i += TB_THREADS) {
+    const int r = i / TB_WORDS, j = i % TB_WORDS;
+    const unsigned in = In[r][j];
+    const unsigned inl = __funnelshift_l(j > 0 ? In[r][j - 1] : 0u, in, 1), inr = __funnelshift_r(in, j < TB_WORDS - 1 ? In[r][j + 1] : 0u, 1);
+    auto lr = [&](unsigned c, unsigned pw, unsigned nw, unsigned& L, unsigned& R) {
+      const unsigned lf = __funnelshift_l(pw, c, 1), rt = __funnelshift_r(c, nw, 1);
+      L = c & (lf | ~inl);   // no pixel to the left: the pixel itself
+      R = c & (rt | ~inr);
+    };
+    const unsigned z = ~Db[cur][r][j], zp = j > 0 ? ~Db[cur][r][j - 1] : 0u, zn = j < TB_WORDS - 1 ? ~Db[cur][r][j + 1] : 0u;
+    const unsigned f = Eb[cur][r][j], fp = j > 0 ? Eb[cur][r][j - 1] : 0u, fn = j < TB_WORDS - 1 ? Eb[cur][r][j + 1] : 0u;
+    unsigned L, R;
+    lr(z, zp, zn, L, R);
+    ZL[r][j] = L; ZR[r][j] = R;
+    lr(f, fp, fn, L, R);
+    FL[r][j] = L; FR[r][j] = R;
+  }
+  __syncthreads();
+  // ---- the eight quadrant planes of the tile's rows: {Z,F} x {left,right} x {row above, row below}, 3 words per row ----
+  for (int i = threadIdx.x; i < TB_OH * 3 * 8; i += TB_THREADS) {
+    const int pl = i / (TB_OH * 3), rem = i % (TB_OH * 3);
+    const int ty = rem / 3, jo = rem % 3;
+    const int y = blockIdx.y * TB_OH + ty;
+    const int xw = blockIdx.x * 3 + jo;      // word of the plane row
+    if (y >= th || xw >= wpr) continue;
+    const int r = ty + halo;
+    const int ro = (pl & 1) ? (y + 1 < th ? r + 1 : r) : (y > 0 ? r - 1 : r);   // the other row of the pair, replicated at the border
+    const unsigned(*src)[TB_WORDS] = (pl >> 1) == 0 ? ZL : ((pl >> 1) == 1 ? ZR : ((pl >> 1) == 2 ? FL : FR));
+    // output word jo = staged bits 16 + 32 jo .. 47 + 32 jo
+    const unsigned a = __funnelshift_r(src[r][jo], src[r][jo + 1], 16), b = __funnelshift_r(src[ro][jo], src[ro][jo + 1], 16);
+    planes[(((int64_t)pl * nframes + n) * th + y) * wpr + xw] = a & b;
+  }
+}
+
+// plane index: (Z left, Z right, F left, F right) x (pair with the row above, pair with the row below) -> 2 * k + below.
+// NG groups of 4 output pixels per thread (4: 128-bit fuzzy loads and stores - a streaming kernel needs the bytes in
+// flight; 1: widths that are not a multiple of 16).  The NG groups of a thread read the same four plane words.
+template <int SC, int NG>
+__global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsigned* __restrict__ planes, int nframes, int th, int tw, int wpr,
+                                                                    const uint8_t* __restrict__ fuzzy, const uint8_t* __restrict__ flags,
+                                                                    uint8_t* __restrict__ out) {
+  const int n = blockIdx.y;
+  const int h = SC * th, w = SC * tw;
+  const bool ens = fuzzy && flags && flags[n] == 0;
+  const int tpr = w / (4 * NG);   // threads per row
+  const int64_t total = (int64_t)h * tpr;
+  const int64_t psz = (int64_t)nframes * th * wpr;   // words per plane
+  constexpr int CPG = 4 / SC;                        // working-resolution columns per group: 1 (4x) or 2 (2x)
+  for (int64_t i = (int64_t)blockIdx.x * TB_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB_THREADS) {
+    const int y = (int)(i / tpr), t = (int)(i - (int64_t)y * tpr);
+    const int r = y / SC, below = (y % SC) >= SC / 2;
+    const unsigned* row = planes + ((int64_t)n * th + r) * wpr;
+    const int c0 = t * NG * CPG;                     // first working-resolution column of the thread: NG * CPG <= 8 bits, one word
+    const int j = c0 >> 5, b = c0 & 31;
+    const unsigned zl = __ldg(row + (0 + below) * psz + j) >> b, zr = __ldg(row + (2 + below) * psz + j) >> b;
+    const unsigned fl = __ldg(row + (4 + below) * psz + j) >> b, fr = __ldg(row + (6 + below) * psz + j) >> b;
+    const int64_t o = ((int64_t)n * h + y) * w + (int64_t)t * 4 * NG;
+    unsigned fz[NG];
+    if (ens) {
+      if (NG == 4) {
+        const uint4 v = ldg_stream16(fuzzy + o);
+        fz[0] = v.x; fz[1 % NG] = v.y; fz[2 % NG] = v.z; fz[3 % NG] = v.w;
+      } else {
+        fz[0] = __ldg(reinterpret_cast<const unsigned*>(fuzzy + o));
+      }
+    }
+    unsigned words[NG];
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      unsigned zb, fb;   // bit q = output pixel q of the group: Z / F of its quadrant
+      if (SC == 4) {     // the 4 pixels share column c0 + k: two on its left half, two on its right half
+        zb = ((zl >> k) & 1u) * 3u | ((zr >> k) & 1u) * 12u;
+        fb = ((fl >> k) & 1u) * 3u | ((fr >> k) & 1u) * 12u;
+      } else {           // pixels: (c, left) (c, right) (c+1, left) (c+1, right), c = c0 + 2k
+        const unsigned a = zl >> (2 * k), bb = zr >> (2 * k), c = fl >> (2 * k), d = fr >> (2 * k);
+        zb = (a & 1u) | ((bb & 1u) << 1) | ((a & 2u) << 1) | ((bb & 2u) << 2);
+        fb = (c & 1u) | ((d & 1u) << 1) | ((c & 2u) << 1) | ((d & 2u) << 2);
+      }
+      // bits -> bytes: 0 where Z, 255 where F, 128 elsewhere
+      const unsigned zm = ((zb & 1u) | ((zb & 2u) << 7) | ((zb & 4u) << 14) | ((zb & 8u) << 21)) * 255u;
+      const unsigned fm = ((fb & 1u) | ((fb & 2u) << 7) | ((fb & 4u) << 14) | ((fb & 8u) << 21)) * 255u;
+      unsigned word = (0x80808080u & ~zm) | fm;
+      if (ens && fz[k]) {
+        const unsigned nz = ((fz[k] & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | fz[k];
+        const unsigned sel = ((nz >> 7) & 0x01010101u) * 255u;
+        word = (word & ~sel) | (0x80808080u & sel);
+      }
+      words[k] = word;
+    }
+    if (NG == 4) stg_stream16(out + o, make_uint4(words[0], words[1 % NG], words[2 % NG], words[3 % NG]));
+    else *reinterpret_cast<unsigned*>(out + o) = words[0];
+  }
+}
+
+}  // namespace
+}  // namespace vu
+
+using namespace vu;
+
+extern "C" size_t vu_trimap_bits_workspace_bytes(int n, int th, int tw) {
+  if (n <= 0 || th <= 0 || tw <= 0) return 0;
+  return (size_t)8 * n * th * ((tw + 31) / 32) * sizeof(unsigned);
+}
+
+extern "C" int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* flags, int n, int h, int w, int th, int tw, int iters,
+                              uint8_t* out, void* workspace, size_t workspace_bytes, vu_stream_t stream) {
+  VU_REQUIRE(mask && out && workspace && n >= 0 && h > 0 && w > 0 && th > 0 && tw > 0 && iters >= 0);
+  VU_REQUIRE((fuzzy == nullptr) == (flags == nullptr));
+  const int sc = (w == 2 * tw && h == 2 * th) ? 2 : ((w == 4 * tw && h == 4 * th) ? 4 : 0);
+  if (sc == 0 || tw % 4 != 0 || iters > TB_MAXR || n > 65535) return VU_ERR_UNSUPPORTED;
+  const void* ptrs[] = {mask, fuzzy, out};
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 15) return VU_ERR_UNSUPPORTED;
+  if (workspace_bytes < vu_trimap_bits_workspace_bytes(n, th, tw) || (reinterpret_cast<uintptr_t>(workspace) & 3)) return VU_ERR_WORKSPACE;
+  if (n == 0) return VU_OK;
+  const int wpr = (tw + 31) / 32;
+  unsigned* planes = static_cast<unsigned*>(workspace);
+  dim3 ga((tw + TB_OW - 1) / TB_OW, (th + TB_OH - 1) / TB_OH, n);
+  const int ng = (w % 16 == 0) ? 4 : 1;
+  const int64_t items = (int64_t)h * (w / (4 * ng));
+  int64_t bx = (items + TB_THREADS - 1) / TB_THREADS;
+  const int64_t cap = ((int64_t)device_sms() * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  dim3 gb((unsigned)(bx < 1 ? 1 : bx), n);
+#define VU_UP(SCV)                                                                                                                   \
+  do {                                                                                                                               \
+    trimap_bits_kernel<SCV><<<ga, TB_THREADS, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, iters, planes, n, wpr);              \
+    if (ng == 4) trimap_up_bits_kernel<SCV, 4><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);          \
+    else trimap_up_bits_kernel<SCV, 1><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);                  \
+  } while (0)
+  if (sc == 2) VU_UP(2);
+  else VU_UP(4);
+#undef VU_UP
+  note_launch();
+  VU_RETURN_LAUNCH();
+}

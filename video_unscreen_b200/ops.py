@@ -131,6 +131,29 @@ def trimap_core(mask_lo, iters):
     return out
 
 
+def trimap_bits_supported(masks, th, tw, iters, fuzzy=None):
+    h, w = masks.shape[-2:]
+    exact = (h == 2 * th and w == 2 * tw) or (h == 4 * th and w == 4 * tw)
+    al = masks.data_ptr() % 16 == 0 and (fuzzy is None or fuzzy.data_ptr() % 16 == 0)
+    return exact and tw % 4 == 0 and 0 <= int(iters) <= 12 and al
+
+
+def trimap_bits(masks, th, tw, iters, fuzzy=None, flags=None, out=None):
+    """the trimap tail of trimap/agent.py:52-60 (+ the ensemble's :97 / :100 with ``fuzzy`` and ``flags``) in bit logic for
+    exact 2x / 4x working resolutions: masks [N,H,W] (or [H,W]) -> trimaps of the same shape."""
+    x = _mask(masks)
+    n = 1 if x.ndim == 2 else x.shape[0]
+    h, w = x.shape[-2:]
+    if out is None:
+        out = torch.empty_like(x)
+    ws_bytes = int(lib().vu_trimap_bits_workspace_bytes(n, int(th), int(tw)))
+    ws = torch.empty(ws_bytes, dtype=u8, device=x.device)
+    fz = _p(_dev(fuzzy)) if fuzzy is not None else ctypes.c_void_p(0)
+    fl = _p(_dev(flags)) if flags is not None else ctypes.c_void_p(0)
+    check(lib().vu_trimap_bits(_p(x), fz, fl, n, h, w, int(th), int(tw), int(iters), _p(out), _p(ws), ws_bytes, _stream()))
+    return out
+
+
 def dilate(x, ksize, iters):
     return morph(x, ksize, iters, _lib.DILATE)
 
