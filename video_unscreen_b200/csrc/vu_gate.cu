@@ -140,18 +140,36 @@ __global__ void __launch_bounds__(GT_THREADS) bgdiff_gate_kernel(const uint8_t* 
       __syncthreads();
     }
   }
-  // ---- out = mask where the dilated bit is set ----
+  // ---- out = mask where the dilated bit is set: 8 pixels (64-bit loads / stores) per thread when the rows allow ----
   const uint8_t* mk = masks + fpix;
   uint8_t* op = out + fpix;
-  for (int i = threadIdx.x; i < GT_TH * (GT_TW / 4); i += GT_THREADS) {
-    const int ty = i / (GT_TW / 4), tg = i - ty * (GT_TW / 4);
-    const int gy = Y0 + ty, gx = X0 + 4 * tg;
-    if (gy >= h || gx >= w) continue;
-    const int sx = 4 + 4 * tg;   // staged pixel index of gx
-    const unsigned bits = (D[ty + 4][sx >> 5] >> (sx & 31)) & 15u;
-    const unsigned keep = ((bits & 1u) ? 0xFFu : 0u) | ((bits & 2u) ? 0xFF00u : 0u) | ((bits & 4u) ? 0xFF0000u : 0u) | ((bits & 8u) ? 0xFF000000u : 0u);
-    const int64_t o = (int64_t)gy * w + gx;
-    *reinterpret_cast<unsigned*>(op + o) = __ldg(reinterpret_cast<const unsigned*>(mk + o)) & keep;
+  auto keep4 = [](unsigned bits) -> unsigned {
+    return (((bits & 1u) | ((bits & 2u) << 7) | ((bits & 4u) << 14) | ((bits & 8u) << 21)) * 255u);
+  };
+  if ((w & 7) == 0) {
+    for (int i = threadIdx.x; i < GT_TH * (GT_TW / 8); i += GT_THREADS) {
+      const int ty = i / (GT_TW / 8), tg = i - ty * (GT_TW / 8);
+      const int gy = Y0 + ty, gx = X0 + 8 * tg;
+      if (gy >= h || gx >= w) continue;
+      const int sx = 4 + 8 * tg;   // staged pixel index of gx: the 8 bits may straddle two words
+      const unsigned lo = D[ty + 4][sx >> 5], hi = (sx >> 5) + 1 < GT_WORDS ? D[ty + 4][(sx >> 5) + 1] : 0u;
+      const unsigned bits = __funnelshift_r(lo, hi, sx & 31) & 255u;
+      const int64_t o = (int64_t)gy * w + gx;
+      uint2 m = __ldg(reinterpret_cast<const uint2*>(mk + o));
+      m.x &= keep4(bits & 15u);
+      m.y &= keep4(bits >> 4);
+      *reinterpret_cast<uint2*>(op + o) = m;
+    }
+  } else {
+    for (int i = threadIdx.x; i < GT_TH * (GT_TW / 4); i += GT_THREADS) {
+      const int ty = i / (GT_TW / 4), tg = i - ty * (GT_TW / 4);
+      const int gy = Y0 + ty, gx = X0 + 4 * tg;
+      if (gy >= h || gx >= w) continue;
+      const int sx = 4 + 4 * tg;   // staged pixel index of gx
+      const unsigned bits = (D[ty + 4][sx >> 5] >> (sx & 31)) & 15u;
+      const int64_t o = (int64_t)gy * w + gx;
+      *reinterpret_cast<unsigned*>(op + o) = __ldg(reinterpret_cast<const unsigned*>(mk + o)) & keep4(bits);
+    }
   }
 }
 
@@ -167,7 +185,7 @@ extern "C" int vu_bgdiff_gate(const uint8_t* frames, const uint8_t* bg, const ui
   if (w % 4 != 0) return VU_ERR_UNSUPPORTED;
   const void* ptrs[] = {frames, bg, masks, out};
   for (const void* p : ptrs)
-    if (reinterpret_cast<uintptr_t>(p) & 3) return VU_ERR_UNSUPPORTED;
+    if (reinterpret_cast<uintptr_t>(p) & ((w & 7) == 0 ? 7 : 3)) return VU_ERR_UNSUPPORTED;
   if (n == 0) return VU_OK;
   if (n > 65535) return VU_ERR_UNSUPPORTED;
   dim3 grid((w + GT_TW - 1) / GT_TW, (h + GT_TH - 1) / GT_TH, n);

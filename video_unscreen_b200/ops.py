@@ -309,7 +309,7 @@ def gate(mask, g):
 
 
 def bgdiff_gate_supported(frames, bg, masks):
-    return frames.shape[-2] % 4 == 0 and all(t.data_ptr() % 4 == 0 for t in (frames, bg, masks))
+    return frames.shape[-2] % 4 == 0 and all(t.data_ptr() % 8 == 0 for t in (frames, bg, masks))
 
 
 def bgdiff_gate(frames, bg, masks, thr):
