@@ -197,7 +197,10 @@ int vu_cf_alpha_lut3d_u8(const uint8_t* hsv, int64_t npix, const uint8_t* lut3d,
  * h == s*th, w == s*tw, s in {2,4}; anything else returns VU_ERR_UNSUPPORTED and
  * the caller composes the stage from the primitives above. */
 int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int th, int tw,
-                 const uint8_t* lut3d, uint8_t* alpha_lo, uint64_t* stats2, vu_stream_t stream);
+                 const uint8_t* lut3d, uint8_t* alpha_lo, uint64_t* stats2, uint64_t* mask_counts2, vu_stream_t stream);
+/* mask_counts2 (nullable): per frame {#(mask > 128), #(mask < 128)}, the early-out counts of agent.py:303-307, taken
+ * from the mask bytes this pass reads anyway; only with s == 2, w % 16 == 0 and 16-byte aligned inputs
+ * (VU_ERR_UNSUPPORTED otherwise: use vu_count_gt_lt_u8). */
 /* postprocess (:259-283) step 1: per frame sum/count of alpha over
  * (alpha>128 && mask>0) -> stats[i] = {sum, count}; step 2 zeroes alpha below
  * 0.8 * sum/count (f64; count==0 leaves alpha untouched).  The d2,e2,e2,d2

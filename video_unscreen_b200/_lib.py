@@ -58,7 +58,7 @@ SIGNATURES = {
     "vu_set128_unflagged": (_i, [_p, _p, _p, _i, _i64, _p, _p]),
     "vu_cf_samples_workspace_bytes": (ctypes.c_size_t, [_i]),
     "vu_cf_samples": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, ctypes.c_size_t, _p]),
-    "vu_cf_lowres": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "vu_cf_lowres": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "vu_resize_up_u8": (_i, [_p, _i, _i, _i, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
     "vu_fuzzy_count": (_i, [_p, _p, _i, _i64, _i3, _i3, _p, _p, _p]),
     "vu_trimap_src_lo": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

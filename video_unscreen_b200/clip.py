@@ -53,12 +53,18 @@ def cf_predict_clip(frames, segmasks, agent, chunk=32, out=None):
     fg_min, bg_min = max(agent.fg_ncomp) * 5, max(agent.bg_ncomp) * 5
     for s, e in _chunks(n, chunk):
         fr, sm = frames[s:e], segmasks[s:e]
-        flags = ops.cf_degenerate_flags(sm, fg_min, bg_min)
         if ops.cf_lowres_supported(h, w, th, tw):
-            # one pass over the frames, then threshold+d2e2e2d2 in shared memory, then the up-scale
-            a_lo, stats = ops.cf_lowres(fr, sm, th, tw, lut3d)
+            # one pass over the frames (the early-out counts of the masks ride along where the pass sees every mask
+            # byte), then threshold + d2e2e2d2 marching in registers, then the up-scale
+            if ops.cf_lowres_counts_supported(fr, sm, th, tw):
+                a_lo, stats, mc = ops.cf_lowres(fr, sm, th, tw, lut3d, want_mask_counts=True)
+                flags = ops.degenerate_flags_from_counts(mc, fg_min, bg_min)
+            else:
+                flags = ops.cf_degenerate_flags(sm, fg_min, bg_min)
+                a_lo, stats = ops.cf_lowres(fr, sm, th, tw, lut3d)
             a_lo = ops.cross_chain(a_lo, [(_lib.DILATE, 2), (_lib.ERODE, 2), (_lib.ERODE, 2), (_lib.DILATE, 2)], stats, 0.8)
         else:
+            flags = ops.cf_degenerate_flags(sm, fg_min, bg_min)
             hsv_lo = ops.resize_linear_image(ops.bgr2hsv(fr), th, tw)
             a_lo = ops.cf_postprocess(ops.cf_alpha_lut3d(hsv_lo, lut3d), ops.resize_linear_mask(sm, th, tw), 0.8)
         # degenerate masks are returned as they came (agent.py:303-307): alt_src / alt_flags

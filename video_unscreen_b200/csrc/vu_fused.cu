@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(FT) cf_lowres_kernel(const uint8_t* __restrict
 // all the loads of a thread in flight before the first conversion
 __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
                                                              int tw, const uint8_t* __restrict__ lut3d, uint8_t* __restrict__ alpha_lo,
-                                                             unsigned long long* __restrict__ stats2) {
+                                                             unsigned long long* __restrict__ stats2, unsigned long long* __restrict__ mcounts2) {
   __shared__ HsvTab tab;
   hsv_tab_init(tab);
   __syncthreads();
@@ -416,6 +416,7 @@ __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __re
   const uint8_t* mk = masks + (int64_t)n * h * w;
   uint8_t* out = alpha_lo + (int64_t)n * th * tw;
   unsigned long long sum = 0, cnt = 0;
+  unsigned mgt = 0, mlt = 0;
   for (int64_t it = (int64_t)blockIdx.x * FT + threadIdx.x; it < items; it += (int64_t)gridDim.x * FT) {
     const int y = (int)(it / per_row), xg = (int)(it - (int64_t)y * per_row);
     uint4 fv[2][3], mv[2];
@@ -425,6 +426,21 @@ __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __re
 #pragma unroll
       for (int k = 0; k < 3; ++k) fv[r][k] = ldg_stream16(p + k);
       mv[r] = ldg_stream16(mk + (int64_t)(2 * y + r) * w + 16 * xg);
+    }
+    if (mcounts2) {   // the early-out counts of agent.py:303-307 from the mask bytes that pass through anyway
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const unsigned ws[4] = {mv[r].x, mv[r].y, mv[r].z, mv[r].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // bytes > 128 and bytes < 128, four at a time: bit 7 of (x + 127) is set iff x > 128 for x < 129 + 128; handle
+          // by the two cases of bit 7 of x
+          const unsigned x = ws[k], hi7 = x & 0x80808080u, lo7 = x & 0x7F7F7F7Fu;
+          const unsigned gt = hi7 & ((lo7 + 0x7F7F7F7Fu));          // bit 7 set and low 7 bits non-zero: x > 128
+          mgt += __popc(gt & 0x80808080u);
+          mlt += 4 - __popc(hi7);                                   // bit 7 clear: x < 128
+        }
+      }
     }
     unsigned res[2] = {0u, 0u};
 #pragma unroll
@@ -453,6 +469,7 @@ __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __re
     *reinterpret_cast<uint2*>(out + (int64_t)y * tw + 8 * xg) = make_uint2(res[0], res[1]);
   }
   warp_block_atomic2(sum, cnt, stats2 + 2 * n);
+  if (mcounts2) warp_block_atomic2(mgt, mlt, mcounts2 + 2 * n);
 }
 
 struct AxisC {
@@ -797,7 +814,7 @@ inline dim3 frame_grid(int n, int64_t items_per_frame) {
 // tabulated mixture evaluation + postprocess statistics (colorfiltering/
 // agent.py:310-320, 277-279).  h == s*th and w == s*tw with s in {2, 4}.
 extern "C" int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int th, int tw, const uint8_t* lut3d,
-                            uint8_t* alpha_lo, uint64_t* stats2, vu_stream_t stream) {
+                            uint8_t* alpha_lo, uint64_t* stats2, uint64_t* mask_counts2, vu_stream_t stream) {
   VU_REQUIRE(frames && masks && lut3d && alpha_lo && stats2 && n >= 0 && h > 0 && w > 0 && th > 0 && tw > 0);
   const int s = (h == 2 * th && w == 2 * tw) ? 2 : ((h == 4 * th && w == 4 * tw) ? 4 : 0);
   if (s == 0 || (w & 3) || (tw & 1)) return VU_ERR_UNSUPPORTED;
@@ -809,7 +826,14 @@ extern "C" int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, 
   auto* st = reinterpret_cast<unsigned long long*>(stats2);
   const bool wide = s == 2 && (w % 16 == 0) && (tw % 8 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && ((reinterpret_cast<uintptr_t>(alpha_lo) & 7) == 0);
-  if (wide) cf_lowres2_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 8)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
+  if (mask_counts2) {   // only the 16-column kernel sees every mask byte
+    if (!wide) return VU_ERR_UNSUPPORTED;
+    e = record_cuda(cudaMemsetAsync(mask_counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
+    if (e) return e;
+  }
+  if (wide)
+    cf_lowres2_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 8)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st,
+                                                                                       reinterpret_cast<unsigned long long*>(mask_counts2));
   else if (s == 2) cf_lowres_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 2)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   else cf_lowres_kernel<4><<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   VU_RETURN_LAUNCH();

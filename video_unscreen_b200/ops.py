@@ -198,15 +198,32 @@ def resize_up(x, dh, dw, mode=0, fuzzy=None, flags=None, alt_src=None, alt_flags
     return out
 
 
-def cf_lowres(frames, masks, th, tw, lut3d):
-    """fused BGR2HSV + down-scale + tabulated mixtures + postprocess statistics; -> (alpha_lo, stats)"""
+def cf_lowres(frames, masks, th, tw, lut3d, want_mask_counts=False):
+    """fused BGR2HSV + down-scale + tabulated mixtures + postprocess statistics; -> (alpha_lo, stats[, mask_counts]).
+    ``want_mask_counts`` (see cf_lowres_counts_supported): also [n,2] = (#(mask > 128), #(mask < 128)) per frame."""
     frames, masks, lut3d = _img(frames), _mask(masks), _dev(lut3d)
     n = 1 if frames.ndim == 3 else frames.shape[0]
     h, w = frames.shape[-3:-1]
     alpha = torch.empty((th, tw) if frames.ndim == 3 else (n, th, tw), dtype=u8, device=frames.device)
     stats = torch.empty((n, 2), dtype=torch.int64, device=frames.device)
-    check(lib().vu_cf_lowres(_p(frames), _p(masks), n, h, w, int(th), int(tw), _p(lut3d), _p(alpha), _p(stats), _stream()))
-    return alpha, stats
+    mc = torch.empty((n, 2), dtype=torch.int64, device=frames.device) if want_mask_counts else None
+    check(lib().vu_cf_lowres(_p(frames), _p(masks), n, h, w, int(th), int(tw), _p(lut3d), _p(alpha), _p(stats), _p(mc), _stream()))
+    return (alpha, stats, mc) if want_mask_counts else (alpha, stats)
+
+
+def cf_lowres_counts_supported(frames, masks, th, tw):
+    h, w = frames.shape[-3:-1]
+    return h == 2 * th and w == 2 * tw and w % 16 == 0 and tw % 8 == 0 and frames.data_ptr() % 16 == 0 and masks.data_ptr() % 16 == 0
+
+
+def degenerate_flags_from_counts(counts2, fg_min, bg_min):
+    """per-frame early-out flags of ColorFilteringAgent.forward from [n,2] (#(mask > 128), #(mask < 128))"""
+    c = _dev(counts2, torch.int64)
+    n = c.shape[0]
+    flags = torch.empty(n, dtype=u8, device=c.device)
+    second = ctypes.c_void_p(c.data_ptr() + 8)
+    check(lib().vu_cf_degenerate_flags(_p(c), second, n, 2, int(fg_min), int(bg_min), _p(flags), _stream()))
+    return flags
 
 
 def cf_lowres_supported(h, w, th, tw):
