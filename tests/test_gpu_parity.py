@@ -449,3 +449,20 @@ def test_trimap_bits_tail(vu, sc, th, tw, iters):
         want2.append(t)
     got2 = vu.ops.trimap_bits(torch.from_numpy(masks).cuda(), th, tw, iters, torch.from_numpy(fuzzy).cuda(), torch.from_numpy(flags).cuda()).cpu().numpy()
     assert np.array_equal(got2, np.stack(want2))
+
+
+@pytest.mark.parametrize("sc,sh,sw", [(2, 135, 240), (4, 90, 160), (2, 7, 12), (4, 5, 6), (2, 33, 100), (4, 67, 34)])
+def test_resize_up_exact_scales(vu, sc, sh, sw):
+    """vu_resize_up_u8 on exact 2x / 4x scales (the constant-weight kernel) against the cv2 model: random grey maps (every
+    phase, every border), plus the early-out frames copied from the alternative source."""
+    rng = np.random.default_rng(sc * 100 + sh + sw)
+    n = 3
+    src = rng.integers(0, 256, (n, sh, sw), dtype=np.uint8)
+    dh, dw = sc * sh, sc * sw
+    want = np.stack([M.resize_linear(x, dw, dh) for x in src])
+    got = host(vu.ops.resize_up(dev(src), dh, dw))
+    assert np.array_equal(got, want)
+    alt = rng.integers(0, 256, (n, dh, dw), dtype=np.uint8)
+    flags = np.array([0, 2, 1], np.uint8)
+    got = host(vu.ops.resize_up(dev(src), dh, dw, alt_src=dev(alt), alt_flags=dev(flags)))
+    assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], alt[1]) and np.array_equal(got[2], alt[2])

@@ -625,6 +625,81 @@ __global__ void __launch_bounds__(FT) resize_up_kernel(const uint8_t* __restrict
   }
 }
 
+// Exact 2x / 4x up-scales (1080p and 4K from the 540 x 960 working resolution), plain mode: the interpolation phases
+// and weights are compile-time constants (2x: 512/1536; 4x: 256/768/1280/1792 of 2048), the taps of a pixel are the 2x2
+// neighbourhood towards its quadrant with replicate clamping (at the borders cv2 resets the fraction horizontally and
+// clamps the index vertically: with both taps on the same pixel and weights that sum to 2048 that is the same
+// number), and a thread owns 8 destination columns for a run of rows: one 64-bit store per row, the horizontal pass of
+// a source row computed once for all the destination rows that use it.
+template <int SC>
+__global__ void __launch_bounds__(FT) resize_up_int_kernel(const uint8_t* __restrict__ src, int sh, int sw, uint8_t* __restrict__ dst,
+                                                           const uint8_t* __restrict__ alt_src, const uint8_t* __restrict__ alt_flags, int run) {
+  constexpr int NS = 8 / SC;   // source columns under the 8 destination columns
+  const int n = blockIdx.z;
+  const int dh = SC * sh, dw = SC * sw;
+  const int tx = blockIdx.x * 32 + (threadIdx.x & 31);   // 8-column group
+  const int ry = blockIdx.y * (FT / 32) + (threadIdx.x >> 5);
+  const int x0 = 8 * tx, y0 = ry * run;
+  if (x0 >= dw || y0 >= dh) return;
+  const int y1 = min(dh, y0 + run);
+  uint8_t* d = dst + (int64_t)n * dh * dw;
+  if (alt_flags && alt_flags[n] != 0) {   // early-out frame: copied from the full-resolution alternative
+    for (int y = y0; y < y1; ++y)
+      *reinterpret_cast<uint2*>(d + (int64_t)y * dw + x0) = __ldg(reinterpret_cast<const uint2*>(alt_src + ((int64_t)n * dh + y) * dw + x0));
+    return;
+  }
+  const uint8_t* s = src + (int64_t)n * sh * sw;
+  const int c0 = x0 / SC;
+  // weights of (left tap, right tap) per phase, in 1/2048
+  auto w0 = [](int ph) { return SC == 2 ? (ph == 0 ? 512 : 1536) : (ph == 0 ? 768 : (ph == 1 ? 256 : (ph == 2 ? 1792 : 1280))); };
+  auto hrow = [&](int sy, int (&R)[8]) {
+    int t[NS + 2];   // source columns c0-1 .. c0+NS, replicated at the borders
+    const uint8_t* r = s + (int64_t)sy * sw;
+#pragma unroll
+    for (int k = 0; k < NS + 2; ++k) t[k] = (int)__ldg(r + min(max(c0 - 1 + k, 0), sw - 1));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = k / SC, ph = k % SC;                     // column c0 + c, phase ph
+      const int il = ph < SC / 2 ? c : c + 1;                // index into t of the left tap (t[c+1] is column c0 + c)
+      R[k] = (t[il] * w0(ph) + t[il + 1] * (2048 - w0(ph))) >> 4;
+    }
+  };
+  int Ra[8], Rb[8];
+  int ya = -1, yb = -1;
+  for (int y = y0; y < y1; ++y) {
+    const int r = y / SC, ph = y % SC;
+    const int ia = ph < SC / 2 ? max(r - 1, 0) : r, ib = ph < SC / 2 ? r : min(r + 1, sh - 1);
+    if (ia != ya) {
+      if (ia == yb) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Ra[k] = Rb[k];
+      } else {
+        hrow(ia, Ra);
+      }
+      ya = ia;
+    }
+    if (ib != yb) {
+      if (ib == ya) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) Rb[k] = Ra[k];
+      } else {
+        hrow(ib, Rb);
+      }
+      yb = ib;
+    }
+    const int b0 = SC == 2 ? (ph == 0 ? 512 : 1536) : (ph == 0 ? 768 : (ph == 1 ? 256 : (ph == 2 ? 1792 : 1280)));
+    const int b1 = 2048 - b0;
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned v = (unsigned)((((b0 * Ra[k]) >> 16) + ((b1 * Rb[k]) >> 16) + 2) >> 2);   // <= 255 by construction
+      if (k < 4) lo |= v << (8 * k);
+      else hi |= v << (8 * (k - 4));
+    }
+    *reinterpret_cast<uint2*>(d + (int64_t)y * dw + x0) = make_uint2(lo, hi);
+  }
+}
+
 // counts2[n] = {#(v > thr), #(v < thr)} in one vectorised pass (the two early-out tests of colorfiltering/agent.py:303-307)
 __global__ void __launch_bounds__(FT) count_gt_lt_kernel(const uint8_t* __restrict__ src, int64_t per_item, int thr, unsigned long long* __restrict__ counts2) {
   const int n = blockIdx.y;
@@ -849,6 +924,18 @@ extern "C" int vu_resize_up_u8(const uint8_t* src, int n, int sh, int sw, uint8_
   VU_REQUIRE((alt_src == nullptr) == (alt_flags == nullptr));
   if (sw == 2 * dw && sh == 2 * dh) return VU_ERR_UNSUPPORTED;  // cv2 switches to INTER_AREA there
   if (n == 0) return VU_OK;
+  {
+    // exact 2x / 4x, plain mode, 8-byte aligned rows: the constant-weight kernel
+    const int sc = (dw == 2 * sw && dh == 2 * sh) ? 2 : ((dw == 4 * sw && dh == 4 * sh) ? 4 : 0);
+    const bool al = ((reinterpret_cast<uintptr_t>(dst) & 7) == 0) && (!alt_src || (reinterpret_cast<uintptr_t>(alt_src) & 7) == 0);
+    if (mode == 0 && sc != 0 && dw % 8 == 0 && al && n <= 65535) {
+      const int run = 16 * sc;   // destination rows per thread: 16 source rows
+      dim3 g((dw / 8 + 31) / 32, ((dh + run - 1) / run + FT / 32 - 1) / (FT / 32), n);
+      if (sc == 2) resize_up_int_kernel<2><<<g, FT, 0, S(stream)>>>(src, sh, sw, dst, alt_src, alt_flags, run);
+      else resize_up_int_kernel<4><<<g, FT, 0, S(stream)>>>(src, sh, sw, dst, alt_src, alt_flags, run);
+      VU_RETURN_LAUNCH();
+    }
+  }
   dim3 grid((dw + RU_TW - 1) / RU_TW, (dh + RU_TH - 1) / RU_TH, n);
   if (mode == 0) resize_up_kernel<0><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
   else resize_up_kernel<1><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
