@@ -104,6 +104,18 @@ int vu_resize_linear_u8(const uint8_t* src, int n, int sh, int sw, int channels,
 int vu_resize_nearest_u8(const uint8_t* src, int n, int sh, int sw, int channels, uint8_t* dst, int dh, int dw,
                          vu_stream_t stream);
 
+/* shift_fg: cv2.warpAffine(img, [[1,0,dx],[0,1,dy]], (w,h)) -- fixed-point
+ * bilinear translation, taps outside the image read 0.
+ * dx / dy are float because the reference stores the matrix as float32.
+ * channels is 1 or 3.  unscreen/utils/imgprocess.py:55-64, replace.py:69,71 */
+int vu_shift_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int channels, float dx, float dy,
+                vu_stream_t stream);
+/* rescale_fg: cv2.resize(fx=fy=factor, INTER_CUBIC) then the centre crop back
+ * to h x w; 1 <= factor <= 16; channels is 1 or 3.
+ * unscreen/utils/imgprocess.py:40-52, replace.py:70,72 */
+int vu_rescale_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int channels, double factor,
+                        vu_stream_t stream);
+
 /* cv2.resize (bilinear) of single-channel maps with the coefficient math hoisted
  * out of the pixel loop.  mode 1 fuses trimap/agent.py:60 (values strictly between
  * 0 and 255 -> 128) and :100 (128 where fuzzy != 0, only for frames with

@@ -190,6 +190,112 @@ def resize_nearest(src, dw, dh):
 
 
 # --------------------------------------------------------------------------
+# geometric pre-steps of the replacement path
+# --------------------------------------------------------------------------
+
+
+def warp_translate(src, dx, dy):
+    """cv2.warpAffine(src, np.float32([[1, 0, dx], [0, 1, dy]]), (W, H)) on
+    uint8 (default INTER_LINEAR, BORDER_CONSTANT 0) -- unscreen/utils/
+    imgprocess.py:55-64 (``shift_fg``), SURVEY.md A.8.
+
+    The matrix is stored as float32, inverted in double (dst(x, y) <- src(x -
+    dx, y - dy)), and evaluated in fixed point: 10 fractional bits per
+    coordinate term, each term rounded half-to-even on its own, +16 and >> 5
+    to a 5-bit sub-pixel fraction; the 2x2 weights are 32 * (32 - fx | fx) *
+    (32 - fy | fy) (exact in the 15-bit remap table, so the table's
+    sum-correction never fires); dst = (sum(w * tap) + 16384) >> 15; taps
+    outside the image read 0."""
+    src = np.asarray(src)
+    h, w = src.shape[:2]
+    b1 = -float(np.float32(dx))
+    b2 = -float(np.float32(dy))
+    X = (int(np.rint(b1 * 1024.0)) + 16 + 1024 * np.arange(w, dtype=np.int64)) >> 5
+    Y = (np.rint((np.arange(h, dtype=np.float64) + b2) * 1024.0).astype(np.int64) + 16) >> 5
+    # cv2 stores the integer part as int16 (saturating)
+    sx = np.clip(X >> 5, -32768, 32767)
+    sy = np.clip(Y >> 5, -32768, 32767)
+    fx = (X & 31)[None, :]
+    fy = (Y & 31)[:, None]
+    s = src.astype(np.int64)
+    if s.ndim == 2:
+        s = s[..., None]
+
+    def tap(yy, xx):
+        ok = ((yy >= 0) & (yy < h))[:, None] & ((xx >= 0) & (xx < w))[None, :]
+        v = s[np.clip(yy, 0, h - 1)][:, np.clip(xx, 0, w - 1)]
+        return v * ok[..., None]
+
+    acc = (tap(sy, sx) * (32 * (32 - fx) * (32 - fy))[..., None] + tap(sy, sx + 1) * (32 * fx * (32 - fy))[..., None]
+           + tap(sy + 1, sx) * (32 * (32 - fx) * fy)[..., None] + tap(sy + 1, sx + 1) * (32 * fx * fy)[..., None])
+    out = ((acc + 16384) >> 15).astype(np.uint8)
+    return out.reshape(src.shape)
+
+
+def cubic_axis(dst, src, factor, off=0, count=None):
+    """tap indices (clamped) and float32 weights of the bicubic (a = -0.75)
+    up-scale by ``factor`` for destination positions off .. off+count-1.
+    Coefficients are evaluated in float64 from the float64 source position and
+    rounded to float32 once."""
+    count = dst - off if count is None else count
+    d = np.arange(off, off + count, dtype=np.float64)
+    p = (d + 0.5) / float(factor) - 0.5
+    s = np.floor(p)
+    x = p - s
+    A = -0.75
+    c0 = ((A * (x + 1) - 5 * A) * (x + 1) + 8 * A) * (x + 1) - 4 * A
+    c1 = ((A + 2) * x - (A + 3)) * x * x + 1
+    c2 = ((A + 2) * (1 - x) - (A + 3)) * (1 - x) * (1 - x) + 1
+    c3 = 1 - c0 - c1 - c2
+    co = np.stack([c0, c1, c2, c3], 1).astype(np.float32)
+    idx = np.clip(s.astype(np.int64)[:, None] + np.arange(-1, 3)[None, :], 0, src - 1)
+    return idx, co
+
+
+def rescale_size(n, factor):
+    """cv2.resize(..., fx=factor): dsize = saturate_cast<int>(n * factor)
+    (round half to even)."""
+    return int(np.rint(n * float(factor)))
+
+
+def resize_cubic_crop(src, factor):
+    """cv2.resize(src, None, fx=factor, fy=factor, interpolation=INTER_CUBIC)
+    followed by the centre crop back to the source size --
+    unscreen/utils/imgprocess.py:40-52 (``rescale_fg``), factor >= 1.
+
+    PARITY NOTE.  cv2 4.13.0 in the build container dispatches this call to
+    Intel IPP's closed-source float32 cubic; with IPP switched off
+    (cv2.ipp.setUseIPP(False)) the same call runs OpenCV's 11-bit fixed-point
+    kernel and 8 % of the values differ by 1.  The model here is the one the
+    default (IPP) path follows: separable float bicubic, a = -0.75, replicated
+    borders, round half to even, saturate.  It is evaluated in float32 with a
+    fixed order (horizontal then vertical, taps -1, 0, +1, +2 accumulated left
+    to right with separate multiplies and adds), which agrees with the IPP
+    result everywhere except at values whose exact result is within float32
+    rounding noise of a .5 tie: < 1e-5 of the values, off by 1 (tools/
+    probe_cubic_*.py).  The CUDA kernel is bit-exact against THIS model."""
+    src = np.asarray(src)
+    h, w = src.shape[:2]
+    dh, dw = rescale_size(h, factor), rescale_size(w, factor)
+    h_off = int((dh - h) / 2)
+    w_off = int((dw - w) / 2)
+    yi, yc = cubic_axis(dh, h, factor, h_off, h)
+    xi, xc = cubic_axis(dw, w, factor, w_off, w)
+    s = src.astype(np.float32)
+    if s.ndim == 2:
+        s = s[..., None]
+    hor = s[:, xi[:, 0]] * xc[:, 0][None, :, None]
+    for k in range(1, 4):
+        hor = hor + s[:, xi[:, k]] * xc[:, k][None, :, None]
+    v = hor[yi[:, 0]] * yc[:, 0][:, None, None]
+    for k in range(1, 4):
+        v = v + hor[yi[:, k]] * yc[:, k][:, None, None]
+    assert hor.dtype == np.float32 and v.dtype == np.float32
+    out = np.clip(np.rint(v), 0, 255).astype(np.uint8)
+    return out.reshape(src.shape)
+
+
+# --------------------------------------------------------------------------
 # morphology
 # --------------------------------------------------------------------------
 

@@ -326,6 +326,25 @@ def replace_blend(fg, mask3, bg):
     return res.astype(np.uint8)
 
 
+def shift_fg(img, dx=0, dy=0):
+    """unscreen/utils/imgprocess.py:55-64."""
+    return cvm.warp_translate(img, dx, dy)
+
+
+def rescale_fg(img, scale_factor=1.1):
+    """unscreen/utils/imgprocess.py:40-52 (see the parity note of
+    ``cvmodel.resize_cubic_crop``)."""
+    return cvm.resize_cubic_crop(img, scale_factor)
+
+
+def replace_frame(fg, mask, bg, dx, dy, scale_factor=1.2):
+    """tools/replace/replace.py:69-76: shift and rescale the foreground and its
+    mask, then blend over the (already resized) new background."""
+    fg_s = rescale_fg(shift_fg(fg, dx, dy), scale_factor)
+    mk_s = rescale_fg(shift_fg(mask, dx, dy), scale_factor)
+    return replace_blend(fg_s, mk_s, bg)
+
+
 def patch_bg(bgimg, frame, alpha, mode):
     """tools/unscreen/green.py:125 (mode 'lt128') and bg.py:99 /
     bg_offline.py:171 (mode 'eq0'): predicated copy frame -> bgimg."""

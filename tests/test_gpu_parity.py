@@ -466,3 +466,53 @@ def test_resize_up_exact_scales(vu, sc, sh, sw):
     flags = np.array([0, 2, 1], np.uint8)
     got = host(vu.ops.resize_up(dev(src), dh, dw, alt_src=dev(alt), alt_flags=dev(flags)))
     assert np.array_equal(got[0], want[0]) and np.array_equal(got[1], alt[1]) and np.array_equal(got[2], alt[2])
+
+
+SHIFTS = [(3, -2), (0.5, 0.5), (0, 0), (-7.3, 4.9), (12.015625, -0.984375), (1e-3, 33.333), (-100, 2), (0.484375, 0.515625), (5.7, 200),
+          (-0.015, -0.016), (1e-30, -1e-30)]
+
+
+@pytest.mark.parametrize("shape", [(64, 80, 3), (64, 80), (61, 83, 3), (45, 37), (135, 240, 3), (70, 496, 3), (33, 1024)])
+def test_shift_fg(vu, shape):
+    """shift_fg (imgprocess.py:55-64) through both kernels -- the TMA tile kernel (rows of a multiple of 16 bytes) and the
+    generic one (anything else) -- against the fixed-point warpAffine model: bit-exact, every sub-pixel phase class,
+    shifts that leave the frame, clips (frames must not leak into each other)."""
+    rng = np.random.default_rng(sum(shape))
+    clip = rng.integers(0, 256, (3,) + shape, dtype=np.uint8)
+    ch = 3 if len(shape) == 3 else 1
+    for dx, dy in SHIFTS:
+        want = np.stack([M.warp_translate(f, dx, dy) for f in clip])
+        got = host(vu.ops.shift(dev(clip), dx, dy, ch))
+        assert np.array_equal(got, want), (shape, dx, dy, int((got != want).sum()))
+    img = clip[0]
+    assert np.array_equal(vu.U.shift_fg(img, dx=2.25, dy=-3.75), M.warp_translate(img, 2.25, -3.75))
+
+
+@pytest.mark.parametrize("shape", [(64, 80, 3), (64, 80), (61, 83, 3), (45, 37), (135, 240, 3), (40, 700), (100, 130, 3)])
+def test_rescale_fg(vu, shape):
+    """rescale_fg (imgprocess.py:40-52) against the float bicubic model: bit-exact (same float32 operation order), for
+    the script's factor 1.2, the default 1.1, and factors whose taps reach over the border (1.0, 1.01) or skip rows (3.7)."""
+    rng = np.random.default_rng(sum(shape) + 1)
+    clip = rng.integers(0, 256, (2,) + shape, dtype=np.uint8)
+    ch = 3 if len(shape) == 3 else 1
+    for f in (1.2, 1.1, 1.0, 1.01, 1.5, 2.0, 3.7):
+        want = np.stack([M.resize_cubic_crop(x, f) for x in clip])
+        got = host(vu.ops.rescale_cubic(dev(clip), f, ch))
+        assert np.array_equal(got, want), (shape, f, int((got != want).sum()))
+    assert np.array_equal(vu.U.rescale_fg(clip[0], 1.2), M.resize_cubic_crop(clip[0], 1.2))
+
+
+def test_replace_with_geometry(vu):
+    """replace.py:69-76 end to end: shift + rescale of foreground and (3-channel and single-channel) mask, then the
+    float64 blend; every stage is bit-exact against the oracle, so the composite is too."""
+    from video_unscreen_b200 import clip as C
+    rng = np.random.default_rng(9)
+    n, h, w = 3, 96, 160
+    fg = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    a = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    a3 = np.repeat(a[..., None], 3, axis=3)
+    bg = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    for dx, dy, sc in [(3, -2, 1.2), (0.5, 0.5, 1.2), (-4.3, 7.9, 1.1)]:
+        want = np.stack([R.replace_frame(fg[i], a3[i], bg, dx, dy, sc) for i in range(n)])
+        assert np.array_equal(host(C.replace_clip(dev(fg), dev(a3), dev(bg), dx, dy, sc)), want)
+        assert np.array_equal(host(C.replace_clip(dev(fg), dev(a), dev(bg), dx, dy, sc)), want)

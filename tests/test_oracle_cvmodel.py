@@ -66,3 +66,35 @@ def test_inrange():
     s = rng.integers(0, 256, (50, 60, 3), dtype=np.uint8)
     lo, hi = np.array([10, 100, 20]), np.array([90, 255, 200])
     assert np.array_equal(M.in_range(s, lo, hi), cv2.inRange(s, lo, hi))
+
+
+@pytest.mark.parametrize("shape", [(61, 83, 3), (64, 48), (135, 240, 3)])
+def test_warp_translate(shape):
+    """shift_fg's cv2.warpAffine translation: bit-exact, including shifts that no phase table of the
+    survey's probe covered (arbitrary fractions, out-of-frame shifts, tiny shifts)."""
+    rng = np.random.default_rng(sum(shape))
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    for dx, dy in [(3, -2), (0.5, 0.5), (0, 0), (-7.3, 4.9), (12.015625, -0.984375), (1e-3, 33.333), (-100, 2), (0.484375, 0.515625),
+                   (5.7, 200), (2.25, -3.75), (-0.015, -0.016), (1e-30, -1e-30)]:
+        ref = cv2.warpAffine(img, np.float32([[1, 0, dx], [0, 1, dy]]), (shape[1], shape[0]))
+        assert np.array_equal(M.warp_translate(img, dx, dy), ref), (dx, dy)
+
+
+CUBIC_TIE_TOL = 1e-4   # fraction of values allowed to differ (by one) from cv2's IPP float cubic; observed < 1.5e-5
+
+
+@pytest.mark.parametrize("shape", [(270, 480, 3), (135, 241, 3), (100, 90)])
+def test_resize_cubic_crop(shape):
+    """rescale_fg's cv2.resize(INTER_CUBIC) + centre crop.  cv2 dispatches to Intel IPP's closed float kernel here; the
+    model agrees except where the exact value sits within float rounding noise of a .5 tie (see the model's parity
+    note): at most one LSB, on fewer than CUBIC_TIE_TOL of the values."""
+    rng = np.random.default_rng(sum(shape))
+    img = rng.integers(0, 256, shape, dtype=np.uint8)
+    h, w = shape[:2]
+    for f in (1.2, 1.1, 1.5, 1.0):
+        r = cv2.resize(img, None, fx=f, fy=f, interpolation=cv2.INTER_CUBIC)
+        assert r.shape[:2] == (M.rescale_size(h, f), M.rescale_size(w, f))
+        ho, wo = int((r.shape[0] - h) / 2), int((r.shape[1] - w) / 2)
+        ref = r[ho:ho + h, wo:wo + w].astype(int)
+        d = np.abs(M.resize_cubic_crop(img, f).astype(int) - ref)
+        assert d.max() <= 1 and (d > 0).mean() <= CUBIC_TIE_TOL, (f, int((d > 0).sum()))

@@ -91,3 +91,25 @@ def test_colorfilter_predict(ref):
     alpha, bg, _ = R.cf_forward_predict(frame, seg, lb, lf, bgh, 160)
     assert np.array_equal(alpha, alpha_ref)
     assert np.abs(bg.astype(int) - bg_ref.astype(int)).max() <= 1
+
+
+def test_replace_geometry(ref):
+    """shift_fg (bit-exact) and rescale_fg (the documented tie tolerance against cv2's IPP cubic) of the live reference,
+    and the composed frame of tools/replace/replace.py:69-76."""
+    rng = np.random.default_rng(81)
+    fg = rng.integers(0, 256, (108, 192, 3), dtype=np.uint8)
+    m3 = np.repeat(rng.integers(0, 256, (108, 192, 1), dtype=np.uint8), 3, axis=2)
+    bg = rng.integers(0, 256, (108, 192, 3), dtype=np.uint8)
+    for dx, dy in [(3, -2), (0.5, 0.5), (-6.37, 2.81)]:
+        assert np.array_equal(R.shift_fg(fg, dx, dy), ref.U.shift_fg(fg, dx=dx, dy=dy))
+        assert np.array_equal(R.shift_fg(m3[..., 0], dx, dy), ref.U.shift_fg(m3[..., 0], dx=dx, dy=dy))
+    for sc in (1.2, 1.1):
+        d = np.abs(R.rescale_fg(fg, sc).astype(int) - ref.U.rescale_fg(fg, scale_factor=sc).astype(int))
+        assert d.max() <= 1 and (d > 0).mean() <= 1e-4
+    # replace.py:69-76 restated with the reference's own functions
+    f = ref.U.rescale_fg(ref.U.shift_fg(fg, dx=3, dy=-2), scale_factor=1.2)
+    m = ref.U.rescale_fg(ref.U.shift_fg(m3, dx=3, dy=-2), scale_factor=1.2)
+    nb = m.astype(np.float64) / 255
+    want = (f.astype(np.float64) * nb + bg.astype(np.float64) * (1 - nb)).astype(np.uint8)
+    d = np.abs(R.replace_frame(fg, m3, bg, 3, -2, 1.2).astype(int) - want.astype(int))
+    assert d.max() <= 2 and (d > 0).mean() <= 1e-3

@@ -149,6 +149,34 @@ def main():
                n * 7 * h * w + 3 * h * w, 1 / dt, "oracle replace_blend on 1 frame (numpy float64, 1 thread); output bit-exact", peak)
         del fg, al, bg, out
 
+    if want("replace_geo_1080p"):
+        # the whole per-frame body of tools/replace/replace.py:69-76: shift + bicubic rescale of foreground and mask, blend
+        n, h, w = 120, 1080, 1080 * 16 // 9
+        g = torch.Generator(device="cuda").manual_seed(4)
+        fg = torch.randint(0, 256, (n, h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+        al = torch.randint(0, 256, (n, h, w), dtype=torch.uint8, device="cuda", generator=g)
+        bg = torch.randint(0, 256, (h, w, 3), dtype=torch.uint8, device="cuda", generator=g)
+        out = [None]
+        for tag, dx, dy in (("int", 3, -2), ("frac", 0.5, 0.5)):   # the two correspondences hard-coded at replace.py:20-23
+            def step():
+                out[0] = clip.replace_clip(fg, al, bg, dx, dy, 1.2)
+            ms, launches = timed(step, args.steps)
+            f0, a0, b0 = fg[0].cpu().numpy(), al[0].cpu().numpy(), bg.cpu().numpy()
+            t0 = time.perf_counter()
+            ref = R.replace_frame(f0, a0, b0, dx, dy, 1.2)
+            dt = time.perf_counter() - t0
+            assert np.array_equal(out[0][0].cpu().numpy(), ref)
+            report("replace_geo_1080p_" + tag, f"replace.py:69-76 with the geometric pre-steps (shift_fg dx={dx} dy={dy}, rescale_fg 1.2), "
+                   "120 x 1080p, single-channel mask, shared background", n, ms, launches, n * 7 * h * w + 3 * h * w, 1 / dt,
+                   "oracle replace_frame on 1 frame (numpy, 1 thread); output bit-exact", peak)
+        for name, fn in (("shift_int", lambda: ops.shift(fg, 3, -2, 3)), ("shift_frac", lambda: ops.shift(fg, 0.5, 0.5, 3)),
+                         ("rescale", lambda: ops.rescale_cubic(fg, 1.2, 3)), ("rescale_mask", lambda: ops.rescale_cubic(al, 1.2, 1))):
+            ms, launches = timed(fn, args.steps)
+            per = (1 if name == "rescale_mask" else 3) * h * w
+            print(json.dumps({"kernel": name, "ms": round(ms, 4), "frames": n, "gbps": round(2 * n * per / ms / 1e6, 1),
+                              "frac": round(2 * n * per / ms / 1e6 / peak, 3)}), flush=True)
+        del fg, al, bg, out
+
     if want("masked_mean_1080p"):
         n, h, w = 300, 1080, 1920
         fr = bench.make_clip_device(n, h, w, 2, torch.device("cuda"))

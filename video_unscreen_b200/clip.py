@@ -144,8 +144,17 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None
     return alpha, tri, fg, bgo
 
 
-def replace_clip(fg, alpha, bg):
-    """tools/replace/replace.py:74-76 for a whole clip; ``bg`` is [H,W,3] (shared) or [N,H,W,3]."""
+def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None):
+    """tools/replace/replace.py:69-76 for a whole clip; ``bg`` is [H,W,3] (shared) or [N,H,W,3].  With ``dx``/``dy``
+    and/or ``scale`` the foreground and its mask first go through shift_fg / rescale_fg (:69-72) like in the script;
+    without them this is the blend of :74-76 alone (BASELINE config 4)."""
+    ach = 3 if alpha.ndim == fg.ndim else 1
+    if dx is not None or dy is not None:
+        fg = ops.shift(fg, dx or 0, dy or 0, 3)
+        alpha = ops.shift(alpha, dx or 0, dy or 0, ach)
+    if scale is not None:
+        fg = ops.rescale_cubic(fg, scale, 3)
+        alpha = ops.rescale_cubic(alpha, scale, ach)
     return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg)
 
 

@@ -1,0 +1,349 @@
+// Geometric pre-steps of the replacement path (tools/replace/replace.py:69-72):
+//
+//   shift_fg   unscreen/utils/imgprocess.py:55-64   cv2.warpAffine(img, [[1,0,dx],[0,1,dy]], (W,H))
+//   rescale_fg unscreen/utils/imgprocess.py:40-52   cv2.resize(fx=fy=s, INTER_CUBIC) + centre crop to the input size
+//
+// shift: cv2's fixed-point warp.  For a pure translation the source position of every destination
+// pixel is (x + ox, y + oy) plus ONE 5-bit sub-pixel fraction (fx, fy) for the whole image, so the warp is a constant
+// 2x2 filter: dst = (32*[(32-fy)*((32-fx)*a + fx*b) + fy*((32-fx)*c + fx*d)] + 16384) >> 15 with taps outside the
+// image reading 0.  The tile kernel lets the TMA unit do both the translation and the border: the box is fetched at
+// byte coordinate (x0 + ox)*C, row y0 + oy - any integers - and the unit zero-fills what lies outside the frame.
+//
+// rescale: separable float bicubic (a = -0.75) with replicated borders, rounded half to even - the model of the
+// Intel-IPP path cv2 4.13 dispatches this call to (oracle/cvmodel.py:resize_cubic_crop holds the parity note).  Only
+// the cropped window is computed.
+#include <cmath>
+#include <cstdlib>
+
+#include "vu_common.cuh"
+#include "vu_tma.cuh"
+
+namespace vu {
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// shift
+// ---------------------------------------------------------------------------------------------------------------
+
+// Y0(y) = rint((y + b2) * 1024) + 16: integer row y + oy and fraction fy of destination row y  (b2 = -dy)
+__host__ __device__ inline void shift_row(int y, double b2, int& sy, int& fy) {
+#ifdef __CUDA_ARCH__
+  const long long Y = ((long long)rint(((double)y + b2) * 1024.0) + 16) >> 5;
+#else
+  const long long Y = ((long long)std::nearbyint(((double)y + b2) * 1024.0) + 16) >> 5;
+#endif
+  long long s = Y >> 5;
+  s = s < -32768 ? -32768 : (s > 32767 ? 32767 : s);   // cv2 keeps the integer part as a saturated int16
+  sy = (int)s;
+  fy = (int)(Y & 31);
+}
+
+// any shape, any alignment: one thread per destination byte
+template <int C>
+__global__ void __launch_bounds__(256) shift_generic_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n, int h, int w, int ox,
+                                                            int fx, double b2) {
+  const int64_t wc = (int64_t)w * C, per = (int64_t)h * wc, total = per * n;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t f = i / per, r = i - f * per;
+    const int y = (int)(r / wc), j = (int)(r - (int64_t)y * wc);
+    const int x = j / C, ch = j - x * C;
+    int sy, fy;
+    shift_row(y, b2, sy, fy);
+    int sx = x + ox;
+    sx = sx < -32768 ? -32768 : (sx > 32767 ? 32767 : sx);
+    const uint8_t* fr = src + f * per;
+    auto tap = [&](int yy, int xx) -> int {
+      return ((unsigned)yy < (unsigned)h && (unsigned)xx < (unsigned)w) ? (int)__ldg(fr + ((int64_t)yy * w + xx) * C + ch) : 0;
+    };
+    const int a = tap(sy, sx), b = tap(sy, sx + 1), c = tap(sy + 1, sx), d = tap(sy + 1, sx + 1);
+    const int acc = 32 * ((32 - fy) * ((32 - fx) * a + fx * b) + fy * ((32 - fx) * c + fx * d));
+    dst[i] = (uint8_t)((acc + 16384) >> 15);
+  }
+}
+
+constexpr int SH_TB = 232;         // destination bytes of a tile row: 29 lanes x 8 bytes
+constexpr int SH_TR = 32;          // destination rows of a tile: 8 warps x 4 consecutive rows
+constexpr int SH_RPW = 4;
+constexpr int SH_BOX_W = 256, SH_BOX_H = SH_TR + 1;
+
+// horizontal pass of 8 destination bytes of one source row: H = (32-fx)*a + fx*b (13 bits) for every byte, as four
+// words of two 16-bit lanes: he[k] = bytes (4k, 4k+2), ho[k] = bytes (4k+1, 4k+3).  `p` points at the 8-byte group of
+// the tile row that holds the first source byte, `m` (0..7) is where in the group it sits.
+template <int C>
+__device__ __forceinline__ void shift_hrow(const uint8_t* p, int m, unsigned wx0, unsigned wx1, unsigned (&s)[3], unsigned (&he)[2],
+                                           unsigned (&ho)[2]) {
+  const uint2 a = *reinterpret_cast<const uint2*>(p), b = *reinterpret_cast<const uint2*>(p + 8);
+  const unsigned w4 = *reinterpret_cast<const unsigned*>(p + 16);
+  const bool q = (m & 4) != 0;
+  const unsigned x0 = q ? a.y : a.x, x1 = q ? b.x : a.y, x2 = q ? b.y : b.x, x3 = q ? w4 : b.y;
+  const unsigned sel = 0x3210u + 0x1111u * (unsigned)(m & 3);
+  s[0] = __byte_perm(x0, x1, sel);
+  s[1] = __byte_perm(x1, x2, sel);
+  s[2] = __byte_perm(x2, x3, sel);
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const unsigned t = __byte_perm(s[k], s[k + 1], C == 1 ? 0x4321 : 0x6543);   // the same bytes, C further right
+    he[k] = (s[k] & 0x00FF00FFu) * wx0 + (t & 0x00FF00FFu) * wx1;
+    ho[k] = __byte_perm(s[k], 0u, 0x4341) * wx0 + __byte_perm(t, 0u, 0x4341) * wx1;
+  }
+}
+
+// The TMA unit wants every row of a box to start on a 16-byte boundary of global memory, so the box is fetched from
+// the aligned column below the (arbitrary) source column and the remainder (0..15 bytes) is taken out when the
+// threads pick their bytes from shared memory: 232 + 15 + C <= 256, the widest box there is.
+template <int C>
+__global__ void __launch_bounds__(256) shift_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint8_t* __restrict__ dst, int h, int64_t wc, int oxc,
+                                                         int oy, int fx, int fy) {
+  __shared__ __align__(128) uint8_t tile[SH_BOX_H * SH_BOX_W];
+  __shared__ __align__(8) unsigned long long bar;
+  const int j0 = blockIdx.x * SH_TB, y0 = blockIdx.y * SH_TR, f = blockIdx.z;
+  const int start = j0 + oxc, astart = start & ~15, m = start - astart;
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&bar);
+  if (threadIdx.x == 0) {
+    tma::mbar_init(mbar, 1);
+    tma::mbar_fence_init();
+    tma::mbar_expect_tx(mbar, SH_BOX_H * SH_BOX_W);
+    tma::load_3d((unsigned)__cvta_generic_to_shared(tile), &tmap, astart, y0 + oy, f, mbar);
+  }
+  __syncthreads();
+  tma::mbar_wait(mbar, 0);
+  const int lane = threadIdx.x & 31, ly = SH_RPW * (threadIdx.x >> 5);
+  const int j = j0 + 8 * lane, y = y0 + ly;
+  if (lane >= SH_TB / 8 || j >= wc || y >= h) return;
+  uint8_t* out = dst + ((int64_t)f * h + y) * wc + j;
+  const uint8_t* p = tile + ly * SH_BOX_W + 8 * lane + (m & 8);
+  const unsigned wx0 = 32 - fx, wx1 = fx, wy = (unsigned)(32 - fy) | ((unsigned)fy << 8);
+  const bool copy = fx == 0 && fy == 0;   // whole-pixel shift
+  unsigned s[3], het[2], hot[2];
+  shift_hrow<C>(p, m & 7, wx0, wx1, s, het, hot);
+#pragma unroll
+  for (int i = 0; i < SH_RPW; ++i) {
+    if (y + i >= h) break;
+    uint2 o;
+    if (copy) {
+      o = make_uint2(s[0], s[1]);
+      shift_hrow<C>(p + (i + 1) * SH_BOX_W, m & 7, wx0, wx1, s, het, hot);
+    } else {
+      unsigned heb[2], hob[2], r[2];
+      shift_hrow<C>(p + (i + 1) * SH_BOX_W, m & 7, wx0, wx1, s, heb, hob);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        // (H_top*(32-fy) + H_bottom*fy + 512) >> 10 per byte: the two H of a byte side by side, one two-way dot product
+        const unsigned b0 = __dp2a_lo(__byte_perm(het[k], heb[k], 0x5410), wy, 512u) >> 10;
+        const unsigned b1 = __dp2a_lo(__byte_perm(hot[k], hob[k], 0x5410), wy, 512u) >> 10;
+        const unsigned b2 = __dp2a_lo(__byte_perm(het[k], heb[k], 0x7632), wy, 512u) >> 10;
+        const unsigned b3 = __dp2a_lo(__byte_perm(hot[k], hob[k], 0x7632), wy, 512u) >> 10;
+        r[k] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        het[k] = heb[k];
+        hot[k] = hob[k];
+      }
+      o = make_uint2(r[0], r[1]);
+    }
+    *reinterpret_cast<uint2*>(out + i * wc) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// rescale (bicubic up-scale + centre crop)
+// ---------------------------------------------------------------------------------------------------------------
+
+// source position of destination coordinate d: first tap is s - 1; coefficients in double from the double
+// position, rounded to float once (oracle/cvmodel.py:cubic_axis; compiled with -fmad=false: every op rounds)
+__device__ __forceinline__ int cubic_taps(int d, double factor, float (&c)[4]) {
+  const double p = ((double)d + 0.5) / factor - 0.5;
+  const double s = floor(p), x = p - s;
+  const double A = -0.75, x1 = x + 1.0, y = 1.0 - x;
+  const double c0 = ((A * x1 - 5.0 * A) * x1 + 8.0 * A) * x1 - 4.0 * A;
+  const double c1 = ((A + 2.0) * x - (A + 3.0)) * x * x + 1.0;
+  const double c2 = ((A + 2.0) * y - (A + 3.0)) * y * y + 1.0;
+  const double c3 = 1.0 - c0 - c1 - c2;
+  c[0] = (float)c0; c[1] = (float)c1; c[2] = (float)c2; c[3] = (float)c3;
+  return (int)s;
+}
+__device__ __forceinline__ int cubic_pos(int d, double factor) { return (int)floor(((double)d + 0.5) / factor - 0.5); }
+
+constexpr int RS_TH = 32, RS_RUN = 8, RS_SRH = RS_TH + 4;
+template <int C>
+struct RsCfg {
+  static constexpr int JW = C == 3 ? 192 : 256;   // destination bytes of a tile row = threads of the CTA
+  static constexpr int TW = JW / C;               // destination pixels of a tile row
+  static constexpr int SRW = (TW + 4) * C;        // floats of a source tile row
+  static constexpr int SMEM = RS_SRH * (SRW + JW) * 4;
+};
+
+// np.clip(np.rint(v), 0, 255) in the low byte of the result: saturating first is the same (rint is monotone), and the
+// add of 1.5 * 2^23 leaves rint(v) - ties to even - in the low mantissa bits without touching the conversion unit
+__device__ __forceinline__ unsigned round_u8(float v) { return __float_as_uint(fminf(fmaxf(v, 0.f), 255.f) + 12582912.f); }
+__device__ __forceinline__ unsigned pack_low_bytes(unsigned a, unsigned b, unsigned c, unsigned d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
+// A CTA computes a tile of TW x 32 destination pixels: (1) the source pixels under the tile into shared memory as
+// floats, taps outside the image replicated from the border there, (2) the horizontal pass of every source row of
+// the tile - one thread per destination byte column, its four taps and weights in registers -, (3) the vertical pass:
+// a thread owns four adjacent destination bytes and walks down eight rows with the four source rows of its window in
+// registers (up-scaling: the window moves by at most one row per destination row).
+template <int C>
+__global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w,
+                                                                      double factor, int yoff, int xoff, int vec) {
+  using K = RsCfg<C>;
+  extern __shared__ __align__(16) float rs_smem[];
+  float* srcf = rs_smem;                       // [RS_SRH][SRW]
+  float* hor = rs_smem + RS_SRH * K::SRW;      // [RS_SRH][JW]
+  __shared__ int ys[RS_TH];
+  __shared__ float yc[RS_TH][4];
+  const int t = threadIdx.x;
+  const int x0 = blockIdx.x * K::TW, y0 = blockIdx.y * RS_TH;
+  const int64_t fbase = (int64_t)blockIdx.z * h * w * C;
+  const int xlast = min(x0 + K::TW, w) - 1, ylast = min(y0 + RS_TH, h) - 1;
+  const int rx0 = cubic_pos(x0 + xoff, factor) - 1, ry0 = cubic_pos(y0 + yoff, factor) - 1;
+  const int ncols = cubic_pos(xlast + xoff, factor) + 2 - rx0 + 1, nrows = cubic_pos(ylast + yoff, factor) + 2 - ry0 + 1;
+  if (t < RS_TH) {
+    float c[4];
+    ys[t] = cubic_taps(min(y0 + t, h - 1) + yoff, factor, c);
+    yc[t][0] = c[0]; yc[t][1] = c[1]; yc[t][2] = c[2]; yc[t][3] = c[3];
+  }
+  // (1)
+  for (int r = 0; r < nrows; ++r) {
+    const uint8_t* srow = src + fbase + (int64_t)min(max(ry0 + r, 0), h - 1) * w * C;
+    for (int qb = t; qb < ncols * C; qb += K::JW) {
+      const int q = qb / C, ch = qb - q * C;
+      srcf[r * K::SRW + qb] = (float)__ldg(srow + min(max(rx0 + q, 0), w - 1) * C + ch);
+    }
+  }
+  // this thread's column of the horizontal pass
+  const int px = min(x0 + t / C, w - 1), ch = t % C;
+  float cx[4];
+  const int o0 = (cubic_taps(px + xoff, factor, cx) - 1 - rx0) * C + ch;
+  __syncthreads();
+  // (2)
+  for (int r = 0; r < nrows; ++r) {
+    const float* s = srcf + r * K::SRW + o0;
+    float a = s[0] * cx[0];
+    a = a + s[C] * cx[1];
+    a = a + s[2 * C] * cx[2];
+    a = a + s[3 * C] * cx[3];
+    hor[r * K::JW + t] = a;
+  }
+  __syncthreads();
+  // (3)
+  constexpr int G = K::JW / 4;
+  const int g = t % G, run = t / G;
+  const int valid = (xlast + 1 - x0) * C - 4 * g;   // bytes of this group inside the image
+  if (valid <= 0) return;
+  const float4* hor4 = reinterpret_cast<const float4*>(hor) + g;
+  float4 w0, w1, w2, w3;
+  int wtop = -1 << 30;
+  w0 = w1 = w2 = w3 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int i = 0; i < RS_RUN; ++i) {
+    const int ly = run * RS_RUN + i, y = y0 + ly;
+    if (y >= h) break;
+    const int top = ys[ly] - 1 - ry0;
+    if (top != wtop) {
+      if (top == wtop + 1) {
+        w0 = w1; w1 = w2; w2 = w3;
+        w3 = hor4[(top + 3) * G];
+      } else {
+        w0 = hor4[top * G]; w1 = hor4[(top + 1) * G]; w2 = hor4[(top + 2) * G]; w3 = hor4[(top + 3) * G];
+      }
+      wtop = top;
+    }
+    const float c0 = yc[ly][0], c1 = yc[ly][1], c2 = yc[ly][2], c3 = yc[ly][3];
+    float4 v;
+    v.x = w0.x * c0; v.y = w0.y * c0; v.z = w0.z * c0; v.w = w0.w * c0;
+    v.x = v.x + w1.x * c1; v.y = v.y + w1.y * c1; v.z = v.z + w1.z * c1; v.w = v.w + w1.w * c1;
+    v.x = v.x + w2.x * c2; v.y = v.y + w2.y * c2; v.z = v.z + w2.z * c2; v.w = v.w + w2.w * c2;
+    v.x = v.x + w3.x * c3; v.y = v.y + w3.y * c3; v.z = v.z + w3.z * c3; v.w = v.w + w3.w * c3;
+    const unsigned b0 = round_u8(v.x), b1 = round_u8(v.y), b2 = round_u8(v.z), b3 = round_u8(v.w);
+    uint8_t* o = dst + fbase + ((int64_t)y * w + x0) * C + 4 * g;
+    if (vec && valid >= 4) {
+      *reinterpret_cast<unsigned*>(o) = pack_low_bytes(b0, b1, b2, b3);
+    } else {
+      o[0] = (uint8_t)b0;
+      if (valid > 1) o[1] = (uint8_t)b1;
+      if (valid > 2) o[2] = (uint8_t)b2;
+      if (valid > 3) o[3] = (uint8_t)b3;
+    }
+  }
+}
+
+template <int C>
+int launch_rescale(const uint8_t* src, uint8_t* dst, int n, int h, int w, double factor, int yoff, int xoff, cudaStream_t stream) {
+  using K = RsCfg<C>;
+  auto kernel = rescale_cubic_kernel<C>;
+  static bool configured = false;
+  if (!configured) {
+    const int e = record_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+    if (e) return e;
+    configured = true;
+  }
+  const int vec = (((int64_t)w * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) ? 1 : 0;
+  dim3 grid((w + K::TW - 1) / K::TW, (h + RS_TH - 1) / RS_TH, n);
+  kernel<<<grid, K::JW, K::SMEM, stream>>>(src, dst, h, w, factor, yoff, xoff, vec);
+  note_launch();
+  return record_cuda(cudaGetLastError());
+}
+
+inline int rescaled_size(int n, double factor) { return (int)std::nearbyint((double)n * factor); }   // cv2: saturate_cast<int>(n * fx)
+
+}  // namespace
+}  // namespace vu
+
+using namespace vu;
+
+extern "C" int vu_shift_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int channels, float dx, float dy, vu_stream_t stream) {
+  VU_REQUIRE(src && dst && n >= 0 && h > 0 && w > 0 && h <= 32767 && w <= 32767);
+  VU_REQUIRE(std::fabs((double)dx) < 1048576.0 && std::fabs((double)dy) < 1048576.0);   // also rejects NaN
+  if (channels != 1 && channels != 3) return VU_ERR_UNSUPPORTED;
+  if (n == 0) return VU_OK;
+  const double b1 = -(double)dx, b2 = -(double)dy;
+  const long long X0 = (long long)std::nearbyint(b1 * 1024.0) + 16;
+  const int ox = (int)(X0 >> 10), fx = (int)((X0 >> 5) & 31);
+  // the tile kernel needs one row offset and one row fraction for the whole image (true unless dy is so small
+  // against the row index that y - dy rounds differently from row to row) and rows the TMA unit can address
+  int oy = 0, fy = 0;
+  shift_row(0, b2, oy, fy);
+  bool uniform = true;
+  for (int y = 1; y < h && uniform; ++y) {
+    int sy, f;
+    shift_row(y, b2, sy, f);
+    uniform = (sy - y == oy) && f == fy;
+  }
+  const int64_t wc = (int64_t)w * channels;
+  tma::EncodeTiledFn enc = tma::encode_tiled_fn();
+  const bool aligned = wc % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  static const bool force_generic = std::getenv("VU_SHIFT_GENERIC") != nullptr;   // test hook
+  if (!force_generic && uniform && aligned && enc && std::abs(oy) < 32767 && std::abs(ox) < 32767) {
+    CUtensorMap tmap;
+    const cuuint64_t dims[3] = {(cuuint64_t)wc, (cuuint64_t)h, (cuuint64_t)n};
+    const cuuint64_t strides[2] = {(cuuint64_t)wc, (cuuint64_t)(wc * h)};
+    const cuuint32_t box[3] = {SH_BOX_W, SH_BOX_H, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t*>(src), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      dim3 grid((unsigned)((wc + SH_TB - 1) / SH_TB), (h + SH_TR - 1) / SH_TR, n);
+      if (grid.y <= 65535 && grid.z <= 65535) {
+        if (channels == 1) shift_tile_kernel<1><<<grid, 256, 0, S(stream)>>>(tmap, dst, h, wc, ox * channels, oy, fx, fy);
+        else shift_tile_kernel<3><<<grid, 256, 0, S(stream)>>>(tmap, dst, h, wc, ox * channels, oy, fx, fy);
+        VU_RETURN_LAUNCH();
+      }
+    }
+  }
+  const int grid = grid_for((int64_t)n * h * wc, 256, 8);
+  if (channels == 1) shift_generic_kernel<1><<<grid, 256, 0, S(stream)>>>(src, dst, n, h, w, ox, fx, b2);
+  else shift_generic_kernel<3><<<grid, 256, 0, S(stream)>>>(src, dst, n, h, w, ox, fx, b2);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_rescale_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int channels, double factor, vu_stream_t stream) {
+  VU_REQUIRE(src && dst && n >= 0 && h > 0 && w > 0);
+  VU_REQUIRE(factor >= 1.0 && factor <= 16.0);
+  if (channels != 1 && channels != 3) return VU_ERR_UNSUPPORTED;
+  if (n == 0) return VU_OK;
+  if (n > 65535 || (h + RS_TH - 1) / RS_TH > 65535) return VU_ERR_UNSUPPORTED;
+  const int dh = rescaled_size(h, factor), dw = rescaled_size(w, factor);
+  const int yoff = (dh - h) / 2, xoff = (dw - w) / 2;   // int((dh - h) / 2) of imgprocess.py:49-50
+  if (channels == 1) return launch_rescale<1>(src, dst, n, h, w, factor, yoff, xoff, S(stream));
+  return launch_rescale<3>(src, dst, n, h, w, factor, yoff, xoff, S(stream));
+}

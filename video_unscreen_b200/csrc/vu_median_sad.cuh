@@ -41,6 +41,7 @@
 #include <stdint.h>
 
 #include <type_traits>
+#include "vu_tma.cuh"
 
 namespace vu {
 namespace msad {
@@ -380,30 +381,10 @@ __global__ void __launch_bounds__(128, CTAS) median_sad_kernel(const uint8_t* __
 // delta = -(number of pads).  The warps are only loosely coupled: a warp waits for the tile on the mbarrier, moves its
 // segment to registers and transposes, bumps a counter and goes searching; the warp that bumps it last knows the
 // buffer is free and launches the fetch of the next tile, which then lands while everybody searches.
-__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned mbar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE_%=;\n"
-      "bra WAIT_%=;\n"
-      "DONE_%=:\n"
-      "}\n" ::"r"(mbar),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(unsigned dst, const void* tmap, int c0, int c1, unsigned mbar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(tmap),
-               "r"(c0), "r"(c1), "r"(mbar)
-               : "memory");
-}
+using tma::mbar_expect_tx;
+using tma::mbar_init;
+using tma::mbar_wait;
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const void* tmap, int c0, int c1, unsigned mbar) { tma::load_2d(dst, tmap, c0, c1, mbar); }
 
 // GQ: groups g < GQ are below Q = ceil(ceil(n/SPLIT)/4) for every n the variant is dispatched for
 template <int SPLIT, int G, int GQ, int SS, int WARPS, int CTAS>

@@ -171,22 +171,8 @@ int launch_median_sad(const uint8_t* frames, int n, int64_t m, int64_t nseg, uin
 }
 
 // TMA tile kernels: the clip as a 2-D uint8 tensor [n][m], boxes of {TILE bytes, 4G frames}
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      (void)cudaGetLastError();
-  }
-  return fn;
-}
+using tma::encode_tiled_fn;
+using tma::EncodeTiledFn;
 
 // pitch = bytes between consecutive frames of the (possibly subsampled) clip
 template <int SPLIT, int G, int GQ, int SS, int TMA_WARPS, int TMA_CTAS>

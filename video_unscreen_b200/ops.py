@@ -261,6 +261,35 @@ def resize_nearest_image(x, dh, dw):
     return _resize(lib().vu_resize_nearest_u8, x, dh, dw, 3)
 
 
+# ---- geometric pre-steps of the replacement path ------------------------------
+
+def _geom_shape(x, channels):
+    """(n, h, w) of an image [H,W,3] / clip [N,H,W,3] (channels 3) or a mask [H,W] / [N,H,W] (channels 1)."""
+    if channels == 3:
+        x = _img(x)
+        return x, (1 if x.ndim == 3 else x.shape[0]), x.shape[-3], x.shape[-2]
+    if channels != 1:
+        raise ValueError("channels must be 1 or 3")
+    x = _mask(x)
+    return x, (1 if x.ndim == 2 else x.shape[0]), x.shape[-2], x.shape[-1]
+
+
+def shift(x, dx, dy, channels=3):
+    """shift_fg (imgprocess.py:55-64): cv2.warpAffine translation by (dx, dy), zero border."""
+    x, n, h, w = _geom_shape(_dev(x), channels)
+    out = torch.empty_like(x)
+    check(lib().vu_shift_u8(_p(x), _p(out), n, h, w, channels, float(dx), float(dy), _stream()))
+    return out
+
+
+def rescale_cubic(x, factor, channels=3):
+    """rescale_fg (imgprocess.py:40-52): bicubic up-scale by ``factor`` and centre crop to the input size."""
+    x, n, h, w = _geom_shape(_dev(x), channels)
+    out = torch.empty_like(x)
+    check(lib().vu_rescale_cubic_u8(_p(x), _p(out), n, h, w, channels, float(factor), _stream()))
+    return out
+
+
 # ---- reductions / mask algebra ----------------------------------------------
 
 def _items(x, item_ndim):

@@ -1,8 +1,9 @@
-"""size math and plain resize (reference: unscreen/utils/imgprocess.py)."""
+"""size math, plain resize and the geometric pre-steps of the replacement path
+(reference: unscreen/utils/imgprocess.py)."""
 from ... import ops
 from ..._io import back, to_dev
 
-__all__ = ["get_target_size", "adaptive_resize"]
+__all__ = ["get_target_size", "adaptive_resize", "rescale_fg", "shift_fg"]
 
 
 def get_target_size(h, w, target_long_side, division=1):
@@ -26,3 +27,25 @@ def adaptive_resize(img, img_target):
     th, tw = img_target.shape[0], img_target.shape[1]
     out = ops.resize_linear_image(t, th, tw) if t.ndim == 3 else ops.resize_linear_mask(t, th, tw)
     return back(out, as_np)
+
+
+def _channels(t):
+    """the reference passes HWC images (fg, 3-channel JPEG masks) and HW maps through the same functions."""
+    if t.ndim == 2:
+        return 1
+    if t.ndim == 3 and t.shape[2] == 3:
+        return 3
+    raise ValueError(f"expected an HW or HWx3 uint8 array, got {tuple(t.shape)}")
+
+
+def rescale_fg(img, scale_factor=1.1):
+    """reference unscreen/utils/imgprocess.py:40-52: bicubic up-scale about the centre, cropped to the input size.
+    Parity with cv2's IPP cubic: equal except for < 1e-5 of the values, off by one."""
+    t, as_np = to_dev(img)
+    return back(ops.rescale_cubic(t, scale_factor, _channels(t)), as_np)
+
+
+def shift_fg(img, dx=0, dy=0):
+    """reference unscreen/utils/imgprocess.py:55-64: cv2.warpAffine translation, zero border (bit-exact)."""
+    t, as_np = to_dev(img)
+    return back(ops.shift(t, dx, dy, _channels(t)), as_np)
