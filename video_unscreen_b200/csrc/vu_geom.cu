@@ -162,125 +162,124 @@ __device__ __forceinline__ int cubic_taps(int d, double factor, float (&c)[4]) {
 }
 __device__ __forceinline__ int cubic_pos(int d, double factor) { return (int)floor(((double)d + 0.5) / factor - 0.5); }
 
-constexpr int RS_TH = 32, RS_RUN = 8, RS_SRH = RS_TH + 4;
+constexpr int RS_TH = 32;            // destination rows between two refills of the source tile
+constexpr int RS_SRH = RS_TH + 4;    // source rows under them (factor >= 1), at most
+constexpr int RS_STRIP = 128;        // destination rows a CTA walks down
 template <int C>
 struct RsCfg {
-  static constexpr int JW = C == 3 ? 192 : 256;   // destination bytes of a tile row = threads of the CTA
-  static constexpr int TW = JW / C;               // destination pixels of a tile row
-  static constexpr int SRW = (TW + 4) * C;        // floats of a source tile row
-  static constexpr int SMEM = RS_SRH * (SRW + JW) * 4;
+  static constexpr int JW = C == 3 ? 192 : 256;            // destination bytes of a strip row = threads of the CTA
+  static constexpr int TW = JW / C;                        // destination pixels of a strip row
+  static constexpr int SRW = ((TW + 4) * C + 6 + 3) / 4 * 4;   // floats of a source tile row: (TW + 4) pixels, widened to whole words
+  static constexpr int LW = C == 3 ? 64 : 128;             // loader threads per source row (>= SRW / 4)
+  static_assert(SRW / 4 <= LW && JW % LW == 0, "loader layout");
 };
 
 // np.clip(np.rint(v), 0, 255) in the low byte of the result: saturating first is the same (rint is monotone), and the
 // add of 1.5 * 2^23 leaves rint(v) - ties to even - in the low mantissa bits without touching the conversion unit
 __device__ __forceinline__ unsigned round_u8(float v) { return __float_as_uint(fminf(fmaxf(v, 0.f), 255.f) + 12582912.f); }
-__device__ __forceinline__ unsigned pack_low_bytes(unsigned a, unsigned b, unsigned c, unsigned d) {
-  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
-}
 
-// A CTA computes a tile of TW x 32 destination pixels: (1) the source pixels under the tile into shared memory as
-// floats, taps outside the image replicated from the border there, (2) the horizontal pass of every source row of
-// the tile - one thread per destination byte column, its four taps and weights in registers -, (3) the vertical pass:
-// a thread owns four adjacent destination bytes and walks down eight rows with the four source rows of its window in
-// registers (up-scaling: the window moves by at most one row per destination row).
+// A CTA owns a strip of TW destination pixels and walks down RS_STRIP destination rows, one thread per destination
+// byte column.  The four horizontal taps of the column (replicated at the image border) and their weights live in
+// registers for the whole walk; the vertical taps of every row of the strip are tabulated once.  Every 32 destination
+// rows the source rows under them are staged in shared memory as floats (aligned 32-bit loads, each byte converted
+// once).  A thread then marches: the horizontal pass of a source row is computed when the vertical window reaches it
+// and kept in a four-deep register window (up-scaling: the window moves by at most one row per destination row), the
+// vertical pass runs from those registers, and the byte goes straight out - a warp stores 32 consecutive bytes.
 template <int C>
 __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int h, int w,
-                                                                      double factor, int yoff, int xoff, int vec) {
+                                                                      double factor, int yoff, int xoff, int words) {
   using K = RsCfg<C>;
-  extern __shared__ __align__(16) float rs_smem[];
-  float* srcf = rs_smem;                       // [RS_SRH][SRW]
-  float* hor = rs_smem + RS_SRH * K::SRW;      // [RS_SRH][JW]
-  __shared__ int ys[RS_TH];
-  __shared__ float yc[RS_TH][4];
+  __shared__ __align__(16) float srcf[RS_SRH * K::SRW];
+  __shared__ int ys[RS_STRIP];
+  __shared__ __align__(16) float yc[RS_STRIP][4];
   const int t = threadIdx.x;
-  const int x0 = blockIdx.x * K::TW, y0 = blockIdx.y * RS_TH;
+  const int x0 = blockIdx.x * K::TW, ystrip = blockIdx.y * RS_STRIP;
+  const int rows = min(RS_STRIP, h - ystrip);
   const int64_t fbase = (int64_t)blockIdx.z * h * w * C;
-  const int xlast = min(x0 + K::TW, w) - 1, ylast = min(y0 + RS_TH, h) - 1;
-  const int rx0 = cubic_pos(x0 + xoff, factor) - 1, ry0 = cubic_pos(y0 + yoff, factor) - 1;
-  const int ncols = cubic_pos(xlast + xoff, factor) + 2 - rx0 + 1, nrows = cubic_pos(ylast + yoff, factor) + 2 - ry0 + 1;
-  if (t < RS_TH) {
+  for (int ly = t; ly < rows; ly += K::JW) {
     float c[4];
-    ys[t] = cubic_taps(min(y0 + t, h - 1) + yoff, factor, c);
-    yc[t][0] = c[0]; yc[t][1] = c[1]; yc[t][2] = c[2]; yc[t][3] = c[3];
+    ys[ly] = cubic_taps(ystrip + ly + yoff, factor, c);
+    *reinterpret_cast<float4*>(yc[ly]) = make_float4(c[0], c[1], c[2], c[3]);
   }
-  // (1)
-  for (int r = 0; r < nrows; ++r) {
-    const uint8_t* srow = src + fbase + (int64_t)min(max(ry0 + r, 0), h - 1) * w * C;
-    for (int qb = t; qb < ncols * C; qb += K::JW) {
-      const int q = qb / C, ch = qb - q * C;
-      srcf[r * K::SRW + qb] = (float)__ldg(srow + min(max(rx0 + q, 0), w - 1) * C + ch);
-    }
-  }
-  // this thread's column of the horizontal pass
+  // source bytes of a row this strip reads: pixels clamp(rx0) .. clamp(rxl), from the 4-byte boundary below
+  const int xlast = min(x0 + K::TW, w) - 1;
+  const int rx0 = min(max(cubic_pos(x0 + xoff, factor) - 1, 0), w - 1), rxl = min(max(cubic_pos(xlast + xoff, factor) + 2, 0), w - 1);
+  const int abase = words ? (rx0 * C) & ~3 : rx0 * C;
+  const int nbytes = rxl * C + C - abase;            // <= SRW
+  // this thread's column
+  const bool live = x0 + t / C < w;
   const int px = min(x0 + t / C, w - 1), ch = t % C;
   float cx[4];
-  const int o0 = (cubic_taps(px + xoff, factor, cx) - 1 - rx0) * C + ch;
-  __syncthreads();
-  // (2)
-  for (int r = 0; r < nrows; ++r) {
-    const float* s = srcf + r * K::SRW + o0;
-    float a = s[0] * cx[0];
-    a = a + s[C] * cx[1];
-    a = a + s[2 * C] * cx[2];
-    a = a + s[3 * C] * cx[3];
-    hor[r * K::JW + t] = a;
+  int o[4];
+  {
+    const int sx = cubic_taps(px + xoff, factor, cx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o[k] = min(max(sx - 1 + k, 0), w - 1) * C + ch - abase;
   }
+  uint8_t* out = dst + fbase + ((int64_t)ystrip * w + x0) * C + t;
+  const int lk = t % K::LW, lr = t / K::LW;
   __syncthreads();
-  // (3)
-  constexpr int G = K::JW / 4;
-  const int g = t % G, run = t / G;
-  const int valid = (xlast + 1 - x0) * C - 4 * g;   // bytes of this group inside the image
-  if (valid <= 0) return;
-  const float4* hor4 = reinterpret_cast<const float4*>(hor) + g;
-  float4 w0, w1, w2, w3;
-  int wtop = -1 << 30;
-  w0 = w1 = w2 = w3 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 1
-  for (int i = 0; i < RS_RUN; ++i) {
-    const int ly = run * RS_RUN + i, y = y0 + ly;
-    if (y >= h) break;
-    const int top = ys[ly] - 1 - ry0;
-    if (top != wtop) {
-      if (top == wtop + 1) {
-        w0 = w1; w1 = w2; w2 = w3;
-        w3 = hor4[(top + 3) * G];
-      } else {
-        w0 = hor4[top * G]; w1 = hor4[(top + 1) * G]; w2 = hor4[(top + 2) * G]; w3 = hor4[(top + 3) * G];
+  for (int l0 = 0; l0 < rows; l0 += RS_TH) {
+    const int l1 = min(l0 + RS_TH, rows);
+    const int ry0 = ys[l0] - 1, nrows = ys[l1 - 1] + 2 - ry0 + 1;
+    // stage the source rows ry0 .. ry0 + nrows - 1 (replicated outside the image)
+    if (words) {
+      if (4 * lk < nbytes) {
+        for (int r = lr; r < nrows; r += K::JW / K::LW) {
+          const uint8_t* srow = src + fbase + (int64_t)min(max(ry0 + r, 0), h - 1) * w * C + abase;
+          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(srow) + lk);
+          *reinterpret_cast<float4*>(srcf + r * K::SRW + 4 * lk) =
+              make_float4(u8_to_f32(v & 255u), u8_to_f32((v >> 8) & 255u), u8_to_f32((v >> 16) & 255u), u8_to_f32(v >> 24));
+        }
       }
-      wtop = top;
-    }
-    const float c0 = yc[ly][0], c1 = yc[ly][1], c2 = yc[ly][2], c3 = yc[ly][3];
-    float4 v;
-    v.x = w0.x * c0; v.y = w0.y * c0; v.z = w0.z * c0; v.w = w0.w * c0;
-    v.x = v.x + w1.x * c1; v.y = v.y + w1.y * c1; v.z = v.z + w1.z * c1; v.w = v.w + w1.w * c1;
-    v.x = v.x + w2.x * c2; v.y = v.y + w2.y * c2; v.z = v.z + w2.z * c2; v.w = v.w + w2.w * c2;
-    v.x = v.x + w3.x * c3; v.y = v.y + w3.y * c3; v.z = v.z + w3.z * c3; v.w = v.w + w3.w * c3;
-    const unsigned b0 = round_u8(v.x), b1 = round_u8(v.y), b2 = round_u8(v.z), b3 = round_u8(v.w);
-    uint8_t* o = dst + fbase + ((int64_t)y * w + x0) * C + 4 * g;
-    if (vec && valid >= 4) {
-      *reinterpret_cast<unsigned*>(o) = pack_low_bytes(b0, b1, b2, b3);
     } else {
-      o[0] = (uint8_t)b0;
-      if (valid > 1) o[1] = (uint8_t)b1;
-      if (valid > 2) o[2] = (uint8_t)b2;
-      if (valid > 3) o[3] = (uint8_t)b3;
+      for (int r = 0; r < nrows; ++r) {
+        const uint8_t* srow = src + fbase + (int64_t)min(max(ry0 + r, 0), h - 1) * w * C + abase;
+        for (int q = t; q < nbytes; q += K::JW) srcf[r * K::SRW + q] = u8_to_f32(__ldg(srow + q));
+      }
     }
+    __syncthreads();
+    if (live) {
+      float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
+      int wtop = -1 << 30;
+      auto hrow = [&](int r) -> float {
+        const float* s = srcf + r * K::SRW;
+        float a = s[o[0]] * cx[0];
+        a = a + s[o[1]] * cx[1];
+        a = a + s[o[2]] * cx[2];
+        a = a + s[o[3]] * cx[3];
+        return a;
+      };
+#pragma unroll 2
+      for (int ly = l0; ly < l1; ++ly) {
+        const int top = ys[ly] - 1 - ry0;
+        if (top != wtop) {
+          if (top == wtop + 1) {
+            h0 = h1; h1 = h2; h2 = h3;
+            h3 = hrow(top + 3);
+          } else {
+            h0 = hrow(top); h1 = hrow(top + 1); h2 = hrow(top + 2); h3 = hrow(top + 3);
+          }
+          wtop = top;
+        }
+        const float4 c = *reinterpret_cast<const float4*>(yc[ly]);
+        float v = h0 * c.x;
+        v = v + h1 * c.y;
+        v = v + h2 * c.z;
+        v = v + h3 * c.w;
+        out[(int64_t)ly * w * C] = (uint8_t)round_u8(v);
+      }
+    }
+    __syncthreads();
   }
 }
 
 template <int C>
 int launch_rescale(const uint8_t* src, uint8_t* dst, int n, int h, int w, double factor, int yoff, int xoff, cudaStream_t stream) {
   using K = RsCfg<C>;
-  auto kernel = rescale_cubic_kernel<C>;
-  static bool configured = false;
-  if (!configured) {
-    const int e = record_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-    if (e) return e;
-    configured = true;
-  }
-  const int vec = (((int64_t)w * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) ? 1 : 0;
-  dim3 grid((w + K::TW - 1) / K::TW, (h + RS_TH - 1) / RS_TH, n);
-  kernel<<<grid, K::JW, K::SMEM, stream>>>(src, dst, h, w, factor, yoff, xoff, vec);
+  const int words = (((int64_t)w * C) % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) ? 1 : 0;
+  dim3 grid((w + K::TW - 1) / K::TW, (h + RS_STRIP - 1) / RS_STRIP, n);
+  rescale_cubic_kernel<C><<<grid, K::JW, 0, stream>>>(src, dst, h, w, factor, yoff, xoff, words);
   note_launch();
   return record_cuda(cudaGetLastError());
 }
@@ -341,7 +340,7 @@ extern "C" int vu_rescale_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int 
   VU_REQUIRE(factor >= 1.0 && factor <= 16.0);
   if (channels != 1 && channels != 3) return VU_ERR_UNSUPPORTED;
   if (n == 0) return VU_OK;
-  if (n > 65535 || (h + RS_TH - 1) / RS_TH > 65535) return VU_ERR_UNSUPPORTED;
+  if (n > 65535 || (h + RS_STRIP - 1) / RS_STRIP > 65535) return VU_ERR_UNSUPPORTED;
   const int dh = rescaled_size(h, factor), dw = rescaled_size(w, factor);
   const int yoff = (dh - h) / 2, xoff = (dw - w) / 2;   // int((dh - h) / 2) of imgprocess.py:49-50
   if (channels == 1) return launch_rescale<1>(src, dst, n, h, w, factor, yoff, xoff, S(stream));
