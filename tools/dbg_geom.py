@@ -4,7 +4,7 @@ from video_unscreen_b200 import ops
 from oracle import cvmodel as M
 what, shape, dx, dy = sys.argv[1], eval(sys.argv[2]), float(sys.argv[3]), float(sys.argv[4])
 rng = np.random.default_rng(0)
-clip = rng.integers(0, 256, (2,) + shape, dtype=np.uint8)
+clip = rng.integers(0, 256, (int(os.environ.get("DBG_N", "2")),) + shape, dtype=np.uint8)
 ch = 3 if len(shape) == 3 else 1
 if what == "shift":
     got = ops.shift(torch.from_numpy(clip).cuda(), dx, dy, ch); torch.cuda.synchronize()

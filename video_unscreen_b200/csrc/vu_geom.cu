@@ -216,7 +216,9 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
 #pragma unroll
     for (int k = 0; k < 4; ++k) o[k] = min(max(sx - 1 + k, 0), w - 1) * C + ch - abase;
   }
-  uint8_t* out = dst + fbase + ((int64_t)ystrip * w + x0) * C + t;
+  const int64_t pitch = (int64_t)w * C;
+  uint8_t* orow = dst + fbase + ((int64_t)ystrip * w + x0) * C + t;
+  const float *s0 = srcf + o[0], *s1 = srcf + o[1], *s2 = srcf + o[2], *s3 = srcf + o[3];
   const int lk = t % K::LW, lr = t / K::LW;
   __syncthreads();
   for (int l0 = 0; l0 < rows; l0 += RS_TH) {
@@ -240,34 +242,28 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
     }
     __syncthreads();
     if (live) {
+      // one source row enters the window per step (r is uniform: the tap addresses are pointer + constant); the
+      // destination rows whose window ends at that row leave with it
       float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
-      int wtop = -1 << 30;
-      auto hrow = [&](int r) -> float {
-        const float* s = srcf + r * K::SRW;
-        float a = s[o[0]] * cx[0];
-        a = a + s[o[1]] * cx[1];
-        a = a + s[o[2]] * cx[2];
-        a = a + s[o[3]] * cx[3];
-        return a;
-      };
-#pragma unroll 2
-      for (int ly = l0; ly < l1; ++ly) {
-        const int top = ys[ly] - 1 - ry0;
-        if (top != wtop) {
-          if (top == wtop + 1) {
-            h0 = h1; h1 = h2; h2 = h3;
-            h3 = hrow(top + 3);
-          } else {
-            h0 = hrow(top); h1 = hrow(top + 1); h2 = hrow(top + 2); h3 = hrow(top + 3);
-          }
-          wtop = top;
+      int ly = l0, due = ys[l0] + 2 - ry0;
+#pragma unroll 4
+      for (int r = 0; r < nrows; ++r) {
+        h0 = h1; h1 = h2; h2 = h3;
+        h3 = s0[r * K::SRW] * cx[0];
+        h3 = h3 + s1[r * K::SRW] * cx[1];
+        h3 = h3 + s2[r * K::SRW] * cx[2];
+        h3 = h3 + s3[r * K::SRW] * cx[3];
+        while (due == r) {
+          const float4 c = *reinterpret_cast<const float4*>(yc[ly]);
+          float v = h0 * c.x;
+          v = v + h1 * c.y;
+          v = v + h2 * c.z;
+          v = v + h3 * c.w;
+          *orow = (uint8_t)round_u8(v);
+          orow += pitch;
+          ++ly;
+          due = ly < l1 ? ys[ly] + 2 - ry0 : -1;
         }
-        const float4 c = *reinterpret_cast<const float4*>(yc[ly]);
-        float v = h0 * c.x;
-        v = v + h1 * c.y;
-        v = v + h2 * c.z;
-        v = v + h3 * c.w;
-        out[(int64_t)ly * w * C] = (uint8_t)round_u8(v);
       }
     }
     __syncthreads();
