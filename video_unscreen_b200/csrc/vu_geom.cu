@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
   using K = RsCfg<C>;
   __shared__ __align__(16) float srcf[RS_SRH * K::SRW];
   __shared__ int ys[RS_STRIP];
-  __shared__ __align__(16) float yc[RS_STRIP][4];
+  __shared__ __align__(16) float ytab[RS_STRIP][8];   // per destination row: 4 vertical weights, then `due` of the NEXT row (-1: none)
   const int t = threadIdx.x;
   const int x0 = blockIdx.x * K::TW, ystrip = blockIdx.y * RS_STRIP;
   const int rows = min(RS_STRIP, h - ystrip);
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
   for (int ly = t; ly < rows; ly += K::JW) {
     float c[4];
     ys[ly] = cubic_taps(ystrip + ly + yoff, factor, c);
-    *reinterpret_cast<float4*>(yc[ly]) = make_float4(c[0], c[1], c[2], c[3]);
+    *reinterpret_cast<float4*>(ytab[ly]) = make_float4(c[0], c[1], c[2], c[3]);
   }
   // source bytes of a row this strip reads: pixels clamp(rx0) .. clamp(rxl), from the 4-byte boundary below
   const int xlast = min(x0 + K::TW, w) - 1;
@@ -220,7 +220,14 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
   uint8_t* orow = dst + fbase + ((int64_t)ystrip * w + x0) * C + t;
   const float *s0 = srcf + o[0], *s1 = srcf + o[1], *s2 = srcf + o[2], *s3 = srcf + o[3];
   const int lk = t % K::LW, lr = t / K::LW;
+  const uint8_t* lbase = src + fbase + abase + 4 * lk;
   __syncthreads();
+  // a destination row is due when the source row that completes its window (first source row of its 32-row group
+  // = row 0) has entered
+  for (int ly = t; ly < rows; ly += K::JW) {
+    const int nx = ly + 1;
+    ytab[ly][4] = __int_as_float((nx < rows && (nx % RS_TH) != 0) ? ys[nx] + 2 - (ys[ly - ly % RS_TH] - 1) : -1);
+  }
   for (int l0 = 0; l0 < rows; l0 += RS_TH) {
     const int l1 = min(l0 + RS_TH, rows);
     const int ry0 = ys[l0] - 1, nrows = ys[l1 - 1] + 2 - ry0 + 1;
@@ -228,10 +235,13 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
     if (words) {
       if (4 * lk < nbytes) {
         for (int r = lr; r < nrows; r += K::JW / K::LW) {
-          const uint8_t* srow = src + fbase + (int64_t)min(max(ry0 + r, 0), h - 1) * w * C + abase;
-          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(srow) + lk);
-          *reinterpret_cast<float4*>(srcf + r * K::SRW + 4 * lk) =
-              make_float4(u8_to_f32(v & 255u), u8_to_f32((v >> 8) & 255u), u8_to_f32((v >> 16) & 255u), u8_to_f32(v >> 24));
+          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(lbase + (int64_t)min(max(ry0 + r, 0), h - 1) * pitch));
+          float4 f;   // byte k under the exponent of 2^23, minus 2^23
+          f.x = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7440)) - 8388608.f;
+          f.y = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7441)) - 8388608.f;
+          f.z = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7442)) - 8388608.f;
+          f.w = __uint_as_float(__byte_perm(v, 0x4B000000u, 0x7443)) - 8388608.f;
+          *reinterpret_cast<float4*>(srcf + r * K::SRW + 4 * lk) = f;
         }
       }
     } else {
@@ -245,7 +255,8 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
       // one source row enters the window per step (r is uniform: the tap addresses are pointer + constant); the
       // destination rows whose window ends at that row leave with it
       float h0 = 0.f, h1 = 0.f, h2 = 0.f, h3 = 0.f;
-      int ly = l0, due = ys[l0] + 2 - ry0;
+      int due = 3;                       // the first row of the group: its window is source rows 0..3
+      const float* yp = ytab[l0];
 #pragma unroll 4
       for (int r = 0; r < nrows; ++r) {
         h0 = h1; h1 = h2; h2 = h3;
@@ -254,15 +265,15 @@ __global__ void __launch_bounds__(RsCfg<C>::JW) rescale_cubic_kernel(const uint8
         h3 = h3 + s2[r * K::SRW] * cx[2];
         h3 = h3 + s3[r * K::SRW] * cx[3];
         while (due == r) {
-          const float4 c = *reinterpret_cast<const float4*>(yc[ly]);
+          const float4 c = *reinterpret_cast<const float4*>(yp);
           float v = h0 * c.x;
           v = v + h1 * c.y;
           v = v + h2 * c.z;
           v = v + h3 * c.w;
           *orow = (uint8_t)round_u8(v);
           orow += pitch;
-          ++ly;
-          due = ly < l1 ? ys[ly] + 2 - ry0 : -1;
+          due = __float_as_int(yp[4]);
+          yp += 8;
         }
       }
     }
