@@ -228,6 +228,38 @@ def main():
     tmp["median_rnd"] = np.median(rnd, axis=0).astype(np.uint8)
     np.savez_compressed(os.path.join(HERE, "temporal.npz"), **tmp)
 
+    geometry(U)
+    write_manifest()
+
+
+def geometry(U):
+    """replacement-path geometry: shift_fg / rescale_fg of the reference and the frame of
+    tools/replace/replace.py:69-76 restated with them.  `python make_golden.py geometry` regenerates this file alone."""
+    rng = np.random.default_rng(11)
+    geo = {}
+    fg = rng.integers(0, 256, (54, 96, 3), dtype=np.uint8)
+    m3 = np.repeat(rng.integers(0, 256, (54, 96, 1), dtype=np.uint8), 3, axis=2)
+    bg = rng.integers(0, 256, (54, 96, 3), dtype=np.uint8)
+    geo["fg"], geo["mask3"], geo["bg"] = fg, m3, bg
+    shifts = np.array([[3, -2], [0.5, 0.5], [-6.37, 2.81], [0, 0], [40.25, -30.75]], np.float64)
+    geo["shifts"] = shifts
+    for i, (dx, dy) in enumerate(shifts):
+        geo[f"shift_fg_{i}"] = U.shift_fg(fg, dx=dx, dy=dy)
+        geo[f"shift_mask_{i}"] = U.shift_fg(m3[..., 0], dx=dx, dy=dy)
+    for tag, sc in (("12", 1.2), ("11", 1.1)):
+        geo[f"rescale_fg_{tag}"] = U.rescale_fg(fg, scale_factor=sc)
+        geo[f"rescale_mask_{tag}"] = U.rescale_fg(m3[..., 0], scale_factor=sc)
+    f = U.rescale_fg(U.shift_fg(fg, dx=3, dy=-2), scale_factor=1.2)
+    m = U.rescale_fg(U.shift_fg(m3, dx=3, dy=-2), scale_factor=1.2)
+    nb = m.astype(np.float64) / 255
+    geo["replace_frame"] = (f.astype(np.float64) * nb + bg.astype(np.float64) * (1 - nb)).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "geometry.npz"), **geo)
+
+
+def write_manifest():
+    import cv2
+    import sklearn
+    import torch
     manifest = {
         "generator": "tests/golden/make_golden.py",
         "reference": "AnyiRao/video_unscreen @ /root/reference (unmodified, import shim)",
@@ -242,4 +274,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["geometry"]:
+        geometry(load_reference()[0])
+        write_manifest()
+    else:
+        main()

@@ -516,3 +516,21 @@ def test_replace_with_geometry(vu):
         want = np.stack([R.replace_frame(fg[i], a3[i], bg, dx, dy, sc) for i in range(n)])
         assert np.array_equal(host(C.replace_clip(dev(fg), dev(a3), dev(bg), dx, dy, sc)), want)
         assert np.array_equal(host(C.replace_clip(dev(fg), dev(a), dev(bg), dx, dy, sc)), want)
+
+
+def test_geometry_golden(vu, golden):
+    """shift_fg / rescale_fg / the replace.py:69-76 frame against outputs of the unmodified reference (tests/golden/
+    geometry.npz): shift bit-exact; rescale within the tie tolerance documented in oracle/cvmodel.py."""
+    from video_unscreen_b200 import clip as C
+    g = golden("geometry")
+    fg, m3, bg = g["fg"], g["mask3"], g["bg"]
+    for i, (dx, dy) in enumerate(g["shifts"]):
+        assert np.array_equal(vu.U.shift_fg(fg, dx=dx, dy=dy), g[f"shift_fg_{i}"]), (dx, dy)
+        assert np.array_equal(vu.U.shift_fg(m3[..., 0], dx=dx, dy=dy), g[f"shift_mask_{i}"]), (dx, dy)
+    for tag, sc in (("12", 1.2), ("11", 1.1)):
+        for mine, ref in ((vu.U.rescale_fg(fg, sc), g[f"rescale_fg_{tag}"]), (vu.U.rescale_fg(m3[..., 0], sc), g[f"rescale_mask_{tag}"])):
+            d = np.abs(mine.astype(int) - ref.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() <= 1e-4
+    got = host(C.replace_clip(dev(fg[None]), dev(m3[None]), dev(bg), 3, -2, 1.2))[0]
+    d = np.abs(got.astype(int) - g["replace_frame"].astype(int))
+    assert d.max() <= 2 and (d > 0).mean() <= 1e-3

@@ -118,3 +118,19 @@ def test_temporal(golden):
     assert np.array_equal(R.temporal_median(t["frames"]), t["median_even"])
     assert np.array_equal(R.temporal_median(t["frames"][:23]), t["median_odd"])
     assert np.array_equal(R.temporal_median(t["rnd"]), t["median_rnd"])
+
+
+def test_geometry(golden):
+    """replacement-path geometry: shift_fg bit-exact; rescale_fg within the documented tie tolerance of cv2's IPP cubic
+    (oracle/cvmodel.py:resize_cubic_crop)."""
+    g = golden("geometry")
+    fg, m3, bg = g["fg"], g["mask3"], g["bg"]
+    for i, (dx, dy) in enumerate(g["shifts"]):
+        assert np.array_equal(R.shift_fg(fg, dx, dy), g[f"shift_fg_{i}"]), (dx, dy)
+        assert np.array_equal(R.shift_fg(m3[..., 0], dx, dy), g[f"shift_mask_{i}"]), (dx, dy)
+    for tag, sc in (("12", 1.2), ("11", 1.1)):
+        for mine, ref in ((R.rescale_fg(fg, sc), g[f"rescale_fg_{tag}"]), (R.rescale_fg(m3[..., 0], sc), g[f"rescale_mask_{tag}"])):
+            d = np.abs(mine.astype(int) - ref.astype(int))
+            assert d.max() <= 1 and (d > 0).mean() <= 1e-4
+    d = np.abs(R.replace_frame(fg, m3, bg, 3, -2, 1.2).astype(int) - g["replace_frame"].astype(int))
+    assert d.max() <= 2 and (d > 0).mean() <= 1e-3
