@@ -258,6 +258,22 @@ def rescale_size(n, factor):
     return int(np.rint(n * float(factor)))
 
 
+def fma32(a, b, c):
+    """float32 fused multiply-add, correctly rounded: the product of two
+    float32 is exact in float64; the float64 sum is made exact with TwoSum,
+    rounded to odd, and only then rounded to float32 (round-to-odd keeps the
+    second rounding honest: float64 carries more than two extra bits)."""
+    p = np.asarray(a, np.float32).astype(np.float64) * np.asarray(b, np.float32).astype(np.float64)
+    c = np.asarray(c, np.float32).astype(np.float64)
+    p, c = np.broadcast_arrays(p, c)
+    t = p + c
+    bb = t - p
+    e = (p - (t - bb)) + (c - bb)
+    fix = (e != 0) & ((t.view(np.int64) & 1) == 0)
+    t = np.where(fix, np.nextafter(t, np.where(e > 0, np.inf, -np.inf)), t)
+    return t.astype(np.float32)
+
+
 def resize_cubic_crop(src, factor):
     """cv2.resize(src, None, fx=factor, fy=factor, interpolation=INTER_CUBIC)
     followed by the centre crop back to the source size --
@@ -269,11 +285,13 @@ def resize_cubic_crop(src, factor):
     kernel and 8 % of the values differ by 1.  The model here is the one the
     default (IPP) path follows: separable float bicubic, a = -0.75, replicated
     borders, round half to even, saturate.  It is evaluated in float32 with a
-    fixed order (horizontal then vertical, taps -1, 0, +1, +2 accumulated left
-    to right with separate multiplies and adds), which agrees with the IPP
-    result everywhere except at values whose exact result is within float32
-    rounding noise of a .5 tie: < 1e-5 of the values, off by 1 (tools/
-    probe_cubic_*.py).  The CUDA kernel is bit-exact against THIS model."""
+    fixed order (horizontal then vertical; taps -1, 0, +1, +2: one multiply,
+    then three fused multiply-adds), which agrees with the IPP result
+    everywhere except at values whose exact result is within float32 rounding
+    noise of a .5 tie: < 2e-5 of the values, off by 1 (tools/probe_cubic_*.py;
+    exact rational evaluation shows IPP rounds true ties to even, and none of
+    48 float32 evaluation orders reproduces it on the near-ties).  The CUDA
+    kernel is bit-exact against THIS model."""
     src = np.asarray(src)
     h, w = src.shape[:2]
     dh, dw = rescale_size(h, factor), rescale_size(w, factor)
@@ -286,10 +304,10 @@ def resize_cubic_crop(src, factor):
         s = s[..., None]
     hor = s[:, xi[:, 0]] * xc[:, 0][None, :, None]
     for k in range(1, 4):
-        hor = hor + s[:, xi[:, k]] * xc[:, k][None, :, None]
+        hor = fma32(s[:, xi[:, k]], xc[:, k][None, :, None], hor)
     v = hor[yi[:, 0]] * yc[:, 0][:, None, None]
     for k in range(1, 4):
-        v = v + hor[yi[:, k]] * yc[:, k][:, None, None]
+        v = fma32(hor[yi[:, k]], yc[:, k][:, None, None], v)
     assert hor.dtype == np.float32 and v.dtype == np.float32
     out = np.clip(np.rint(v), 0, 255).astype(np.uint8)
     return out.reshape(src.shape)
