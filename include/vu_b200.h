@@ -116,6 +116,17 @@ int vu_shift_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int chann
 int vu_rescale_cubic_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int channels, double factor,
                         vu_stream_t stream);
 
+/* color_correct (unscreen/utils/imgprocess.py:263-300, green.py:120) for a
+ * clip, after its two cv2.resize calls: frames_lo [n,th,tw,3] and alpha_lo
+ * [n,th,tw] are the frames / alphas resized to the working resolution
+ * (vu_resize_linear_u8), alpha [n,h,w] the full-resolution alphas, bg_bgr the
+ * background colour (3 bytes, HOST memory), mean_exp the target mean (0.95).
+ * out [n,h,w] = uint8(alpha * distance map).  Workspace: device memory. */
+size_t vu_color_correct_workspace_bytes(int n, int th, int tw);
+int vu_color_correct(const uint8_t* frames_lo, const uint8_t* alpha_lo, const uint8_t* alpha, int n, int h, int w, int th,
+                     int tw, const uint8_t* bg_bgr, double mean_exp, uint8_t* out, void* workspace,
+                     size_t workspace_bytes, vu_stream_t stream);
+
 /* cv2.resize (bilinear) of single-channel maps with the coefficient math hoisted
  * out of the pixel loop.  mode 1 fuses trimap/agent.py:60 (values strictly between
  * 0 and 255 -> 128) and :100 (128 where fuzzy != 0, only for frames with

@@ -53,6 +53,53 @@ def bgr2hsv(img):
     return np.stack([h, s, v], axis=-1).astype(np.uint8)
 
 
+# cv2's 8-bit BGR2Lab (sRGB, D65): integer tables.  gamma table: 3 fractional
+# bits; cube-root table: 15 fractional bits over 3072 entries; 12-bit matrix.
+_LAB_GAMMA_SHIFT = 3
+_LAB_SHIFT = 12
+_LAB_SHIFT2 = _LAB_SHIFT + _LAB_GAMMA_SHIFT
+
+
+def lab_tables():
+    """(gamma[256], cbrt[3072], coeffs[3][3] for R,G,B) of cv2's RGB2Lab_b.
+    cv2 fills the cube-root table with its own float cube-root routine; the
+    correctly rounded values below differ from it in exactly two entries that
+    any colour reaches (49 and 628), fixed here by hand -- pinned by the
+    exhaustive 2^24 test in tests/test_oracle_cvmodel.py."""
+    i = np.arange(256) / 255.0
+    g = np.where(i <= 0.04045, i / 12.92, ((i + 0.055) / 1.055) ** 2.4)
+    gamma = np.rint(255.0 * (1 << _LAB_GAMMA_SHIFT) * g).astype(np.int64)
+    x = np.arange(256 * 3 // 2 * (1 << _LAB_GAMMA_SHIFT)) / (255.0 * (1 << _LAB_GAMMA_SHIFT))
+    f = np.where(x < 216 / 24389.0, x * (841 / 108.0) + 16 / 116.0, np.cbrt(x))
+    cbrt = np.rint((1 << _LAB_SHIFT2) * f).astype(np.int64)
+    cbrt[49] -= 1
+    cbrt[628] += 1
+    m = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169], [0.019334, 0.119193, 0.950227]])
+    wp = np.array([0.950456, 1.0, 1.088754])
+    coeffs = np.rint((1 << _LAB_SHIFT) * m / wp[:, None]).astype(np.int64)
+    return gamma, cbrt, coeffs
+
+
+_LAB_GAMMA, _LAB_CBRT, _LAB_COEFFS = lab_tables()
+
+
+def bgr2lab(img):
+    """cv2.cvtColor(img, COLOR_BGR2Lab) for uint8."""
+    img = np.asarray(img)
+    b, g, r = (_LAB_GAMMA[img[..., k]] for k in range(3))
+
+    def descale(v, n):
+        return (v + (1 << (n - 1))) >> n
+
+    fx, fy, fz = (_LAB_CBRT[descale(r * _LAB_COEFFS[k, 0] + g * _LAB_COEFFS[k, 1] + b * _LAB_COEFFS[k, 2], _LAB_SHIFT)] for k in range(3))
+    lscale = (116 * 255 + 50) // 100
+    lshift = -((16 * 255 * (1 << _LAB_SHIFT2) + 50) // 100)
+    L = descale(lscale * fy + lshift, _LAB_SHIFT2)
+    a = descale(500 * (fx - fy) + (128 << _LAB_SHIFT2), _LAB_SHIFT2)
+    bb = descale(200 * (fy - fz) + (128 << _LAB_SHIFT2), _LAB_SHIFT2)
+    return np.clip(np.stack([L, a, bb], -1), 0, 255).astype(np.uint8)
+
+
 def bgr2gray(img):
     """cv2.cvtColor(img, COLOR_BGR2GRAY) for uint8 (15-bit coefficients)."""
     img = np.asarray(img)

@@ -345,6 +345,54 @@ def replace_frame(fg, mask, bg, dx, dy, scale_factor=1.2):
     return replace_blend(fg_s, mk_s, bg)
 
 
+def nearest_index(dst, src):
+    """source indices of torch.nn.functional.interpolate(mode='nearest') on the
+    CPU for one axis: identity for equal sizes, i >> 1 for an exact doubling,
+    else floor(float32(i) * float32(src / dst)) clamped."""
+    i = np.arange(dst)
+    if dst == src:
+        return i
+    if dst == 2 * src:
+        return i >> 1
+    scale = np.float32(src) / np.float32(dst)
+    return np.minimum(np.floor(i.astype(np.float32) * scale).astype(np.int64), src - 1)
+
+
+COLOR_CORRECT_MAX_ITERS = 24
+
+
+def color_correct(img, alpha, bg_color, target_long_side=960, mean_exp=0.95):
+    """unscreen/utils/imgprocess.py:263-300: chroma distance to the background
+    colour in Lab at the working resolution, normalised, square-rooted until
+    its mean over the matte reaches ``mean_exp``, and multiplied into alpha.
+
+    float32 like the reference (torch CPU) except for one thing: the mean of
+    the loop condition is accumulated in float64 here (torch sums float32 in an
+    implementation-defined order), so the iteration count can differ only when
+    the reference's mean lies within float32 summation noise of ``mean_exp``."""
+    f32 = np.float32
+    h, w = img.shape[:2]
+    th, tw = get_target_size(h, w, target_long_side)
+    lab = cvm.bgr2lab(cvm.resize_linear(img, tw, th))
+    bg = cvm.bgr2lab(np.asarray(bg_color, np.uint8).reshape(1, 1, 3))
+    d = (lab.astype(f32) / f32(255.0))[:, :, 1:] - (bg.astype(f32) / f32(255.0))[:, :, 1:]
+    dist = np.sqrt(d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1])
+    lo, hi = dist.min(), dist.max()
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dist = ((dist - lo) / (hi - lo)).astype(f32)
+    a_lo = cvm.resize_linear(alpha, tw, th)
+    sel = (a_lo > 0) & (dist > 0)
+    for _ in range(COLOR_CORRECT_MAX_ITERS):
+        if not sel.any() or not (dist[sel].mean(dtype=np.float64) < mean_exp):
+            break
+        dist = np.sqrt(dist)
+    dist[a_lo == 0] = 0
+    dist = dist[nearest_index(h, th)][:, nearest_index(w, tw)]
+    with np.errstate(invalid="ignore"):
+        out = alpha.astype(f32) * dist
+    return np.where(np.isnan(out), 0, out).astype(np.uint8)
+
+
 def patch_bg(bgimg, frame, alpha, mode):
     """tools/unscreen/green.py:125 (mode 'lt128') and bg.py:99 /
     bg_offline.py:171 (mode 'eq0'): predicated copy frame -> bgimg."""

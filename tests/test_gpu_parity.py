@@ -534,3 +534,28 @@ def test_geometry_golden(vu, golden):
     got = host(C.replace_clip(dev(fg[None]), dev(m3[None]), dev(bg), 3, -2, 1.2))[0]
     d = np.abs(got.astype(int) - g["replace_frame"].astype(int))
     assert d.max() <= 2 and (d > 0).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("h,w,L", [(108, 192, 96), (216, 384, 96), (150, 110, 60), (96, 160, 160), (270, 480, 240)])
+def test_color_correct(vu, h, w, L):
+    """color_correct (imgprocess.py:263-300) against the oracle (itself bit-exact against the live reference in
+    tests/test_oracle_vs_reference.py): bit-exact, single images through the reference-shaped function and a clip through
+    the batched op; working resolutions that are the frame size, half of it, and a non-integer ratio; mattes that are
+    empty (no iteration) and a frame of one single colour (0 / 0: the reference's NaN casts to 0)."""
+    from video_unscreen_b200 import synth
+    n = 3
+    frames, segs = synth.green_clip(n, h, w, seed=h + L)
+    rng = np.random.default_rng(w)
+    alphas = np.stack([np.minimum(np.where(rng.random((h, w)) < 0.3, rng.integers(0, 256, (h, w)), 255).astype(np.uint8), segs[i]) for i in range(n)])
+    alphas[2] = 0
+    th, tw = R.get_target_size(h, w, L)
+    for col in ((60, 200, 40), (200, 30, 30)):
+        c = np.array(col, np.uint8)
+        want = np.stack([R.color_correct(frames[i], alphas[i], c, target_long_side=L) for i in range(n)])
+        got = host(vu.ops.color_correct(dev(frames), dev(alphas), c, th, tw))
+        assert np.array_equal(got, want), (col, int((got != want).sum()))
+        assert np.array_equal(vu.U.color_correct(frames[0], alphas[0], c, target_long_side=L), want[0])
+    flat = np.full((h, w, 3), 77, np.uint8)
+    a = np.full((h, w), 200, np.uint8)
+    c = np.array((60, 200, 40), np.uint8)
+    assert np.array_equal(vu.U.color_correct(flat, a, c, target_long_side=L), R.color_correct(flat, a, c, target_long_side=L))

@@ -98,3 +98,9 @@ def test_resize_cubic_crop(shape):
         ref = r[ho:ho + h, wo:wo + w].astype(int)
         d = np.abs(M.resize_cubic_crop(img, f).astype(int) - ref)
         assert d.max() <= 1 and (d > 0).mean() <= CUBIC_TIE_TOL, (f, int((d > 0).sum()))
+
+
+def test_bgr2lab_exhaustive():
+    """cv2's 8-bit BGR2Lab over all 2^24 colours: bit-exact (color_correct, imgprocess.py:285-287)."""
+    img = all_colours()
+    assert np.array_equal(M.bgr2lab(img), cv2.cvtColor(img, cv2.COLOR_BGR2Lab))

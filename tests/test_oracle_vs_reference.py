@@ -113,3 +113,21 @@ def test_replace_geometry(ref):
     want = (f.astype(np.float64) * nb + bg.astype(np.float64) * (1 - nb)).astype(np.uint8)
     d = np.abs(R.replace_frame(fg, m3, bg, 3, -2, 1.2).astype(int) - want.astype(int))
     assert d.max() <= 2 and (d > 0).mean() <= 1e-3
+
+
+@pytest.mark.parametrize("h,w,L", [(108, 192, 96), (216, 384, 96), (150, 110, 60), (96, 160, 160)])
+def test_color_correct(ref, h, w, L):
+    """color_correct (imgprocess.py:263-300) against the live reference: bit-exact (the float32 sequence is restated
+    operation by operation; only the loop's mean is accumulated differently, see the oracle's docstring)."""
+    from video_unscreen_b200 import synth
+    frames, segs = synth.green_clip(2, h, w, seed=h + L)
+    rng = np.random.default_rng(w)
+    for i in range(2):
+        alpha = segs[i].copy()
+        alpha[rng.random((h, w)) < 0.3] = rng.integers(0, 256)
+        alpha = np.minimum(alpha, segs[i])
+        for col in ((60, 200, 40), (200, 30, 30)):
+            c = np.array(col, np.uint8)
+            want = ref.U.color_correct(frames[i].copy(), alpha.copy(), c.copy(), target_long_side=L)
+            got = R.color_correct(frames[i], alpha, c, target_long_side=L)
+            assert np.array_equal(got, want), (i, col, int((got != want).sum()))

@@ -44,6 +44,8 @@ SIGNATURES = {
     "vu_resize_nearest_u8": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _p]),
     "vu_shift_u8": (_i, [_p, _p, _i, _i, _i, _i, _f, _f, _p]),
     "vu_rescale_cubic_u8": (_i, [_p, _p, _i, _i, _i, _i, _d, _p]),
+    "vu_color_correct_workspace_bytes": (_sz, [_i, _i, _i]),
+    "vu_color_correct": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _d, _p, _p, _sz, _p]),
     "vu_count_cmp_u8": (_i, [_p, _i, _i64, _i, _i, _p, _p]),
     "vu_count_and_u8": (_i, [_p, _p, _i, _i64, _p, _p]),
     "vu_mask_clear_where": (_i, [_p, _p, _p, _i64, _p]),

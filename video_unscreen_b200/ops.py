@@ -7,6 +7,7 @@ device tensors; nothing synchronises.
 """
 import ctypes
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -287,6 +288,25 @@ def rescale_cubic(x, factor, channels=3):
     x, n, h, w = _geom_shape(_dev(x), channels)
     out = torch.empty_like(x)
     check(lib().vu_rescale_cubic_u8(_p(x), _p(out), n, h, w, channels, float(factor), _stream()))
+    return out
+
+
+def color_correct(frames, alpha, bg_color, th, tw, mean_exp=0.95):
+    """color_correct (imgprocess.py:263-300) for an image [H,W,3] + alpha [H,W] or a clip [N,H,W,3] + [N,H,W]:
+    alpha scaled by the normalised Lab chroma distance to ``bg_color`` (3 uint8 values, host side) computed at the
+    working resolution th x tw."""
+    frames, alpha = _img(frames), _mask(alpha)
+    n = 1 if frames.ndim == 3 else frames.shape[0]
+    h, w = frames.shape[-3], frames.shape[-2]
+    if tuple(alpha.shape[-2:]) != (h, w) or alpha.numel() != n * h * w:
+        raise ValueError(f"alpha {tuple(alpha.shape)} does not match frames {tuple(frames.shape)}")
+    col = np.ascontiguousarray(np.asarray(bg_color, dtype=np.uint8).reshape(3))
+    frames_lo = resize_linear_image(frames, th, tw)
+    alpha_lo = resize_linear_mask(alpha, th, tw)
+    ws = torch.empty(lib().vu_color_correct_workspace_bytes(n, th, tw), dtype=u8, device=frames.device)
+    out = torch.empty_like(alpha)
+    check(lib().vu_color_correct(_p(frames_lo), _p(alpha_lo), _p(alpha), n, h, w, int(th), int(tw), col.ctypes.data, float(mean_exp), _p(out),
+                                 _p(ws), ws.numel(), _stream()))
     return out
 
 

@@ -3,7 +3,7 @@
 from ... import ops
 from ..._io import back, to_dev
 
-__all__ = ["get_target_size", "adaptive_resize", "rescale_fg", "shift_fg"]
+__all__ = ["get_target_size", "adaptive_resize", "color_correct", "rescale_fg", "shift_fg"]
 
 
 def get_target_size(h, w, target_long_side, division=1):
@@ -49,3 +49,13 @@ def shift_fg(img, dx=0, dy=0):
     """reference unscreen/utils/imgprocess.py:55-64: cv2.warpAffine translation, zero border (bit-exact)."""
     t, as_np = to_dev(img)
     return back(ops.shift(t, dx, dy, _channels(t)), as_np)
+
+
+def color_correct(img, alpha, bg_color, target_long_side=960, mean_exp=0.95):
+    """reference unscreen/utils/imgprocess.py:263-300 (green.py:120): alpha times the normalised Lab chroma distance
+    to the background colour.  Bit-exact float32 sequence; the loop's mean is accumulated in float64 on the device."""
+    t, as_np = to_dev(img)
+    a, _ = to_dev(alpha)
+    th, tw = get_target_size(t.shape[0], t.shape[1], target_long_side)
+    col = bg_color.cpu().numpy() if hasattr(bg_color, "cpu") else bg_color
+    return back(ops.color_correct(t, a, col, th, tw, mean_exp), as_np)
