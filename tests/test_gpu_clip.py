@@ -60,6 +60,28 @@ def test_green_clip_matches_agents_and_oracle(env, tag, h, w, L):
         assert np.array_equal(fg[i], R.get_fg(frames[i], a_o, patched)), i
 
 
+@pytest.mark.parametrize("tag,h,w,L", [("x2", 108, 192, 96), ("x4", 216, 384, 96)])
+def test_green_clip_with_color_correct(env, tag, h, w, L):
+    """green.py:99-126 with the colour-correction stage (:120) between the trimap and get_fg; the default working
+    resolution of color_correct (960) is above these frames, so it runs at full resolution here."""
+    n = 4
+    frames, segs = synth.green_clip(n, h, w, seed=8)
+    lb, lf, bgh = env.tables[tag]
+    cf = env.CF(input_long_side=L)
+    cf.set_tables(lb, lf, bgh)
+    ta = env.TA(input_long_side=L)
+    alpha, tri, fg, bgo = (t.cpu().numpy() for t in env.clip.green_clip(dev(frames), dev(segs), cf, ta, chunk=3, color_correct=True))
+    bg_color = cf.bg_color_bgr()
+    for i in range(n):
+        a_o, _, _ = R.cf_forward_predict(frames[i], segs[i], lb, lf, bgh, L)
+        assert np.array_equal(tri[i], R.generate_trimap_withbg(a_o, frames[i], bg_color, L)), i
+        a_c = R.color_correct(frames[i], a_o, bg_color)
+        assert np.array_equal(alpha[i], a_c), i
+        patched = R.patch_bg(np.broadcast_to(bg_color, frames[i].shape), frames[i], a_c, "lt128")
+        assert np.array_equal(bgo[i], patched), i
+        assert np.array_equal(fg[i], R.get_fg(frames[i], a_c, patched)), i
+
+
 def test_trimap_clip_variants(env, golden):
     t = golden("trimap")
     L = int(t["x2_L"])

@@ -177,6 +177,26 @@ def main():
                               "frac": round(2 * n * per / ms / 1e6 / peak, 3)}), flush=True)
         del fg, al, bg, out
 
+    if want("color_correct_1080p"):
+        n, h, w = 120, 1080, 1080 * 16 // 9
+        fr, sg, _, _ = green_clip_dev(n, h, w)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        al = torch.minimum(sg, torch.randint(0, 256, sg.shape, dtype=torch.uint8, device="cuda", generator=g) | 128)
+        col = np.array([60, 200, 40], np.uint8)
+        out = [None]
+
+        def step():
+            out[0] = clip.color_correct_clip(fr, al, col, chunk=30)
+        ms, launches = timed(step, args.steps)
+        f0, a0 = fr[0].cpu().numpy(), al[0].cpu().numpy()
+        t0 = time.perf_counter()
+        ref = R.color_correct(f0, a0, col)
+        dt = time.perf_counter() - t0
+        assert np.array_equal(out[0][0].cpu().numpy(), ref)
+        report("color_correct_1080p", "color_correct (imgprocess.py:263-300, green.py:120), 120 x 1080p, working resolution 540 x 960", n, ms,
+               launches, n * 5 * h * w, 1 / dt, "oracle color_correct on 1 frame (numpy, 1 thread); output bit-exact", peak)
+        del fr, sg, al, out
+
     if want("masked_mean_1080p"):
         n, h, w = 300, 1080, 1920
         fr = bench.make_clip_device(n, h, w, 2, torch.device("cuda"))

@@ -118,10 +118,22 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
     return tri
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None, bg_tile=None):
+def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=16):
+    """color_correct (imgprocess.py:263-300) over a clip, chunk by chunk."""
+    from .unscreen.utils.imgprocess import get_target_size
+    n, h, w, _ = frames.shape
+    th, tw = get_target_size(h, w, target_long_side)
+    out = torch.empty_like(alpha)
+    for s, e in _chunks(n, chunk):
+        out[s:e] = ops.color_correct(frames[s:e], alpha[s:e], bg_color, th, tw, mean_exp)
+    return out
+
+
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None, bg_tile=None, color_correct=False):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
     stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
-    bgimg[alpha<128] = frame[...] -> get_fg.  Returns alpha, trimap, fg, bg.
+    [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.
+    Returns alpha, trimap, fg, bg.
     ``bg_color`` ((3,) BGR, host) / ``bg_tile`` ([1,4,3] device) default to the agent's background colour; pass them
     in when the call is captured into a CUDA graph (fetching them synchronises)."""
     n, h, w, _ = frames.shape
@@ -138,6 +150,9 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None
         a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk)
         alpha[s:e] = a
         tri[s:e] = trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk)
+        if color_correct:
+            a = color_correct_clip(frames[s:e], a, bg_color, chunk=chunk)
+            alpha[s:e] = a
         f, b = ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True)
         fg[s:e] = f
         bgo[s:e] = b
