@@ -126,6 +126,13 @@ size_t vu_color_correct_workspace_bytes(int n, int th, int tw);
 int vu_color_correct(const uint8_t* frames_lo, const uint8_t* alpha_lo, const uint8_t* alpha, int n, int h, int w, int th,
                      int tw, const uint8_t* bg_bgr, double mean_exp, uint8_t* out, void* workspace,
                      size_t workspace_bytes, vu_stream_t stream);
+/* The same from the full-resolution frames [n,h,w,3], with cv2's down-scale
+ * fused in, when the frame is exactly 2x or 4x the working resolution and w is
+ * a multiple of 16 (1080p and 4K at target_long_side 960); otherwise
+ * VU_ERR_UNSUPPORTED: resize and call vu_color_correct. */
+int vu_color_correct_frames(const uint8_t* frames, const uint8_t* alpha, int n, int h, int w, int th, int tw,
+                            const uint8_t* bg_bgr, double mean_exp, uint8_t* out, void* workspace,
+                            size_t workspace_bytes, vu_stream_t stream);
 
 /* cv2.resize (bilinear) of single-channel maps with the coefficient math hoisted
  * out of the pixel loop.  mode 1 fuses trimap/agent.py:60 (values strictly between

@@ -16,6 +16,7 @@ DILATE, ERODE = 0, 1
 CMP_GE, CMP_GT, CMP_LT, CMP_EQ, CMP_NE = range(5)
 PATCH_NONE, PATCH_ALPHA_LT128, PATCH_ALPHA_EQ0 = range(3)
 BLEND_NAIVE, BLEND_FUSE, BLEND_COMPOSITE, BLEND_REPLACE = range(4)
+ERR_UNSUPPORTED = -2   # enum vu_status: VU_ERR_UNSUPPORTED
 
 _p = ctypes.c_void_p
 _i = ctypes.c_int
@@ -46,6 +47,7 @@ SIGNATURES = {
     "vu_rescale_cubic_u8": (_i, [_p, _p, _i, _i, _i, _i, _d, _p]),
     "vu_color_correct_workspace_bytes": (_sz, [_i, _i, _i]),
     "vu_color_correct": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _d, _p, _p, _sz, _p]),
+    "vu_color_correct_frames": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _d, _p, _p, _sz, _p]),
     "vu_count_cmp_u8": (_i, [_p, _i, _i64, _i, _i, _p, _p]),
     "vu_count_and_u8": (_i, [_p, _p, _i, _i64, _p, _p]),
     "vu_mask_clear_where": (_i, [_p, _p, _p, _i64, _p]),

@@ -301,10 +301,15 @@ def color_correct(frames, alpha, bg_color, th, tw, mean_exp=0.95):
     if tuple(alpha.shape[-2:]) != (h, w) or alpha.numel() != n * h * w:
         raise ValueError(f"alpha {tuple(alpha.shape)} does not match frames {tuple(frames.shape)}")
     col = np.ascontiguousarray(np.asarray(bg_color, dtype=np.uint8).reshape(3))
-    frames_lo = resize_linear_image(frames, th, tw)
-    alpha_lo = resize_linear_mask(alpha, th, tw)
     ws = torch.empty(lib().vu_color_correct_workspace_bytes(n, th, tw), dtype=u8, device=frames.device)
     out = torch.empty_like(alpha)
+    rc = lib().vu_color_correct_frames(_p(frames), _p(alpha), n, h, w, int(th), int(tw), col.ctypes.data, float(mean_exp), _p(out), _p(ws),
+                                       ws.numel(), _stream())
+    if rc != _lib.ERR_UNSUPPORTED:      # exact 2x / 4x working resolution: the down-scale is fused into the first kernel
+        check(rc)
+        return out
+    frames_lo = resize_linear_image(frames, th, tw)
+    alpha_lo = resize_linear_mask(alpha, th, tw)
     check(lib().vu_color_correct(_p(frames_lo), _p(alpha_lo), _p(alpha), n, h, w, int(th), int(tw), col.ctypes.data, float(mean_exp), _p(out),
                                  _p(ws), ws.numel(), _stream()))
     return out
