@@ -253,6 +253,17 @@ def geometry(U):
     m = U.rescale_fg(U.shift_fg(m3, dx=3, dy=-2), scale_factor=1.2)
     nb = m.astype(np.float64) / 255
     geo["replace_frame"] = (f.astype(np.float64) * nb + bg.astype(np.float64) * (1 - nb)).astype(np.uint8)
+    # color_correct (imgprocess.py:263-300) on frames of the synthetic green clip, working resolutions 1x, 1/2, ragged
+    from video_unscreen_b200 import synth
+    frames, segs = synth.green_clip(2, 108, 192, seed=12)
+    alpha = np.minimum(segs, np.where(rng.random(segs.shape) < 0.3, rng.integers(0, 256, segs.shape), 255).astype(np.uint8))
+    geo["cc_frames"], geo["cc_alpha"] = frames, alpha
+    geo["cc_colors"] = np.array([[60, 200, 40], [200, 30, 30]], np.uint8)
+    geo["cc_long_sides"] = np.array([96, 192, 70])
+    for ci, col in enumerate(geo["cc_colors"]):
+        for L in geo["cc_long_sides"]:
+            for i in range(2):
+                geo[f"cc_{ci}_{int(L)}_{i}"] = U.color_correct(frames[i].copy(), alpha[i].copy(), col.copy(), target_long_side=int(L))
     np.savez_compressed(os.path.join(HERE, "geometry.npz"), **geo)
 
 

@@ -74,3 +74,21 @@ def test_agents_mirror_reference_signatures():
         BackgroundAgent().forward(None, None, method="nope")
     ag = ColorFilteringAgent()
     assert not ag.is_trained() and len(ag.bg_gmms) == 3 and len(ag.fg_gmms) == 3
+
+
+def test_generated_lab_tables_match_the_oracle():
+    """video_unscreen_b200/csrc/vu_lab_tables.inc (tools/gen_lab_tables.py) holds the tables of oracle.cvmodel.bgr2lab,
+    which tests/test_oracle_cvmodel.py pins against cv2 over all 2^24 colours."""
+    import re
+
+    from oracle import cvmodel as M
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(ROOT, "video_unscreen_b200", "csrc", "vu_lab_tables.inc")).read().replace("\\\n", " ")
+    tabs = {}
+    for name, body in re.findall(r"#define (\w+)\s+([0-9,\s]+)", text):
+        tabs[name] = np.array([int(v) for v in body.replace(" ", "").strip(",").split(",") if v])
+    gamma, cbrt, coeffs = M.lab_tables()
+    assert np.array_equal(tabs["VU_LAB_GAMMA_TABLE"], gamma) and np.array_equal(tabs["VU_LAB_CBRT_TABLE"], cbrt)
+    src = open(os.path.join(ROOT, "video_unscreen_b200", "csrc", "vu_colorcorrect.cu")).read()
+    m = re.search(r"#define VU_LAB_COEFFS \{([0-9,\s]+)\}", src)
+    assert [int(v) for v in m.group(1).split(",")] == coeffs.reshape(-1).tolist()

@@ -559,3 +559,14 @@ def test_color_correct(vu, h, w, L):
     a = np.full((h, w), 200, np.uint8)
     c = np.array((60, 200, 40), np.uint8)
     assert np.array_equal(vu.U.color_correct(flat, a, c, target_long_side=L), R.color_correct(flat, a, c, target_long_side=L))
+
+
+def test_color_correct_golden(vu, golden):
+    """color_correct against outputs of the unmodified reference (tests/golden/geometry.npz): bit-exact; the 1/2 working
+    resolution takes the fused down-scale kernel, the others the resize + vu_color_correct path."""
+    g = golden("geometry")
+    for ci, col in enumerate(g["cc_colors"]):
+        for L in g["cc_long_sides"]:
+            for i in range(2):
+                got = vu.U.color_correct(g["cc_frames"][i], g["cc_alpha"][i], col, target_long_side=int(L))
+                assert np.array_equal(got, g[f"cc_{ci}_{int(L)}_{i}"]), (ci, int(L), i)

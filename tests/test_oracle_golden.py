@@ -134,3 +134,14 @@ def test_geometry(golden):
             assert d.max() <= 1 and (d > 0).mean() <= 1e-4
     d = np.abs(R.replace_frame(fg, m3, bg, 3, -2, 1.2).astype(int) - g["replace_frame"].astype(int))
     assert d.max() <= 2 and (d > 0).mean() <= 1e-3
+
+
+def test_color_correct(golden):
+    """color_correct outputs of the unmodified reference (green-clip frames, three working resolutions, two background
+    colours): bit-exact."""
+    g = golden("geometry")
+    for ci, col in enumerate(g["cc_colors"]):
+        for L in g["cc_long_sides"]:
+            for i in range(2):
+                got = R.color_correct(g["cc_frames"][i], g["cc_alpha"][i], col, target_long_side=int(L))
+                assert np.array_equal(got, g[f"cc_{ci}_{int(L)}_{i}"]), (ci, int(L), i)
