@@ -43,10 +43,10 @@ __global__ void __launch_bounds__(THREADS) get_fg_kernel(const uint8_t* __restri
     const unsigned* f4 = reinterpret_cast<const unsigned*>(frame) + 3 * g;
     const unsigned aw = __ldg(reinterpret_cast<const unsigned*>(alpha) + g);
     if (PATCH != VU_PATCH_NONE) {
-      // a patched pixel has bg == frame, hence fg = HSV2BGR(hsv - (1 - a/255) * hsv): with the alpha == 0 patch that is
-      // HSV2BGR(0,0,0) = black.  Whole warps of such pixels (everything outside the matte) skip the arithmetic, and the
-      // loads too when the patched background is not asked for.
-      const bool allzero = PATCH == VU_PATCH_ALPHA_EQ0 && aw == 0u;
+      // a patched pixel has bg == frame, hence fg = HSV2BGR(hsv - (1 - a/255) * hsv): at alpha == 0 - patched under both
+      // rules (== 0, < 128) - that is HSV2BGR(0,0,0) = black.  Whole warps of such pixels (everything outside the matte)
+      // skip the arithmetic, and the loads too when the patched background is not asked for.
+      const bool allzero = aw == 0u;
       if (__all_sync(__activemask(), allzero)) {
         unsigned* d4 = reinterpret_cast<unsigned*>(fg_out) + 3 * g;
         d4[0] = 0u; d4[1] = 0u; d4[2] = 0u;
@@ -122,8 +122,9 @@ __global__ void __launch_bounds__(THREADS) get_fg16_kernel(const uint4* __restri
     uint4 fv[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frame + 3 * g + k);
-    if (PATCH == VU_PATCH_ALPHA_EQ0 && (av.x | av.y | av.z | av.w) == 0u) {
-      // every pixel patched with itself: fg = HSV2BGR(hsv - 1.0 * hsv) = black
+    if (PATCH != VU_PATCH_NONE && (av.x | av.y | av.z | av.w) == 0u) {
+      // alpha == 0 is patched under both rules (== 0, < 128): every pixel's background is the pixel itself and
+      // fg = HSV2BGR(hsv - 1.0 * hsv) = black
 #pragma unroll
       for (int k = 0; k < 3; ++k) stg_stream16(fg_out + 3 * g + k, make_uint4(0u, 0u, 0u, 0u));
       if (WRITE_BG) {
