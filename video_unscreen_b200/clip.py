@@ -68,17 +68,18 @@ def cf_predict_clip(frames, segmasks, agent, chunk=32, out=None):
             hsv_lo = ops.resize_linear_image(ops.bgr2hsv(fr), th, tw)
             a_lo = ops.cf_postprocess(ops.cf_alpha_lut3d(hsv_lo, lut3d), ops.resize_linear_mask(sm, th, tw), 0.8)
         # degenerate masks are returned as they came (agent.py:303-307): alt_src / alt_flags
-        alpha[s:e] = ops.resize_up(a_lo, h, w, alt_src=sm, alt_flags=flags)
+        ops.resize_up(a_lo, h, w, alt_src=sm, alt_flags=flags, out=alpha[s:e])
     return alpha
 
 
-def _trimap_tail(masks, agent, fuzzy=None, flags=None):
-    """nearest down (+ ensemble clearing) -> dilate/erode/classify -> bilinear up + snap (+ fuzzy override)"""
+def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None):
+    """nearest down (+ ensemble clearing) -> dilate/erode/classify -> bilinear up + snap (+ fuzzy override); written into
+    ``out`` when given"""
     n, h, w = masks.shape
     ih, iw = get_target_size(h, w, agent.input_long_side)
     if agent.kernelsize == 3 and ops.trimap_bits_supported(masks, ih, iw, agent.iters, fuzzy):
         # exact 2x / 4x working resolution (1080p, 4K): the whole tail in bit logic, two launches
-        return ops.trimap_bits(masks, ih, iw, agent.iters, fuzzy, flags)
+        return ops.trimap_bits(masks, ih, iw, agent.iters, fuzzy, flags, out=out)
     m = ops.trimap_src_lo(masks, ih, iw, fuzzy, flags)
     if agent.kernelsize == 3 and agent.iters <= ops.CROSS_MAX_PASSES:
         tri = ops.trimap_core(m, agent.iters)
@@ -86,8 +87,12 @@ def _trimap_tail(masks, agent, fuzzy=None, flags=None):
         tri = ops.trimap_classify(ops.dilate(m, agent.kernelsize, agent.iters), ops.erode(m, agent.kernelsize, agent.iters))
     if (ih, iw) == (h, w) or (ih == 2 * h and iw == 2 * w):   # copy / cv2's INTER_AREA corner cases: unfused tail
         t = ops.trimap_snap(ops.resize_linear_mask(tri, h, w))
-        return ops.set128_unflagged(t, fuzzy, flags) if fuzzy is not None else t
-    return ops.resize_up(tri, h, w, mode=1, fuzzy=fuzzy, flags=flags)
+        t = ops.set128_unflagged(t, fuzzy, flags) if fuzzy is not None else t
+        if out is not None:
+            out.copy_(t)
+            return out
+        return t
+    return ops.resize_up(tri, h, w, mode=1, fuzzy=fuzzy, flags=flags, out=out)
 
 
 def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
@@ -101,7 +106,7 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
     for s, e in _chunks(n, chunk):
         m = masks[s:e]
         if frames is None:
-            tri[s:e] = _trimap_tail(m, agent)
+            _trimap_tail(m, agent, out=tri[s:e])
             continue
         fr = frames[s:e]
         if isinstance(bg, np.ndarray) and bg.ndim == 1:
@@ -114,18 +119,19 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
             fuzzy = ops.mask_and01(m, bgmask)
         flags = ops.ratio_flags(counts, 0.1)       # 0: ensemble, 1: trust mask, 2: empty mask
         # an empty mask is returned as is (all zeros); the plain branch of an all-zero mask is all zeros too
-        tri[s:e] = _trimap_tail(m, agent, fuzzy, flags)
+        _trimap_tail(m, agent, fuzzy, flags, out=tri[s:e])
     return tri
 
 
-def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=16):
-    """color_correct (imgprocess.py:263-300) over a clip, chunk by chunk."""
+def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=16, out=None):
+    """color_correct (imgprocess.py:263-300) over a clip, chunk by chunk (``out`` must not alias ``alpha``)."""
     from .unscreen.utils.imgprocess import get_target_size
     n, h, w, _ = frames.shape
     th, tw = get_target_size(h, w, target_long_side)
-    out = torch.empty_like(alpha)
+    if out is None:
+        out = torch.empty_like(alpha)
     for s, e in _chunks(n, chunk):
-        out[s:e] = ops.color_correct(frames[s:e], alpha[s:e], bg_color, th, tw, mean_exp)
+        ops.color_correct(frames[s:e], alpha[s:e], bg_color, th, tw, mean_exp, out=out[s:e])
     return out
 
 
@@ -147,15 +153,12 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None
     if bg_tile is None:
         bg_tile = torch.from_numpy(np.tile(bg_color, (1, 4, 1))).to(dev)     # constant background: a 4-pixel periodic image
     for s, e in _chunks(n, chunk):
-        a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk)
-        alpha[s:e] = a
-        tri[s:e] = trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk)
+        # every stage writes straight into its slice of the clip-sized results
+        a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
+        trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
         if color_correct:
-            a = color_correct_clip(frames[s:e], a, bg_color, chunk=chunk)
-            alpha[s:e] = a
-        f, b = ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True)
-        fg[s:e] = f
-        bgo[s:e] = b
+            a = color_correct_clip(frames[s:e], a.clone(), bg_color, chunk=chunk, out=alpha[s:e])
+        ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True, out=fg[s:e], bg_out=bgo[s:e])
     return alpha, tri, fg, bgo
 
 
@@ -185,13 +188,14 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=16):
     tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     fg = torch.empty_like(frames)
     for s, e in _chunks(n, chunk):
+        # every stage writes straight into its slice of the clip-sized results
         if ops.bgdiff_gate_supported(frames[s:e], bg, masks[s:e]):
-            a = ops.bgdiff_gate(frames[s:e], bg, masks[s:e], thr)
+            a = ops.bgdiff_gate(frames[s:e], bg, masks[s:e], thr, out=alpha[s:e])
         else:
             a = ops.gate(masks[s:e], ops.dilate(ops.bgdiff_gray(frames[s:e], bg, thr), 4, 2))
-        alpha[s:e] = a
-        tri[s:e] = trimap_clip(a, trimap_agent, chunk=chunk)
-        fg[s:e] = ops.get_fg(frames[s:e], a, bg, _lib.PATCH_ALPHA_EQ0)
+            alpha[s:e] = a
+        trimap_clip(a, trimap_agent, chunk=chunk, out=tri[s:e])
+        ops.get_fg(frames[s:e], a, bg, _lib.PATCH_ALPHA_EQ0, out=fg[s:e])
     return bg, alpha, tri, fg
 
 

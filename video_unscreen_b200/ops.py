@@ -145,8 +145,7 @@ def trimap_bits(masks, th, tw, iters, fuzzy=None, flags=None, out=None):
     x = _mask(masks)
     n = 1 if x.ndim == 2 else x.shape[0]
     h, w = x.shape[-2:]
-    if out is None:
-        out = torch.empty_like(x)
+    out = _out(out, x.shape, x.device)
     ws_bytes = int(lib().vu_trimap_bits_workspace_bytes(n, int(th), int(tw)))
     ws = torch.empty(ws_bytes, dtype=u8, device=x.device)
     fz = _p(_dev(fuzzy)) if fuzzy is not None else ctypes.c_void_p(0)
@@ -188,12 +187,22 @@ def resize_linear_mask(x, dh, dw):
     return resize_up(x, dh, dw)
 
 
-def resize_up(x, dh, dw, mode=0, fuzzy=None, flags=None, alt_src=None, alt_flags=None):
+def _out(out, shape, device):
+    """the caller's output tensor (a contiguous uint8 CUDA tensor of the right shape: e.g. a slice of a clip-sized result,
+    so that chunked pipelines do not copy their chunks) or a fresh one."""
+    if out is None:
+        return torch.empty(shape, dtype=u8, device=device)
+    if tuple(out.shape) != tuple(shape) or out.dtype != u8 or not out.is_cuda or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous CUDA uint8 tensor of shape {tuple(shape)}")
+    return out
+
+
+def resize_up(x, dh, dw, mode=0, fuzzy=None, flags=None, alt_src=None, alt_flags=None, out=None):
     """cv2.resize (bilinear) of masks with fused epilogues (see vu_resize_up_u8)."""
     x = _mask(x)
     n = 1 if x.ndim == 2 else x.shape[0]
     sh, sw = x.shape[-2:]
-    out = torch.empty((dh, dw) if x.ndim == 2 else (n, dh, dw), dtype=u8, device=x.device)
+    out = _out(out, (dh, dw) if x.ndim == 2 else (n, dh, dw), x.device)
     check(lib().vu_resize_up_u8(_p(x), n, sh, sw, _p(out), int(dh), int(dw), int(mode), _p(fuzzy), _p(flags), _p(alt_src), _p(alt_flags),
                                 _stream()))
     return out
@@ -291,7 +300,7 @@ def rescale_cubic(x, factor, channels=3):
     return out
 
 
-def color_correct(frames, alpha, bg_color, th, tw, mean_exp=0.95):
+def color_correct(frames, alpha, bg_color, th, tw, mean_exp=0.95, out=None):
     """color_correct (imgprocess.py:263-300) for an image [H,W,3] + alpha [H,W] or a clip [N,H,W,3] + [N,H,W]:
     alpha scaled by the normalised Lab chroma distance to ``bg_color`` (3 uint8 values, host side) computed at the
     working resolution th x tw."""
@@ -302,7 +311,7 @@ def color_correct(frames, alpha, bg_color, th, tw, mean_exp=0.95):
         raise ValueError(f"alpha {tuple(alpha.shape)} does not match frames {tuple(frames.shape)}")
     col = np.ascontiguousarray(np.asarray(bg_color, dtype=np.uint8).reshape(3))
     ws = torch.empty(lib().vu_color_correct_workspace_bytes(n, th, tw), dtype=u8, device=frames.device)
-    out = torch.empty_like(alpha)
+    out = _out(out, alpha.shape, alpha.device)
     rc = lib().vu_color_correct_frames(_p(frames), _p(alpha), n, h, w, int(th), int(tw), col.ctypes.data, float(mean_exp), _p(out), _p(ws),
                                        ws.numel(), _stream())
     if rc != _lib.ERR_UNSUPPORTED:      # exact 2x / 4x working resolution: the down-scale is fused into the first kernel
@@ -383,14 +392,14 @@ def bgdiff_gate_supported(frames, bg, masks):
     return frames.shape[-2] % 4 == 0 and all(t.data_ptr() % 8 == 0 for t in (frames, bg, masks))
 
 
-def bgdiff_gate(frames, bg, masks, thr):
+def bgdiff_gate(frames, bg, masks, thr, out=None):
     """mask * (dilate_mask(g, 4, 2) // 255), g = thresholded BGR2GRAY(|frame - bg|), fused and bit-packed
     (tools/unscreen/bg.py:85-92 == bg_offline.py:154-160); frames [N,H,W,3] or [H,W,3], bg [H,W,3] or [N,H,W,3]."""
     frames, bg, masks = _img(frames), _img(bg), _dev(masks)
     h, w = frames.shape[-3], frames.shape[-2]
     n = frames.numel() // (h * w * 3)
     nb = bg.numel() // (h * w * 3)
-    out = torch.empty_like(masks)
+    out = _out(out, masks.shape, masks.device)
     check(lib().vu_bgdiff_gate(_p(frames), _p(bg), _p(masks), n, h, w, nb, int(thr), _p(out), _stream()))
     return out
 
@@ -465,12 +474,12 @@ def cf_threshold(alpha, mask, thr_ratio=0.8):
 
 # ---- compositing ----------------------------------------------------------------
 
-def get_fg(frame, alpha, bg, patch=_lib.PATCH_NONE, want_bg=False):
+def get_fg(frame, alpha, bg, patch=_lib.PATCH_NONE, want_bg=False, out=None, bg_out=None):
     frame, alpha, bg = _img(frame), _mask(alpha), _img(bg)
     if alpha.shape != frame.shape[:-1]:
         raise ValueError("alpha must have the frame's [N,]H,W")
-    fg = torch.empty_like(frame)
-    bgo = torch.empty_like(frame) if want_bg else None
+    fg = _out(out, frame.shape, frame.device)
+    bgo = _out(bg_out, frame.shape, frame.device) if want_bg else None
     check(lib().vu_get_fg(_p(frame), _p(alpha), _p(bg), frame.numel() // 3, bg.numel() // 3, patch, _p(fg), _p(bgo), _stream()))
     return (fg, bgo) if want_bg else fg
 
