@@ -40,7 +40,7 @@ def _chunks(n, chunk):
         yield s, min(n, s + chunk)
 
 
-def cf_predict_clip(frames, segmasks, agent, chunk=32, out=None):
+def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None):
     """ColorFilteringAgent.forward(frame, mask, iters=0) for every frame of
     frames[N,H,W,3] / segmasks[N,H,W] with the agent's current mixtures
     (reference colorfiltering/agent.py:285-354, predict-only branch :319-321).
@@ -95,7 +95,7 @@ def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None):
     return ops.resize_up(tri, h, w, mode=1, fuzzy=fuzzy, flags=flags, out=out)
 
 
-def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
+def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None):
     """TrimapAgent.forward for every frame: mask-only (trimap/agent.py:35-61) or,
     with ``frames`` and ``bg`` ((3,) colour or [H,W,3] / [N,H,W,3] image), the
     background-gated variant (:63-101) with its per-frame ratio test decided on
@@ -123,7 +123,24 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=32, out=None):
     return tri
 
 
-def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=16, out=None):
+def cf_trimap_clip(frames, segmasks, cf_agent, trimap_agent, bg_color=None, chunk=64, out_alpha=None, out_trimap=None):
+    """BASELINE config 1: ColorFilteringAgent.forward(iters=0) then TrimapAgent.forward(alpha, frame, bg colour) for every
+    frame, chunk by chunk.  Chunks bound the temporaries (about 12 bytes per pixel and frame); make them as large as memory
+    allows: 300 x 1080p takes 4.1 ms in chunks of 30, 3.6 ms in chunks of 100, 3.4 ms in one piece (launch gaps and the
+    partial last wave of every kernel).  Returns alpha, trimap."""
+    n, h, w, _ = frames.shape
+    dev = frames.device
+    alpha = out_alpha if out_alpha is not None else torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    tri = out_trimap if out_trimap is not None else torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+    if bg_color is None:
+        bg_color = cf_agent.bg_color_bgr()
+    for s, e in _chunks(n, chunk):
+        a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
+        trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
+    return alpha, tri
+
+
+def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=64, out=None):
     """color_correct (imgprocess.py:263-300) over a clip, chunk by chunk (``out`` must not alias ``alpha``)."""
     from .unscreen.utils.imgprocess import get_target_size
     n, h, w, _ = frames.shape
@@ -135,7 +152,7 @@ def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0
     return out
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=16, bg_color=None, bg_tile=None, color_correct=False):
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
     stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
     [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.
@@ -176,7 +193,7 @@ def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None):
     return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg)
 
 
-def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=16):
+def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24):
     """bg_step: exact temporal-median background, then per frame the difference
     gate (bg_offline.py:154-160), mask-only trimap (:166) and get_fg with the
     alpha==0 patch (:171-172), CNN stage skipped (alpha := gated mask).
@@ -202,7 +219,7 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=16):
 BGSTEP_HALO = 24   # full-resolution rows: 6 working-resolution rows at 1/4 scale (r=5 diamond + one bilinear tap); covers dilate(4,2)
 
 
-def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=16, scale=4):
+def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24, scale=4):
     """bgstep_clip on this rank's ROW TILE of the clip (BASELINE config 5: spatial-tile sharding):
     the temporal median of the tile's rows (every pixel is independent), then the per-frame stages on the tile plus a
     halo of BGSTEP_HALO rows read from the local frames, cropped back.  ``frames`` / ``masks`` are the WHOLE frames here
