@@ -286,6 +286,12 @@ int vu_temporal_median_u8_ws(const uint8_t* frames, int n, int64_t m, uint8_t* o
  * bg_out[h*w*3], mask_always_out[h*w] (255 where count <= min_count). */
 int vu_masked_temporal_mean(const uint8_t* frames, const uint8_t* masks, int n, int64_t npix, int min_count,
                             uint8_t* bg_out, uint8_t* mask_always_out, vu_stream_t stream);
+/* The same from the RAW masks, with dilate_mask(mask, 3, 2) (bg_offline.py:116)
+ * fused in as two bit-plane dilations: the dilated masks never exist.
+ * w % 16 == 0 and 16-byte aligned pointers, else VU_ERR_UNSUPPORTED (dilate with
+ * vu_morph_u8, then vu_masked_temporal_mean). */
+int vu_masked_temporal_mean_dilate32(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int min_count,
+                                     uint8_t* bg_out, uint8_t* mask_always_out, vu_stream_t stream);
 
 #ifdef __cplusplus
 }

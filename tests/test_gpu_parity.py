@@ -570,3 +570,22 @@ def test_color_correct_golden(vu, golden):
             for i in range(2):
                 got = vu.U.color_correct(g["cc_frames"][i], g["cc_alpha"][i], col, target_long_side=int(L))
                 assert np.array_equal(got, g[f"cc_{ci}_{int(L)}_{i}"]), (ci, int(L), i)
+
+
+@pytest.mark.parametrize("n,h,w", [(7, 40, 64), (24, 33, 272), (5, 16, 128), (12, 50, 400), (9, 21, 16)])
+def test_masked_mean_fused_dilation(vu, n, h, w):
+    """the masked temporal mean with dilate_mask(mask, 3, 2) fused in as bit-plane logic (vu_masked_temporal_mean_dilate32)
+    against the oracle (dilate, then mean) and against the unfused kernels: grey masks with values around both thresholds
+    (250, 255), features on tile borders and image borders."""
+    rng = np.random.default_rng(n * h + w)
+    frames = rng.integers(0, 256, (n, h, w, 3), dtype=np.uint8)
+    masks = rng.choice(np.array([0, 0, 0, 0, 0, 0, 0, 120, 249, 250, 254, 255, 255], np.uint8), size=(n, h, w))
+    masks[:, :, ::37] = 0
+    masks[:, 0, :] = np.where(rng.random((n, w)) < 0.3, 255, 0)
+    masks[:, :, w - 1] = np.where(rng.random((n, h)) < 0.3, 255, 0)
+    masks[0] = 255
+    want_bg, want_always = R.masked_temporal_mean(frames, masks, min_count=2)
+    bg, always = vu.ops.masked_temporal_mean_raw(dev(frames), dev(masks), 3, 2, 2)
+    assert np.array_equal(host(bg), want_bg) and np.array_equal(host(always), want_always)
+    bg2, always2 = vu.ops.masked_temporal_mean(dev(frames), vu.ops.dilate(dev(masks), 3, 2), 2)
+    assert np.array_equal(host(bg), host(bg2)) and np.array_equal(host(always), host(always2))

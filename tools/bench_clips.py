@@ -209,8 +209,7 @@ def main():
         res = [None]
 
         def step():
-            md = ops.dilate(masks, 3, 2)                       # bg_offline.py:116
-            res[0] = ops.masked_temporal_mean(fr, md, 10)      # :117-125
+            res[0] = ops.masked_temporal_mean_raw(fr, masks, 3, 2, 10)   # bg_offline.py:116-125, the dilation fused in
         ms, launches = timed(step, args.steps)
         rows = 64
         t0 = time.perf_counter()

@@ -86,6 +86,7 @@ SIGNATURES = {
     "vu_temporal_median_workspace_bytes": (ctypes.c_size_t, [_i, _i64]),
     "vu_temporal_median_u8_ws": (_i, [_p, _i, _i64, _p, _p, ctypes.c_size_t, _p]),
     "vu_masked_temporal_mean": (_i, [_p, _p, _i, _i64, _i, _p, _p, _p]),
+    "vu_masked_temporal_mean_dilate32": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
 }
 
 

@@ -338,6 +338,152 @@ __global__ void __launch_bounds__(TT) masked_mean16_kernel(const uint4* __restri
   }
 }
 
+// The masked mean with the masks' dilate_mask(mask, 3, 2) (bg_offline.py:116) fused in.  The mean only asks two yes/no
+// questions of a dilated mask value d: d == 255 (the frame is dropped) and d < 250 (the pixel counts).  A grey-scale
+// dilation commutes with thresholds - max(taps) >= T  <=>  any tap >= T - so instead of dilating bytes the kernel
+// thresholds the raw mask to two bit planes (m == 255, m >= 250) and dilates THOSE, 32 pixels per instruction: two
+// passes of the 3x3 cross in shared memory, taps outside the image contributing nothing.  The dilated
+// masks never exist.  A CTA owns a tile of 128 x 16 pixels and walks through the frames; a thread owns 8 pixels of the
+// tile and (200 of the 256 threads) one 16-pixel chunk of the staged mask (tile + halo).  The mask chunk of frame f + 1
+// is requested as soon as that of frame f is thresholded, the frame pixels of f + 1 as soon as those of f are
+// accumulated: both have the other half of an iteration to arrive.
+constexpr int MD_TW = 128, MD_TH = 16, MD_HX = 16, MD_HY = 2;
+constexpr int MD_ROWS = MD_TH + 2 * MD_HY;              // 20 staged rows
+constexpr int MD_CHUNKS = (MD_TW + 2 * MD_HX) / 16;     // 10 staged 16-pixel chunks per row
+constexpr int MD_WORDS = MD_CHUNKS / 2;                 // 5 words of 32 pixels
+constexpr int MD_PITCH = MD_WORDS + 1;
+static_assert(MD_ROWS * MD_CHUNKS <= 256, "one staged chunk per thread");
+
+// bit 7 of every byte of t -> a nibble
+__device__ __forceinline__ unsigned md_nibble(unsigned t) { return ((((t >> 7) & 0x01010101u) * 0x01020408u) >> 24) & 15u; }
+
+constexpr int MD_FPI = 6;   // frames per iteration (and per pair of barriers)
+
+__global__ void __launch_bounds__(256, 2) masked_mean_dilate_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int n, int h,
+                                                                  int w, int min_count, uint8_t* __restrict__ bg_out,
+                                                                  uint8_t* __restrict__ always_out) {
+  // [stage: thresholded / dilated][frame of the iteration][plane][row][word]; plane 0: m == 255, plane 1: m >= 250
+  __shared__ unsigned bits[2][MD_FPI][2][MD_ROWS][MD_PITCH];
+  const int t = threadIdx.x;
+  const int x0 = blockIdx.x * MD_TW, y0 = blockIdx.y * MD_TH;
+  const int64_t npix = (int64_t)h * w;
+  // own pixels: 8 of them
+  const int ty = t >> 4, cx = t & 15;
+  const int oy = y0 + ty, ox = x0 + 8 * cx;
+  const bool own = oy < h && ox < w;
+  // staged chunk
+  const bool sval = t < MD_ROWS * MD_CHUNKS;
+  const int sr = t / MD_CHUNKS, sc = t % MD_CHUNKS;
+  const int gy = y0 - MD_HY + sr, gx = x0 - MD_HX + 16 * sc;
+  const bool sin = sval && gy >= 0 && gy < h && gx >= 0 && gx < w;
+  const uint8_t* mp = masks + (int64_t)gy * w + gx;
+  const uint8_t* fp = frames + ((int64_t)oy * w + ox) * 3;
+  unsigned sum[24], cnt[8];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) sum[i] = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cnt[i] = 0;
+  uint4 cm[MD_FPI];
+  uint2 cf[MD_FPI][3];
+  // a frame past the end of the clip behaves like a mask of 255 everywhere: dropped and not counted; chunks outside
+  // the image are 0 everywhere: they add nothing to a dilation
+  auto fetch_masks = [&](int f0) {
+#pragma unroll
+    for (int u = 0; u < MD_FPI; ++u) {
+      if (f0 + u >= n) cm[u] = make_uint4(~0u, ~0u, ~0u, ~0u);
+      else if (sin) cm[u] = ldg_stream16(mp + (int64_t)(f0 + u) * npix);
+      else cm[u] = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  auto fetch_frames = [&](int f0) {
+#pragma unroll
+    for (int u = 0; u < MD_FPI; ++u)
+      if (own && f0 + u < n) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) cf[u][k] = __ldg(reinterpret_cast<const uint2*>(fp + (int64_t)(f0 + u) * npix * 3) + k);
+      }
+  };
+  fetch_masks(0);
+  fetch_frames(0);
+  for (int f0 = 0; f0 < n; f0 += MD_FPI) {
+    // threshold the staged chunks to the two planes, 16 bits each
+    if (sval) {
+#pragma unroll
+      for (int u = 0; u < MD_FPI; ++u) {
+        unsigned a = 0, b = 0;
+        const unsigned ws[4] = {cm[u].x, cm[u].y, cm[u].z, cm[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const unsigned x = ws[q], lo7 = x & 0x7F7F7F7Fu;
+          a |= md_nibble((lo7 + 0x01010101u) & x) << (4 * q);     // byte == 255: bit 7 set and the low 7 bits carry
+          b |= md_nibble((lo7 + 0x06060606u) & x) << (4 * q);     // byte >= 250
+        }
+        reinterpret_cast<unsigned short*>(bits[0][u][0][sr])[sc] = (unsigned short)a;
+        reinterpret_cast<unsigned short*>(bits[0][u][1][sr])[sc] = (unsigned short)b;
+      }
+    }
+    if (f0 + MD_FPI < n) fetch_masks(f0 + MD_FPI);
+    __syncthreads();
+    // two passes of the 3x3 cross at once: the radius-2 diamond, 13 taps (equal to the two passes also at the image
+    // border: between two pixels of a rectangle at L1 distance 2 there is always an intermediate pixel inside it);
+    // only the tile's own rows are needed
+    for (int it = t; it < MD_FPI * 2 * MD_TH * MD_WORDS; it += 256) {
+      const int dsel = it / (MD_TH * MD_WORDS), di = it % (MD_TH * MD_WORDS);
+      const int dr = MD_HY + di / MD_WORDS, dj = di % MD_WORDS;
+      const unsigned(*src)[MD_PITCH] = bits[0][dsel >> 1][dsel & 1];
+      auto word = [&](int r, int j) -> unsigned { return (unsigned)j < (unsigned)MD_WORDS ? src[r][j] : 0u; };
+      unsigned acc = word(dr - 2, dj) | word(dr + 2, dj);
+#pragma unroll
+      for (int d = -1; d <= 1; ++d) {
+        const unsigned c = word(dr + d, dj), p = word(dr + d, dj - 1), q = word(dr + d, dj + 1);
+        acc |= c | __funnelshift_l(p, c, 1) | __funnelshift_r(c, q, 1);
+        if (d == 0) acc |= __funnelshift_l(p, c, 2) | __funnelshift_r(c, q, 2);
+      }
+      bits[1][dsel >> 1][dsel & 1][dr][dj] = acc;
+    }
+    __syncthreads();
+    if (own) {
+#pragma unroll
+      for (int u = 0; u < MD_FPI; ++u) {
+        const unsigned a = reinterpret_cast<const unsigned char*>(bits[1][u][0][ty + MD_HY])[cx + 2];
+        const unsigned b = reinterpret_cast<const unsigned char*>(bits[1][u][1][ty + MD_HY])[cx + 2];
+        const unsigned* fw = reinterpret_cast<const unsigned*>(cf[u]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const unsigned keep = ((a >> i) & 1u) ^ 1u;              // frame * (1 - dilated // 255)
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int bi = 3 * i + k;
+            sum[bi] += keep ? ((fw[bi >> 2] >> (8 * (bi & 3))) & 255u) : 0u;
+          }
+          cnt[i] += ((b >> i) & 1u) ^ 1u;                          // count += (dilated < 250)
+        }
+      }
+    }
+    if (f0 + MD_FPI < n) fetch_frames(f0 + MD_FPI);
+  }
+  if (!own) return;
+  unsigned ow[6], aw[2] = {0u, 0u};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) ow[k] = 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool always = cnt[i] <= (unsigned)min_count;
+    const double den = (double)(cnt[i] ? cnt[i] : 1u);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const int b = 3 * i + k;
+      const double q = fmin(fmax(__ddiv_rn((double)sum[b], den), 0.0), 255.0);
+      ow[b >> 2] |= (always ? 0u : (unsigned)(int)q) << (8 * (b & 3));
+    }
+    aw[i >> 2] |= (always ? 255u : 0u) << (8 * (i & 3));
+  }
+  uint2* bo = reinterpret_cast<uint2*>(bg_out + ((int64_t)oy * w + ox) * 3);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) bo[k] = make_uint2(ow[2 * k], ow[2 * k + 1]);
+  *reinterpret_cast<uint2*>(always_out + (int64_t)oy * w + ox) = make_uint2(aw[0], aw[1]);
+}
+
 template <class P, int U>
 int launch_median(const uint8_t* frames, int n, int64_t m, int64_t nseg, uint8_t* out, vu_stream_t stream, const uint8_t* flags = nullptr) {
   static bool configured = false;
@@ -484,6 +630,19 @@ extern "C" int vu_temporal_median_u8_ws(const uint8_t* frames, int n, int64_t m,
     return record_cuda(cudaGetLastError());
   }
   return VU_OK;
+}
+
+extern "C" int vu_masked_temporal_mean_dilate32(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int min_count, uint8_t* bg_out,
+                                                uint8_t* mask_always_out, vu_stream_t stream) {
+  VU_REQUIRE(frames && masks && bg_out && mask_always_out && n >= 1 && h > 0 && w > 0);
+  if (n > 16000000) return VU_ERR_UNSUPPORTED;  // 32-bit sums: 255 * n must fit
+  const void* ptrs[] = {frames, masks, bg_out, mask_always_out};
+  for (const void* p : ptrs)
+    if (reinterpret_cast<uintptr_t>(p) & 15) return VU_ERR_UNSUPPORTED;
+  if (w % 16 != 0 || (h + MD_TH - 1) / MD_TH > 65535) return VU_ERR_UNSUPPORTED;
+  dim3 grid((w + MD_TW - 1) / MD_TW, (h + MD_TH - 1) / MD_TH);
+  masked_mean_dilate_kernel<<<grid, 256, 0, S(stream)>>>(frames, masks, n, h, w, min_count, bg_out, mask_always_out);
+  VU_RETURN_LAUNCH();
 }
 
 extern "C" int vu_masked_temporal_mean(const uint8_t* frames, const uint8_t* masks, int n, int64_t npix, int min_count, uint8_t* bg_out,

@@ -546,6 +546,21 @@ def masked_temporal_mean(frames, masks_dilated, min_count=10):
     return bg, always
 
 
+def masked_temporal_mean_raw(frames, masks, ksize=3, iters=2, min_count=10):
+    """bg_offline.py:106-125 from the raw masks: dilate_mask(mask, ksize, iters) then the masked mean; for the script's
+    (3, 2) the dilation is fused into the mean as bit-plane logic (vu_masked_temporal_mean_dilate32)."""
+    frames, masks = _img(frames), _mask(masks)
+    n, h, w, _ = frames.shape
+    if (ksize, iters) == (3, 2):
+        bg = torch.empty((h, w, 3), dtype=u8, device=frames.device)
+        always = torch.empty((h, w), dtype=u8, device=frames.device)
+        rc = lib().vu_masked_temporal_mean_dilate32(_p(frames), _p(masks), n, h, w, int(min_count), _p(bg), _p(always), _stream())
+        if rc != _lib.ERR_UNSUPPORTED:
+            check(rc)
+            return bg, always
+    return masked_temporal_mean(frames, dilate(masks, ksize, iters), min_count)
+
+
 # ---- per-frame branches on the device (batched clips) --------------------------------
 
 def cf_samples(hsv_lo, mask_lo, mask_op, max_samples, prior=None, invert=False):

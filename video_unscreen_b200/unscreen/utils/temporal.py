@@ -21,8 +21,7 @@ def masked_temporal_mean(frames, masks, ksize=3, iters=2, min_count=10):
     (bg_always[H,W,3], mask_always[H,W]); the TELEA inpaint of :127-129 is out of scope."""
     f, as_np = to_dev(frames)
     m, _ = to_dev(masks)
-    md = ops.dilate(m, ksize, iters)
-    bg, always = ops.masked_temporal_mean(f, md, min_count)
+    bg, always = ops.masked_temporal_mean_raw(f, m, ksize, iters, min_count)
     return back(bg, as_np), back(always, as_np)
 
 
