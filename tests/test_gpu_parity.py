@@ -589,3 +589,35 @@ def test_masked_mean_fused_dilation(vu, n, h, w):
     assert np.array_equal(host(bg), want_bg) and np.array_equal(host(always), want_always)
     bg2, always2 = vu.ops.masked_temporal_mean(dev(frames), vu.ops.dilate(dev(masks), 3, 2), 2)
     assert np.array_equal(host(bg), host(bg2)) and np.array_equal(host(always), host(always2))
+
+
+def test_replace_geometry_full_size(vu):
+    """shift_fg / rescale_fg at BASELINE config 4's frame size (1080p): identities (a zero shift and a unit scale return
+    the clip), an integer shift and its inverse restore everything that stayed inside the frame, and one whole frame of
+    each against the oracle."""
+    from video_unscreen_b200 import synth
+    frames, _ = synth.green_clip(3, 1080, 1920, seed=21)
+    d = dev(frames)
+    assert torch.equal(vu.ops.shift(d, 0, 0, 3), d)
+    assert torch.equal(vu.ops.rescale_cubic(d, 1.0, 3), d)
+    back = vu.ops.shift(vu.ops.shift(d, 37, -21, 3), -37, 21, 3)
+    # dx = 37 moves the content right, dy = -21 moves it up: the rows below 21 and the columns from 1920 - 37 on left the frame
+    assert torch.equal(back[:, 21:, : 1920 - 37], d[:, 21:, : 1920 - 37])
+    assert not bool(back[:, :21].any()) and not bool(back[:, :, 1920 - 37:].any())          # ... and came back as border
+    assert np.array_equal(host(vu.ops.shift(d[:1], 0.5, 0.5, 3))[0], M.warp_translate(frames[0], 0.5, 0.5))
+    assert np.array_equal(host(vu.ops.rescale_cubic(d[1:2], 1.2, 3))[0], M.resize_cubic_crop(frames[1], 1.2))
+
+
+@pytest.mark.parametrize("h,w", [(1080, 1920), (2160, 3840)])
+def test_color_correct_full_size(vu, h, w):
+    """color_correct at the two BASELINE frame sizes (working resolution 540 x 960: the fused 2x and 4x down-scale
+    kernels) against the oracle, one frame each, plus the property that the result never exceeds alpha."""
+    from video_unscreen_b200 import synth
+    frames, segs = synth.green_clip(2, h, w, seed=h)
+    rng = np.random.default_rng(h)
+    alpha = np.minimum(segs, rng.integers(100, 256, segs.shape).astype(np.uint8))
+    col = np.array([60, 200, 40], np.uint8)
+    th, tw = R.get_target_size(h, w, 960)
+    got = host(vu.ops.color_correct(dev(frames), dev(alpha), col, th, tw))
+    assert np.array_equal(got[1], R.color_correct(frames[1], alpha[1], col))
+    assert bool((got <= alpha).all())
