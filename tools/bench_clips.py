@@ -72,6 +72,7 @@ def report(name, desc, frames, ms, launches, algo_bytes, cpu_fps, cpu_note, peak
 
 def main():
     chunk4k = int(os.environ.get("VU_CHUNK4K", "24"))   # frames per chunk of the 4K pipelines
+    streams = int(os.environ.get("VU_STREAMS", "2"))     # chunks overlap on this many streams
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--only", default="")
@@ -91,10 +92,10 @@ def main():
         alpha = torch.empty((n, h, w), dtype=torch.uint8, device="cuda")
         tri = torch.empty_like(alpha)
 
-        chunk = int(os.environ.get("VU_CHUNK", "100"))
+        chunk = int(os.environ.get("VU_CHUNK", "50"))
 
         def step():
-            clip.cf_trimap_clip(fr, sg, cf, ta, col, chunk=chunk, out_alpha=alpha, out_trimap=tri)
+            clip.cf_trimap_clip(fr, sg, cf, ta, col, chunk=chunk, out_alpha=alpha, out_trimap=tri, streams=streams)
         ms, launches = timed(step, args.steps)
         lb, lf, bgh = cf.tables()
         t0 = time.perf_counter()
@@ -115,9 +116,9 @@ def main():
         tile = torch.from_numpy(np.tile(col, (1, 4, 1))).cuda()
 
         def step():
-            return clip.green_clip(fr, sg, cf, ta, chunk=chunk4k, bg_color=col, bg_tile=tile)
+            return clip.green_clip(fr, sg, cf, ta, chunk=chunk4k, bg_color=col, bg_tile=tile, streams=streams)
         ms, launches = timed(step, max(2, args.steps // 2), warmup=1)
-        a_d, t_d, f_d, b_d = [x[1].cpu().numpy() for x in (step() if not GRAPH else clip.green_clip(fr, sg, cf, ta, chunk=chunk4k, bg_color=col, bg_tile=tile))]
+        a_d, t_d, f_d, b_d = [x[1].cpu().numpy() for x in (step() if not GRAPH else clip.green_clip(fr, sg, cf, ta, chunk=chunk4k, bg_color=col, bg_tile=tile, streams=streams))]
         lb, lf, bgh = cf.tables()
         t0 = time.perf_counter()
         a_o, _, _ = R.cf_forward_predict(fr_h[1], sg_h[1], lb, lf, bgh, 960)
@@ -188,7 +189,7 @@ def main():
         out = [None]
 
         def step():
-            out[0] = clip.color_correct_clip(fr, al, col, chunk=120)
+            out[0] = clip.color_correct_clip(fr, al, col, chunk=int(os.environ.get("VU_CHUNK", "60")), streams=streams)
         ms, launches = timed(step, args.steps)
         f0, a0 = fr[0].cpu().numpy(), al[0].cpu().numpy()
         t0 = time.perf_counter()
@@ -230,9 +231,9 @@ def main():
                              for t in range(n)])
 
         def step():
-            return clip.bgstep_clip(fr, masks, ta, chunk=chunk4k)
+            return clip.bgstep_clip(fr, masks, ta, chunk=chunk4k, streams=streams)
         ms, launches = timed(step, max(2, args.steps // 2), warmup=1)
-        bg_d, a_d, t_d, f_d = clip.bgstep_clip(fr, masks, ta, chunk=chunk4k)
+        bg_d, a_d, t_d, f_d = clip.bgstep_clip(fr, masks, ta, chunk=chunk4k, streams=streams)
         i = n // 2
         frame_h, mask_h, bg_h = fr[i].cpu().numpy(), masks[i].cpu().numpy(), bg_d.cpu().numpy()
         rows = 64                                             # the oracle median on a strip, scaled (np.partition over 120 frames)

@@ -40,6 +40,37 @@ def _chunks(n, chunk):
         yield s, min(n, s + chunk)
 
 
+_SIDE_STREAMS = {}
+
+
+def _overlap_chunks(n, chunk, body, streams=2):
+    """``body(s, e)`` for every chunk [s, e) of n frames.  The chunks of these pipelines are independent, so with
+    ``streams`` > 1 consecutive chunks go to alternating side streams: the partial last waves and launch gaps of one
+    chunk's kernels are filled by the next chunk's.  Inputs must be ready on the current stream; everything the bodies
+    wrote is ready on it at return.  Sequential while a CUDA graph is being captured."""
+    spans = list(_chunks(n, chunk))
+    if streams <= 1 or len(spans) <= 1 or torch.cuda.is_current_stream_capturing():
+        for s, e in spans:
+            body(s, e)
+        return
+    cur = torch.cuda.current_stream()
+    key = (cur.device, streams)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=cur.device) for _ in range(streams)]
+    pool = _SIDE_STREAMS[key][:min(streams, len(spans))]
+    ready = torch.cuda.Event()
+    ready.record(cur)
+    for st in pool:
+        st.wait_event(ready)
+    for i, (s, e) in enumerate(spans):
+        with torch.cuda.stream(pool[i % len(pool)]):
+            body(s, e)
+    for st in pool:
+        done = torch.cuda.Event()
+        done.record(st)
+        cur.wait_event(done)
+
+
 def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None):
     """ColorFilteringAgent.forward(frame, mask, iters=0) for every frame of
     frames[N,H,W,3] / segmasks[N,H,W] with the agent's current mixtures
@@ -123,36 +154,38 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None):
     return tri
 
 
-def cf_trimap_clip(frames, segmasks, cf_agent, trimap_agent, bg_color=None, chunk=64, out_alpha=None, out_trimap=None):
+def cf_trimap_clip(frames, segmasks, cf_agent, trimap_agent, bg_color=None, chunk=50, out_alpha=None, out_trimap=None, streams=2):
     """BASELINE config 1: ColorFilteringAgent.forward(iters=0) then TrimapAgent.forward(alpha, frame, bg colour) for every
     frame, chunk by chunk.  Chunks bound the temporaries (about 12 bytes per pixel and frame); make them as large as memory
     allows: 300 x 1080p takes 4.1 ms in chunks of 30, 3.6 ms in chunks of 100, 3.4 ms in one piece (launch gaps and the
-    partial last wave of every kernel).  Returns alpha, trimap."""
+    partial last wave of every kernel); with ``streams`` = 2 consecutive chunks overlap on two streams and fill each
+    other's gaps: 3.05 ms in chunks of 50.  Returns alpha, trimap."""
     n, h, w, _ = frames.shape
     dev = frames.device
     alpha = out_alpha if out_alpha is not None else torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     tri = out_trimap if out_trimap is not None else torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     if bg_color is None:
         bg_color = cf_agent.bg_color_bgr()
-    for s, e in _chunks(n, chunk):
+    def body(s, e):
         a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
         trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
+    cf_agent.tables_dev(), cf_agent.lut3d_dev()      # built (once) on the current stream, not on a side stream
+    _overlap_chunks(n, chunk, body, streams)
     return alpha, tri
 
 
-def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=64, out=None):
+def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0.95, chunk=64, out=None, streams=2):
     """color_correct (imgprocess.py:263-300) over a clip, chunk by chunk (``out`` must not alias ``alpha``)."""
     from .unscreen.utils.imgprocess import get_target_size
     n, h, w, _ = frames.shape
     th, tw = get_target_size(h, w, target_long_side)
     if out is None:
         out = torch.empty_like(alpha)
-    for s, e in _chunks(n, chunk):
-        ops.color_correct(frames[s:e], alpha[s:e], bg_color, th, tw, mean_exp, out=out[s:e])
+    _overlap_chunks(n, chunk, lambda s, e: ops.color_correct(frames[s:e], alpha[s:e], bg_color, th, tw, mean_exp, out=out[s:e]), streams)
     return out
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False):
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
     stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
     [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.
@@ -169,20 +202,23 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None
         bg_color = cf_agent.bg_color_bgr()
     if bg_tile is None:
         bg_tile = torch.from_numpy(np.tile(bg_color, (1, 4, 1))).to(dev)     # constant background: a 4-pixel periodic image
-    for s, e in _chunks(n, chunk):
+    def body(s, e):
         # every stage writes straight into its slice of the clip-sized results
         a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
         trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
         if color_correct:
             a = color_correct_clip(frames[s:e], a.clone(), bg_color, chunk=chunk, out=alpha[s:e])
         ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True, out=fg[s:e], bg_out=bgo[s:e])
+    cf_agent.tables_dev(), cf_agent.lut3d_dev()      # built (once) on the current stream, not on a side stream
+    _overlap_chunks(n, chunk, body, streams)
     return alpha, tri, fg, bgo
 
 
 def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None):
     """tools/replace/replace.py:69-76 for a whole clip; ``bg`` is [H,W,3] (shared) or [N,H,W,3].  With ``dx``/``dy``
     and/or ``scale`` the foreground and its mask first go through shift_fg / rescale_fg (:69-72) like in the script;
-    without them this is the blend of :74-76 alone (BASELINE config 4)."""
+    without them this is the blend of :74-76 alone (BASELINE config 4).  Whole-clip launches: these kernels fill the
+    machine on their own (chunks on two streams were slower, 2.43 against 2.27 ms per 120 frames)."""
     ach = 3 if alpha.ndim == fg.ndim else 1
     if dx is not None or dy is not None:
         fg = ops.shift(fg, dx or 0, dy or 0, 3)
@@ -193,7 +229,7 @@ def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None):
     return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg)
 
 
-def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24):
+def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2):
     """bg_step: exact temporal-median background, then per frame the difference
     gate (bg_offline.py:154-160), mask-only trimap (:166) and get_fg with the
     alpha==0 patch (:171-172), CNN stage skipped (alpha := gated mask).
@@ -204,7 +240,7 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24):
     alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     fg = torch.empty_like(frames)
-    for s, e in _chunks(n, chunk):
+    def body(s, e):
         # every stage writes straight into its slice of the clip-sized results
         if ops.bgdiff_gate_supported(frames[s:e], bg, masks[s:e]):
             a = ops.bgdiff_gate(frames[s:e], bg, masks[s:e], thr, out=alpha[s:e])
@@ -213,6 +249,7 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24):
             alpha[s:e] = a
         trimap_clip(a, trimap_agent, chunk=chunk, out=tri[s:e])
         ops.get_fg(frames[s:e], a, bg, _lib.PATCH_ALPHA_EQ0, out=fg[s:e])
+    _overlap_chunks(n, chunk, body, streams)
     return bg, alpha, tri, fg
 
 

@@ -491,14 +491,14 @@ def get_bg(alpha, bg):
     return out
 
 
-def blend(mode, fg, alpha, bg=None):
+def blend(mode, fg, alpha, bg=None, out=None):
     fg, alpha = _img(fg), _dev(alpha)
     ac = 3 if alpha.shape == fg.shape else 1
     if ac == 1 and alpha.shape != fg.shape[:-1]:
         raise ValueError("alpha must be [N,]H,W or the image's shape")
     if bg is not None:
         bg = _img(bg)
-    out = torch.empty_like(fg)
+    out = _out(out, fg.shape, fg.device)
     check(lib().vu_blend(mode, _p(fg), _p(alpha), ac, _p(bg), fg.numel() // 3, (bg.numel() // 3) if bg is not None else 0, _p(out), _stream()))
     return out
 
