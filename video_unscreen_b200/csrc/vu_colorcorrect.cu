@@ -157,9 +157,9 @@ __global__ void __launch_bounds__(CC_THREADS) cc_lab_dist_lowres_kernel(const ui
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const int bi = 3 * q + c;
-            acc[c] += (fw[bi >> 2] >> (8 * (bi & 3))) & 255;
+            acc[c] = (int)__dp4a(fw[bi >> 2], 1u << (8 * (bi & 3)), (unsigned)acc[c]);   // byte extraction + add on the FMA pipe
           }
-          aacc += (aw[q >> 2] >> (8 * (q & 3))) & 255;
+          aacc = (int)__dp4a(aw[q >> 2], 1u << (8 * (q & 3)), (unsigned)aacc);
         }
       }
       int a, b;

@@ -113,12 +113,17 @@ __device__ __forceinline__ void hsv2bgr_px(int hi, int si, int vi, const HsvTab&
 }
 
 // unpack / pack 4 BGR pixels held in three little-endian words
+// byte k of w on the FMA pipe (IDP.4A with a one-hot selector) instead of the ALU pipe (SHF + LOP3): the per-pixel
+// kernels run the ALU pipe at 85 % and the FMA pipe at 15 % (profiles/r01_cf_lowres2_wide_ncu_keys.txt); moving the
+// byte extraction over took 16 % off cf_lowres2_wide
+__device__ __forceinline__ int byte_fma(unsigned w, int k) { return (int)__dp4a(w, 1u << (8 * k), 0u); }
+
 __device__ __forceinline__ void unpack12(unsigned w0, unsigned w1, unsigned w2, int (&c)[12]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    c[i] = (w0 >> (8 * i)) & 255;
-    c[4 + i] = (w1 >> (8 * i)) & 255;
-    c[8 + i] = (w2 >> (8 * i)) & 255;
+    c[i] = byte_fma(w0, i);
+    c[4 + i] = byte_fma(w1, i);
+    c[8 + i] = byte_fma(w2, i);
   }
 }
 __device__ __forceinline__ void pack12(const int (&c)[12], unsigned& w0, unsigned& w1, unsigned& w2) {

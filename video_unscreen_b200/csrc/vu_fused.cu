@@ -21,6 +21,8 @@
 //                      fuzzy override (:100).
 //  vu_fuzzy_count      is_pixel_inrange (bg colour) + fuzzy area + the two
 //                      counts of trimap/agent.py:90-94 in one pass.
+#include <cstdlib>
+
 #include "vu_common.cuh"
 #include "vu_cross_march.cuh"
 
@@ -454,11 +456,11 @@ __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __re
         for (int k = 0; k < 2; ++k) {
           const int q = 2 * o + k;   // pixel of the 16
           const int b0 = 3 * q, b1 = 3 * q + 1, b2 = 3 * q + 2;
-          const int B = (fw[b0 >> 2] >> (8 * (b0 & 3))) & 255, G = (fw[b1 >> 2] >> (8 * (b1 & 3))) & 255, R = (fw[b2 >> 2] >> (8 * (b2 & 3))) & 255;
+          const int B = byte_fma(fw[b0 >> 2], b0 & 3), G = byte_fma(fw[b1 >> 2], b1 & 3), R = byte_fma(fw[b2 >> 2], b2 & 3);
           int hh, ss, vv;
           bgr2hsv_px(B, G, R, tab, hh, ss, vv);
           acc0 += hh; acc1 += ss; acc2 += vv;
-          macc += (mw[q >> 2] >> (8 * (q & 3))) & 255;
+          if (k == 0) macc = (int)__dp4a(mw[q >> 2], 0x0101u << (8 * (q & 3)), (unsigned)macc);   // both columns of the pair: one word
         }
       }
       const int hh = (acc0 + 2) >> 2, ss = (acc1 + 2) >> 2, vv = (acc2 + 2) >> 2, mm = (macc + 2) >> 2;
@@ -906,8 +908,7 @@ extern "C" int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, 
     e = record_cuda(cudaMemsetAsync(mask_counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
     if (e) return e;
   }
-  if (wide)
-    cf_lowres2_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 8)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st,
+  if (wide) cf_lowres2_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 8)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st,
                                                                                        reinterpret_cast<unsigned long long*>(mask_counts2));
   else if (s == 2) cf_lowres_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 2)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   else cf_lowres_kernel<4><<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(TT) masked_mean16_kernel(const uint4* __restri
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int b = 3 * i + k;
-          sum[b] += ((fw[b >> 2] >> (8 * (b & 3))) & 255u) * keep;
+          sum[b] = __dp4a(fw[b >> 2], keep << (8 * (b & 3)), sum[b]);   // byte * keep + sum: one IDP.4A on the FMA pipe
         }
         cnt[i] += mv < 250u;                          // count += (mask < 250)
       }
@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(256, 2) masked_mean_dilate_kernel(const uint8_
 #pragma unroll
           for (int k = 0; k < 3; ++k) {
             const int bi = 3 * i + k;
-            sum[bi] += keep ? ((fw[bi >> 2] >> (8 * (bi & 3))) & 255u) : 0u;
+            sum[bi] = __dp4a(fw[bi >> 2], keep << (8 * (bi & 3)), sum[bi]);   // byte * keep + sum: one IDP.4A on the FMA pipe
           }
           cnt[i] += ((b >> i) & 1u) ^ 1u;                          // count += (dilated < 250)
         }
