@@ -229,7 +229,7 @@ int vu_cf_alpha_lut3d_u8(const uint8_t* hsv, int64_t npix, const uint8_t* lut3d,
 int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int th, int tw,
                  const uint8_t* lut3d, uint8_t* alpha_lo, uint64_t* stats2, uint64_t* mask_counts2, vu_stream_t stream);
 /* mask_counts2 (nullable): per frame {#(mask > 128), #(mask < 128)}, the early-out counts of agent.py:303-307, taken
- * from the mask bytes this pass reads anyway; only with s == 2, w % 16 == 0 and 16-byte aligned inputs
+ * from the mask bytes this pass reads (at s == 4 it then reads all four rows of the mask); w % 16 == 0 and 16-byte aligned inputs
  * (VU_ERR_UNSUPPORTED otherwise: use vu_count_gt_lt_u8). */
 /* postprocess (:259-283) step 1: per frame sum/count of alpha over
  * (alpha>128 && mask>0) -> stats[i] = {sum, count}; step 2 zeroes alpha below

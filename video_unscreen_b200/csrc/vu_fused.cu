@@ -474,6 +474,78 @@ __global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __re
   if (mcounts2) warp_block_atomic2(mgt, mlt, mcounts2 + 2 * n);
 }
 
+// S = 4 (4K at the default working resolution), 16 full-resolution columns x 4 rows per thread: four outputs, each the
+// rounded mean of the centre 2x2 of its 4x4 block (rows 4y+1, 4y+2, columns 4x+1, 4x+2: what cv2's bilinear comes to at
+// exactly 4x).  Only the two centre rows of the frame are read; with mcounts2 all four rows of the mask
+// are, for the early-out counts of agent.py:303-307.
+__global__ void __launch_bounds__(FT) cf_lowres4_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
+                                                             int tw, const uint8_t* __restrict__ lut3d, uint8_t* __restrict__ alpha_lo,
+                                                             unsigned long long* __restrict__ stats2, unsigned long long* __restrict__ mcounts2) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  const int n = blockIdx.y;
+  const int per_row = tw / 4;
+  const int64_t items = (int64_t)th * per_row;
+  const uint8_t* fr = frames + (int64_t)n * h * w * 3;
+  const uint8_t* mk = masks + (int64_t)n * h * w;
+  uint8_t* out = alpha_lo + (int64_t)n * th * tw;
+  unsigned long long sum = 0, cnt = 0;
+  unsigned mgt = 0, mlt = 0;
+  for (int64_t it = (int64_t)blockIdx.x * FT + threadIdx.x; it < items; it += (int64_t)gridDim.x * FT) {
+    const int y = (int)(it / per_row), xg = (int)(it - (int64_t)y * per_row);
+    uint4 fv[2][3], mv[4];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const uint4* p = reinterpret_cast<const uint4*>(fr + ((int64_t)(4 * y + 1 + r) * w + 16 * xg) * 3);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fv[r][k] = ldg_stream16(p + k);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (mcounts2 || r == 1 || r == 2) mv[r] = ldg_stream16(mk + (int64_t)(4 * y + r) * w + 16 * xg);
+    if (mcounts2) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned ws[4] = {mv[r].x, mv[r].y, mv[r].z, mv[r].w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const unsigned x = ws[k], hi7 = x & 0x80808080u, lo7 = x & 0x7F7F7F7Fu;
+          mgt += __popc(hi7 & (lo7 + 0x7F7F7F7Fu) & 0x80808080u);   // bit 7 set and low 7 bits non-zero: x > 128
+          mlt += 4 - __popc(hi7);                                   // bit 7 clear: x < 128
+        }
+      }
+    }
+    unsigned res = 0u;
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {   // output o: full-resolution columns 4o+1, 4o+2 of rows 4y+1, 4y+2
+      int acc0 = 0, acc1 = 0, acc2 = 0, macc = 0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const unsigned* fw = reinterpret_cast<const unsigned*>(fv[r]);
+        const unsigned* mw = reinterpret_cast<const unsigned*>(&mv[1 + r]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int q = 4 * o + 1 + k;
+          const int b0 = 3 * q, b1 = 3 * q + 1, b2 = 3 * q + 2;
+          const int B = byte_fma(fw[b0 >> 2], b0 & 3), G = byte_fma(fw[b1 >> 2], b1 & 3), R = byte_fma(fw[b2 >> 2], b2 & 3);
+          int hh, ss, vv;
+          bgr2hsv_px(B, G, R, tab, hh, ss, vv);
+          acc0 += hh; acc1 += ss; acc2 += vv;
+        }
+        macc = (int)__dp4a(mw[o], 0x00010100u, (unsigned)macc);   // bytes 1 and 2 of the block's mask word
+      }
+      const int hh = (acc0 + 2) >> 2, ss = (acc1 + 2) >> 2, vv = (acc2 + 2) >> 2, mm = (macc + 2) >> 2;
+      const unsigned a = __ldg(lut3d + ((hh << 16) | (ss << 8) | vv));
+      if (a > 128 && mm > 0) { sum += a; ++cnt; }
+      res |= a << (8 * o);
+    }
+    *reinterpret_cast<unsigned*>(out + (int64_t)y * tw + 4 * xg) = res;
+  }
+  warp_block_atomic2(sum, cnt, stats2 + 2 * n);
+  if (mcounts2) warp_block_atomic2(mgt, mlt, mcounts2 + 2 * n);
+}
+
 struct AxisC {
   int i0, i1, w0, w1;
 };
@@ -903,13 +975,17 @@ extern "C" int vu_cf_lowres(const uint8_t* frames, const uint8_t* masks, int n, 
   auto* st = reinterpret_cast<unsigned long long*>(stats2);
   const bool wide = s == 2 && (w % 16 == 0) && (tw % 8 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && ((reinterpret_cast<uintptr_t>(alpha_lo) & 7) == 0);
-  if (mask_counts2) {   // only the 16-column kernel sees every mask byte
-    if (!wide) return VU_ERR_UNSUPPORTED;
+  const bool wide4 = s == 4 && (w % 16 == 0) && (tw % 4 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(masks) & 15) == 0) && ((reinterpret_cast<uintptr_t>(alpha_lo) & 3) == 0);
+  if (mask_counts2) {   // only the 16-column kernels see every mask byte
+    if (!wide && !wide4) return VU_ERR_UNSUPPORTED;
     e = record_cuda(cudaMemsetAsync(mask_counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
     if (e) return e;
   }
   if (wide) cf_lowres2_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 8)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st,
                                                                                        reinterpret_cast<unsigned long long*>(mask_counts2));
+  else if (wide4) cf_lowres4_wide_kernel<<<frame_grid(n, (int64_t)th * (tw / 4)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st,
+                                                                                             reinterpret_cast<unsigned long long*>(mask_counts2));
   else if (s == 2) cf_lowres_kernel<2><<<frame_grid(n, (int64_t)th * (tw / 2)), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   else cf_lowres_kernel<4><<<frame_grid(n, (int64_t)th * tw), FT, 0, S(stream)>>>(frames, masks, h, w, th, tw, lut3d, alpha_lo, st);
   VU_RETURN_LAUNCH();

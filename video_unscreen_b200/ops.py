@@ -223,7 +223,8 @@ def cf_lowres(frames, masks, th, tw, lut3d, want_mask_counts=False):
 
 def cf_lowres_counts_supported(frames, masks, th, tw):
     h, w = frames.shape[-3:-1]
-    return h == 2 * th and w == 2 * tw and w % 16 == 0 and tw % 8 == 0 and frames.data_ptr() % 16 == 0 and masks.data_ptr() % 16 == 0
+    exact = (h == 2 * th and w == 2 * tw and tw % 8 == 0) or (h == 4 * th and w == 4 * tw and tw % 4 == 0)
+    return exact and w % 16 == 0 and frames.data_ptr() % 16 == 0 and masks.data_ptr() % 16 == 0
 
 
 def degenerate_flags_from_counts(counts2, fg_min, bg_min):
