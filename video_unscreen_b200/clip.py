@@ -71,7 +71,7 @@ def _overlap_chunks(n, chunk, body, streams=2):
         cur.wait_event(done)
 
 
-def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None):
+def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None, streams=2):
     """ColorFilteringAgent.forward(frame, mask, iters=0) for every frame of
     frames[N,H,W,3] / segmasks[N,H,W] with the agent's current mixtures
     (reference colorfiltering/agent.py:285-354, predict-only branch :319-321).
@@ -82,7 +82,8 @@ def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None):
     lut3d = agent.lut3d_dev()
     alpha = out if out is not None else torch.empty((n, h, w), dtype=torch.uint8, device=frames.device)
     fg_min, bg_min = max(agent.fg_ncomp) * 5, max(agent.bg_ncomp) * 5
-    for s, e in _chunks(n, chunk):
+
+    def body(s, e):
         fr, sm = frames[s:e], segmasks[s:e]
         if ops.cf_lowres_supported(h, w, th, tw):
             # one pass over the frames (the early-out counts of the masks ride along where the pass sees every mask
@@ -100,6 +101,7 @@ def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None):
             a_lo = ops.cf_postprocess(ops.cf_alpha_lut3d(hsv_lo, lut3d), ops.resize_linear_mask(sm, th, tw), 0.8)
         # degenerate masks are returned as they came (agent.py:303-307): alt_src / alt_flags
         ops.resize_up(a_lo, h, w, alt_src=sm, alt_flags=flags, out=alpha[s:e])
+    _overlap_chunks(n, chunk, body, streams)
     return alpha
 
 
@@ -126,7 +128,7 @@ def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None):
     return ops.resize_up(tri, h, w, mode=1, fuzzy=fuzzy, flags=flags, out=out)
 
 
-def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None):
+def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None, streams=2):
     """TrimapAgent.forward for every frame: mask-only (trimap/agent.py:35-61) or,
     with ``frames`` and ``bg`` ((3,) colour or [H,W,3] / [N,H,W,3] image), the
     background-gated variant (:63-101) with its per-frame ratio test decided on
@@ -134,11 +136,12 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None):
     n, h, w = masks.shape
     tri = out if out is not None else torch.empty((n, h, w), dtype=torch.uint8, device=masks.device)
     half = np.array(agent.color_winsize) // 2
-    for s, e in _chunks(n, chunk):
+
+    def body(s, e):
         m = masks[s:e]
         if frames is None:
             _trimap_tail(m, agent, out=tri[s:e])
-            continue
+            return
         fr = frames[s:e]
         if isinstance(bg, np.ndarray) and bg.ndim == 1:
             hsv = bgr2hsv_pixel(bg)
@@ -151,6 +154,7 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None):
         flags = ops.ratio_flags(counts, 0.1)       # 0: ensemble, 1: trust mask, 2: empty mask
         # an empty mask is returned as is (all zeros); the plain branch of an all-zero mask is all zeros too
         _trimap_tail(m, agent, fuzzy, flags, out=tri[s:e])
+    _overlap_chunks(n, chunk, body, streams)
     return tri
 
 
