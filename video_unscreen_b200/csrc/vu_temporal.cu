@@ -385,6 +385,10 @@ __global__ void __launch_bounds__(256, 2) masked_mean_dilate_kernel(const uint8_
   for (int i = 0; i < 8; ++i) cnt[i] = 0;
   uint4 cm[MD_FPI];
   uint2 cf[MD_FPI][3];
+#pragma unroll
+  for (int u = 0; u < MD_FPI; ++u)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cf[u][k] = make_uint2(0u, 0u);   // padding frames are added and taken back out: any value, but a defined one
   // a frame past the end of the clip behaves like a mask of 255 everywhere: dropped and not counted; chunks outside
   // the image are 0 everywhere: they add nothing to a dilation
   auto fetch_masks = [&](int f0) {
@@ -448,15 +452,23 @@ __global__ void __launch_bounds__(256, 2) masked_mean_dilate_kernel(const uint8_
         const unsigned a = reinterpret_cast<const unsigned char*>(bits[1][u][0][ty + MD_HY])[cx + 2];
         const unsigned b = reinterpret_cast<const unsigned char*>(bits[1][u][1][ty + MD_HY])[cx + 2];
         const unsigned* fw = reinterpret_cast<const unsigned*>(cf[u]);
+        // every byte is summed and every pixel counted (one IDP.4A with a constant selector each: FMA pipe, nothing on
+        // the ALU pipe) ...
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const unsigned keep = ((a >> i) & 1u) ^ 1u;              // frame * (1 - dilated // 255)
+        for (int bi = 0; bi < 24; ++bi) sum[bi] = __dp4a(fw[bi >> 2], 1u << (8 * (bi & 3)), sum[bi]);
+        // ... and the masked pixels - few - are taken back out: frame * (1 - dilated // 255), count += (dilated < 250)
+        if (a | b) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            const int bi = 3 * i + k;
-            sum[bi] = __dp4a(fw[bi >> 2], keep << (8 * (bi & 3)), sum[bi]);   // byte * keep + sum: one IDP.4A on the FMA pipe
+          for (int i = 0; i < 8; ++i) {
+            if ((a >> i) & 1u) {
+#pragma unroll
+              for (int k = 0; k < 3; ++k) {
+                const int bi = 3 * i + k;
+                sum[bi] -= (fw[bi >> 2] >> (8 * (bi & 3))) & 255u;
+              }
+            }
+            cnt[i] += (b >> i) & 1u;                               // here: the frames that do NOT count
           }
-          cnt[i] += ((b >> i) & 1u) ^ 1u;                          // count += (dilated < 250)
         }
       }
     }
@@ -466,10 +478,12 @@ __global__ void __launch_bounds__(256, 2) masked_mean_dilate_kernel(const uint8_
   unsigned ow[6], aw[2] = {0u, 0u};
 #pragma unroll
   for (int k = 0; k < 6; ++k) ow[k] = 0u;
+  const unsigned walked = (unsigned)((n + MD_FPI - 1) / MD_FPI * MD_FPI);   // frames of the walk, the padding ones included (never counted)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const bool always = cnt[i] <= (unsigned)min_count;
-    const double den = (double)(cnt[i] ? cnt[i] : 1u);
+    const unsigned c = walked - cnt[i];
+    const bool always = c <= (unsigned)min_count;
+    const double den = (double)(c ? c : 1u);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const int b = 3 * i + k;
