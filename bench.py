@@ -14,6 +14,13 @@ host memory (H2D of the clip and D2H of the background inside the timed
 region); `roofline` = algorithmic bytes of the dominant kernel / its CUDA-event
 duration against the measured HBM copy bandwidth; `cpu_baseline` = the oracle
 port on this box's host cores over a bounded sample.
+
+The same line carries `configs`: one block per BASELINE.json config (frames/s,
+roofline, cpu_baseline, e2e, bit-exact check; tools/bench_configs.py), sharded
+the way north_star names when run under torchrun (frame ranges for the
+per-frame configs, row tiles of ONE 4K clip for bg_step: "scaling": "strong"),
+`roofline_worst_case` (the median on uniform-random bytes) and `per_frame` (the
+reference's per-frame numpy API).  `--configs none` skips them.
 """
 import argparse
 import json
@@ -77,6 +84,31 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def config_dict(args, wl):
+    """identical in both arms (the driver compares them)"""
+    n, h, w, desc = wl
+    return {"workload": args.workload, "description": desc, "frames": n, "height": h, "width": w}
+
+
+def pin_to_gpu_cpus(index):
+    """bind this rank to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer is allocated, so the
+    staging memory of the e2e path sits on the GPU's NUMA node.  Returns what was done (for the bench line)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if want and want != allowed:
+            os.sched_setaffinity(0, want)
+            return {"pinned": True, "cpus": len(want), "of_allowed": len(allowed)}
+        return {"pinned": False, "cpus": len(allowed), "why": "the GPU's CPU set already equals the allowed set" if want else "no overlap"}
+    except Exception as ex:
+        return {"pinned": False, "why": str(ex)[:80]}
+
+
 def cpu_median_sample(frames_host, rows, threads):
     """oracle median (oracle.refport.temporal_median == np.median(...).astype(u8))
     over `rows` rows of every frame, split over `threads` host threads."""
@@ -123,13 +155,54 @@ def run_reference_arm(args, wl):
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup_ref, "ms_per_step": dt * 1e3 * (h / rows), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": args.workload, "description": desc, "frames": n, "height": h, "width": w},
+        "config": config_dict(args, wl),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                          "sample": sample + "; oracle.refport.temporal_median (np.partition, the survey's np.median spec; the reference has no median)"},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "a per-pixel-independent op: the rows/h scaling of the sampled rows is exact up to cache effects",
     }
+    if args.configs != "none":
+        line["configs"] = reference_configs(threads)
     print(json.dumps(line), flush=True)
     return 0
+
+
+def reference_configs(threads):
+    """the oracle port of the per-frame BASELINE configs on the host cores (one frame per thread), for the reference arm"""
+    from oracle import refport as R
+    BC = _bench_configs()
+    from video_unscreen_b200 import synth
+    c = np.load(os.path.join(ROOT, "tests", "golden", "colorfilter.npz"))
+    tabs = {}
+    for tag in ("x2", "x4"):
+        lb = np.stack([R.gmm_lut(c[f"{tag}_bg{i}_means"], c[f"{tag}_bg{i}_covs"], c[f"{tag}_bg{i}_weights"]) for i in range(3)])
+        lf = np.stack([R.gmm_lut(c[f"{tag}_fg{i}_means"], c[f"{tag}_fg{i}_covs"], c[f"{tag}_fg{i}_weights"]) for i in range(3)])
+        tabs[tag] = (lb, lf, R.bg_color_hsv([np.atleast_1d(c[f"{tag}_bg{i}_means"])[0] for i in range(3)]))
+    col = np.array(synth.GREEN_BG, np.uint8)
+    out = {}
+    fr, sg = zip(*[synth.green_frame(1080, 1920, t=t, n=6, seed=0) for t in range(2)])
+
+    def cfg1(i):
+        a, _, _ = R.cf_forward_predict(fr[i % 2], sg[i % 2], *tabs["x2"], 960)
+        return R.generate_trimap_withbg(a, fr[i % 2], col, 960)
+    dt, _ = BC.parallel_cpu(cfg1, list(range(threads)), threads)
+    out["cf_trimap_1080p"] = {"value": threads / dt, "unit": "frames/s", "cores": threads, "kind": "port", "sample": f"{threads} frames in {dt:.1f} s"}
+    f4, s4 = synth.green_frame(2160, 3840, t=1, n=3, seed=0)
+
+    def cfg3(i):
+        a, _, _ = R.cf_forward_predict(f4, s4, *tabs["x4"], 960)
+        R.generate_trimap_withbg(a, f4, col, 960)
+        b = R.patch_bg(np.broadcast_to(col, f4.shape), f4, a, "lt128")
+        return R.get_fg(f4, a, b)
+    th4 = min(threads, 8)
+    dt, _ = BC.parallel_cpu(cfg3, list(range(th4)), th4)
+    out["green_4k"] = {"value": th4 / dt, "unit": "frames/s", "cores": th4, "kind": "port", "sample": f"{th4} 4K frames in {dt:.1f} s"}
+    rng = np.random.default_rng(3)
+    fg, al, bg = rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8), rng.integers(0, 256, (1080, 1920), dtype=np.uint8), \
+        rng.integers(0, 256, (1080, 1920, 3), dtype=np.uint8)
+    dt, _ = BC.parallel_cpu(lambda i: R.replace_blend(fg, al, bg), list(range(2 * threads)), threads)
+    out["replace_1080p"] = {"value": 2 * threads / dt, "unit": "frames/s", "cores": threads, "kind": "port", "sample": f"{2 * threads} frames in {dt:.1f} s"}
+    return out
 
 
 # --------------------------------------------------------------------------
@@ -184,28 +257,19 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def _bench_configs():
+    import importlib
+    if os.path.join(ROOT, "tools") not in sys.path:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+    return importlib.import_module("bench_configs")
+
+
+def make_masks_device(n, h, w, device):
+    return _bench_configs().make_masks_device(n, h, w, device)
+
+
 def make_clip_device(n, h, w, seed, device):
-    """synthetic bg_step clip generated on the device (textured static background,
-    per-frame noise in [-6,6], a moving ellipse covering each pixel in < 50 % of
-    the frames) -- same structure as video_unscreen_b200.synth.bgstep_clip."""
-    import torch
-    g = torch.Generator(device=device).manual_seed(1000 + seed)
-    tex = torch.randint(0, 256, (1, 3, h, w), device=device, generator=g, dtype=torch.uint8).float()
-    bg = torch.nn.functional.avg_pool2d(tex, 11, stride=1, padding=5, count_include_pad=False)[0].permute(1, 2, 0)
-    bg = bg.clamp(0, 255).to(torch.int16)
-    frames = torch.empty((n, h, w, 3), dtype=torch.uint8, device=device)
-    yy = torch.arange(h, device=device, dtype=torch.float32)[:, None]
-    xx = torch.arange(w, device=device, dtype=torch.float32)[None, :]
-    person = torch.tensor([120, 140, 200], device=device, dtype=torch.int16)
-    for t in range(n):
-        noise = torch.randint(-6, 7, (h, w, 3), device=device, generator=g, dtype=torch.int16)
-        f = (bg + noise).clamp_(0, 255)
-        cx = w * (0.15 + 0.7 * t / max(n - 1, 1))
-        ell = (((xx - cx) / (w * 0.1)) ** 2 + ((yy - h / 2.0) / (h * 0.4)) ** 2) <= 1.0
-        pn = torch.randint(-40, 41, (h, w, 3), device=device, generator=g, dtype=torch.int16)
-        f = torch.where(ell[..., None], (person + pn).clamp_(0, 255), f)
-        frames[t] = f.to(torch.uint8)
-    return frames
+    return _bench_configs().make_clip_device(n, h, w, seed, device)
 
 
 def run_gpu_arm(args, wl):
@@ -223,6 +287,7 @@ def run_gpu_arm(args, wl):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_cpus(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
@@ -294,9 +359,30 @@ def run_gpu_arm(args, wl):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
         assert torch.equal(res, out.cpu())
+        # the ceiling of this path: the same bytes through a plain cudaMemcpyAsync from the same pinned buffer, all ranks at once
+        stage = torch.empty_like(frames)
+        stage.copy_(host, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            stage.copy_(host, non_blocking=True)
+        c1.record()
+        c1.synchronize()
+        barrier()
+        copy_ms = c0.elapsed_time(c1) / 3
+        del stage
+        if world > 1:
+            t = torch.tensor([copy_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            copy_ms = float(t.item())
+        ceiling_fps = world * n / (copy_ms * 1e-3)
         e2e = {"value": world * n * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(host.numel()),
                "d2h_bytes_per_step": int(res.numel()), "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-               "api": "video_unscreen_b200.unscreen.utils.temporal_median(pinned host clip) -> host background"}
+               "api": "video_unscreen_b200.unscreen.utils.temporal_median(pinned host clip) -> host background",
+               "h2d_ceiling": {"gbs_per_gpu": host.numel() / copy_ms / 1e6, "ms": copy_ms, "frames_per_s": ceiling_fps,
+                               "what": f"plain cudaMemcpyAsync of the same pinned clip on all {world} ranks at once (max over ranks)"},
+               "frac_of_h2d_ceiling": (world * n * e2e_steps / e2e_s) / ceiling_fps, "cpu_affinity": affinity}
     except RuntimeError as ex:  # e.g. not enough pinnable host memory
         e2e = {"value": None, "unit": "frames/s", "error": str(ex)[:200]}
 
@@ -315,21 +401,61 @@ def run_gpu_arm(args, wl):
                          "oracle.refport.temporal_median (np.partition == the np.median spec; the reference has no median); "
                          "output compared bit-exactly with the GPU result"}
 
+    # ---- the median's worst case: uniform-random bytes (no concentration around the estimate: every warp falls back) ----
+    peak, peak_src = measured_peak()
+    worst = None
+    if args.configs != "none":
+        g = torch.Generator(device=dev).manual_seed(7)
+        frames.random_(0, 256, generator=g)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(10):
+            step()
+        w1.record()
+        w1.synchronize()
+        wms = w0.elapsed_time(w1) / 10
+        s16, _ = frames[:, :8].to(torch.int16).sort(0)
+        if not torch.equal(out[:8], ((s16[(n - 1) // 2] + s16[n // 2]) >> 1).to(torch.uint8)):
+            raise SystemExit("bench: temporal median of the uniform-random clip failed its spot check")
+        worst = {"data": "uniform-random bytes", "launch_ms": wms, "achieved": algo_bytes / (wms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                 "frac": algo_bytes / (wms * 1e-3) / 1e9 / peak, "frames_per_s": n / (wms * 1e-3)}
+    del frames, host
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE configs, sharded the way north_star names ----
+    configs, per_frame = None, None
+    if args.configs != "none":
+        BC = _bench_configs()
+        D = BC.Dist()
+        configs = {}
+        names = list(BC.RUNNERS) if args.configs == "all" else [c for c in args.configs.split(",") if c in BC.RUNNERS]
+        for name in names:
+            configs[name] = BC.RUNNERS[name](D, args.config_steps, 3, peak, cpu=(world == 1 and not args.no_cpu))
+            torch.cuda.empty_cache()
+        if world == 8 and "bgstep_4k" in names:
+            configs["bgstep_4k_2000"] = BC.run_bgstep_4k(D, args.config_steps, 3, peak, cpu=False, frames=2000)
+            torch.cuda.empty_cache()
+        if world == 1 and rank == 0:
+            per_frame = BC.per_frame_latency(D)
+
     if rank == 0:
-        peak, peak_src = measured_peak()
         achieved = algo_bytes / (kernel_ms * 1e-3) / 1e9
         traffic = measured_traffic(args.workload)
         line = {
             "metric": METRIC, "value": world * n * args.steps / (total_ms * 1e-3), "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": args.workload, "description": desc, "frames": n, "height": h, "width": w,
-                       "clip_bytes": n * m, "l2": "inputs (1.87 GB at 1080p) larger than the 126 MB L2; no flush needed",
-                       "sharding": "one clip (spatial tile set) per GPU, no collective"},
+            "config": config_dict(args, wl),
+            "notes": {"clip_bytes": n * m, "l2": "inputs (1.87 GB at 1080p) larger than the 126 MB L2; no flush needed",
+                      "sharding": "one clip (spatial tile set) per GPU, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": KERNELS.get(args.workload, KERNELS["median_1080p"]), "algorithmic_bytes_per_launch": algo_bytes,
                          "launch_ms": kernel_ms, "peak_source": peak_src},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline_worst_case": worst, "configs": configs, "per_frame": per_frame,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -347,6 +473,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--sample-rows", type=int, default=540, help="rows of every frame the CPU arm processes per step")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--configs", default="all", help="'all', 'none' or a comma list of tools/bench_configs.py workloads for the `configs` block")
+    ap.add_argument("--config-steps", type=int, default=10, help="timed steps per workload of the `configs` block")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

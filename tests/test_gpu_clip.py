@@ -148,7 +148,7 @@ def test_sharded_equals_whole(env, world):
 
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_row_tile_sharding_with_halo(env, world):
-    """BASELINE config 5's layout on one GPU, tiles run one after the other: every rank's row tile (+ 24-row halo) through
+    """BASELINE config 5's layout on one GPU, tiles run one after the other: every rank's row tile (+ 28 / 24-row halo) through
     median, difference gate, trimap and get_fg equals the same rows of the whole-clip pipeline."""
     n, h, w = 10, 384, 640                    # working resolution 96 x 160: scale 4, like 4K -> 540 x 960
     frames, masks, _ = synth.bgstep_clip(n, h, w, seed=8)
@@ -157,7 +157,7 @@ def test_row_tile_sharding_with_halo(env, world):
     bg, alpha, tri, fg = env.clip.bgstep_clip(f_d, m_d, ta, thr=25, chunk=4)
     covered = 0
     for rank in range(world):
-        (r0, r1), bg_t, a_t, t_t, f_t = env.clip.bgstep_clip_tile(f_d, m_d, ta, rank, world, thr=25, chunk=4, scale=4)
+        (r0, r1), bg_t, a_t, t_t, f_t = env.clip.bgstep_clip_tile(f_d, m_d, ta, rank, world, thr=25, chunk=4)
         assert r0 % 4 == 0 and (r1 % 4 == 0 or r1 == h)
         assert torch.equal(bg_t, bg[r0:r1])
         assert torch.equal(a_t, alpha[:, r0:r1])
@@ -165,3 +165,35 @@ def test_row_tile_sharding_with_halo(env, world):
         assert torch.equal(f_t, fg[:, r0:r1])
         covered += r1 - r0
     assert covered == h
+
+
+def test_row_tile_halo_regression(env):
+    """the top halo must cover the 4-row upward reach of dilate(4,2) on top of the trimap's 24 rows; data with
+    difference / mask pixels 20..32 rows off the tile boundary (tests/test_sharding_gloo.py::_halo_case).  Also: a rank
+    that holds only its rows (+ halo) of the clip gets the same result, and a portrait clip is refused."""
+    from test_sharding_gloo import _halo_case
+    h, w = 128, 256
+    cases = [_halo_case(h, w, seed) for seed in range(4)]
+    frames = np.stack([c[0] for c in cases])
+    masks = np.stack([c[2] for c in cases])
+    # the median of these 4 frames is the flat background (differences are sparse and at different places)
+    f_d, m_d = dev(frames), dev(masks)
+    ta = env.TA(input_long_side=64)
+    bg, alpha, tri, fg = env.clip.bgstep_clip(f_d, m_d, ta, thr=25, chunk=3)
+    assert np.array_equal(bg.cpu().numpy(), R.temporal_median(frames))
+    for i in range(len(cases)):
+        a_o = R.bgdiff_gate(frames[i], bg.cpu().numpy(), masks[i], 25)
+        assert np.array_equal(alpha[i].cpu().numpy(), a_o) and np.array_equal(tri[i].cpu().numpy(), R.generate_trimap(a_o, 64))
+    for world in (2, 4):
+        for rank in range(world):
+            (r0, r1), bg_t, a_t, t_t, f_t = env.clip.bgstep_clip_tile(f_d, m_d, ta, rank, world, thr=25, chunk=3)
+            assert torch.equal(a_t, alpha[:, r0:r1]) and torch.equal(t_t, tri[:, r0:r1]) and torch.equal(f_t, fg[:, r0:r1])
+            assert torch.equal(bg_t, bg[r0:r1])
+            # the rank holds rows [a0, a1) only
+            _, _, ht, hb, _, _ = env.clip.bgstep_tile_geometry(h, w, ta, rank, world)
+            a0, a1 = r0 - ht, r1 + hb
+            (q0, q1), _, a_l, t_l, f_l = env.clip.bgstep_clip_tile(f_d[:, a0:a1].contiguous(), m_d[:, a0:a1].contiguous(), ta, rank, world,
+                                                                 thr=25, chunk=3, rows=(a0, a1, h))
+            assert (q0, q1) == (r0, r1) and torch.equal(a_l, a_t) and torch.equal(t_l, t_t) and torch.equal(f_l, f_t)
+    with pytest.raises(ValueError):
+        env.clip.bgstep_tile_geometry(250, 130, ta, 0, 2)       # 250x130 -> 64x33: no exact scale

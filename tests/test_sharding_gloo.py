@@ -72,3 +72,50 @@ def test_world_size_2_gloo():
         assert p.exitcode == 0
     assert res[0][1] and res[1][1]
     assert res[0][2] == (0, 150) and res[1][2] == (150, 300)
+
+
+def _halo_case(h=128, w=256, seed=0):
+    """frames whose whole-frame results depend on rows up to 28 above a tile boundary: sparse difference pixels and sparse
+    mask pixels around row h/2 (a diff pixel at r0-26 plus a mask pixel at r0-24 changes the trimap at r0)."""
+    rng = np.random.default_rng(seed)
+    bg = np.full((h, w, 3), 90, np.uint8)
+    frame = bg.copy()
+    mask = np.zeros((h, w), np.uint8)
+    r0 = h // 2
+    for x in range(8, w - 8, 8):
+        d = int(rng.integers(20, 32))
+        frame[r0 - d - 2, x] = 250          # a difference two rows above ...
+        mask[r0 - d, x] = 255               # ... opens the gate for a mask pixel at r0 - d (dilate(4,2) reaches 4 up / 2 down)
+        d = int(rng.integers(18, 28))
+        frame[r0 + d + 1, x + 4] = 250
+        mask[r0 + d, x + 4] = 255
+    return frame, bg, mask
+
+
+def _tile_pipeline_oracle(frame, bg, mask, a0, a1, long_side):
+    from oracle import refport as R
+    alpha = R.bgdiff_gate(frame[a0:a1], bg[a0:a1], mask[a0:a1], 25)
+    return alpha, R.generate_trimap(alpha, long_side)
+
+
+def test_bgstep_halo_covers_the_stencils():
+    """the (top, bottom) halo of shard.bgstep_halo makes a row tile's gate + trimap equal the whole frame's (oracle
+    arithmetic, CPU); the old symmetric 24-row halo does not (the regression this guards against)."""
+    from oracle import refport as R
+    assert shard.bgstep_halo(4, 5) == (28, 24) and shard.bgstep_halo(2, 5) == (16, 14)
+    h, w, long_side, scale = 128, 256, 64, 4
+    bad = 0
+    for seed in range(4):
+        frame, bg, mask = _halo_case(h, w, seed)
+        alpha_w = R.bgdiff_gate(frame, bg, mask, 25)
+        tri_w = R.generate_trimap(alpha_w, long_side)
+        assert (tri_w == 128).any()
+        for halo in (shard.bgstep_halo(scale, 5), 24):
+            for r0, r1, ht, hb in shard.row_tiles(h, 2, halo=halo, align=scale):
+                a, t = _tile_pipeline_oracle(frame, bg, mask, r0 - ht, r1 + hb, long_side)
+                same = np.array_equal(a[ht:ht + r1 - r0], alpha_w[r0:r1]) and np.array_equal(t[ht:ht + r1 - r0], tri_w[r0:r1])
+                if halo == 24:
+                    bad += not same
+                else:
+                    assert same, (seed, r0, r1)
+    assert bad > 0, "the test data no longer exercises rows 25..28 above the boundary"

@@ -71,6 +71,61 @@ def _overlap_chunks(n, chunk, body, streams=2):
         cur.wait_event(done)
 
 
+_PIPE_STREAMS = {}
+
+
+def streamed(host_inputs, host_outputs, body, chunk, depth=2):
+    """A clip that lives in (pinned) HOST memory through a per-frame clip pipeline, chunk by chunk, with the host->device
+    copies, the kernels and the device->host copies of consecutive chunks overlapping on three streams (PCIe is full
+    duplex: the step costs max(H2D, D2H), not their sum, and the kernels hide under the copies).
+
+    ``host_inputs`` / ``host_outputs``: lists of CPU tensors [N, ...] (pinned, or the copies are synchronous);
+    ``body(s, e, *device_input_chunks, outs)`` runs frames [s, e): ``outs`` are device staging tensors [e - s, ...], one
+    per host output, which the body must fill (pass them as ``out=`` to the clip functions).  Chunks must be independent
+    (every per-frame stage is).  Returns after the last device->host copy has landed."""
+    n = host_inputs[0].shape[0]
+    cur = torch.cuda.current_stream()
+    dev = cur.device
+    if dev not in _PIPE_STREAMS:
+        _PIPE_STREAMS[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+    s_in, s_run, s_out = _PIPE_STREAMS[dev]
+    depth = max(1, min(depth, -(-n // chunk)))
+    bufs_in = [[torch.empty((chunk,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in host_inputs] for _ in range(depth)]
+    bufs_out = [[torch.empty((chunk,) + tuple(t.shape[1:]), dtype=t.dtype, device=dev) for t in host_outputs] for _ in range(depth)]
+    start = torch.cuda.Event()
+    start.record(cur)
+    for st in (s_in, s_run, s_out):
+        st.wait_event(start)
+    ran = [None] * depth        # kernels of the chunk that used slot k are done: its input buffers are free
+    landed = [None] * depth     # its outputs are on the host: its output buffers are free
+    for i, (s, e) in enumerate(_chunks(n, chunk)):
+        k = i % depth
+        with torch.cuda.stream(s_in):
+            if ran[k] is not None:
+                s_in.wait_event(ran[k])
+            ins = [b[:e - s] for b in bufs_in[k]]
+            for b, t in zip(ins, host_inputs):
+                b.copy_(t[s:e], non_blocking=True)
+            up = torch.cuda.Event()
+            up.record(s_in)
+        with torch.cuda.stream(s_run):
+            s_run.wait_event(up)
+            if landed[k] is not None:
+                s_run.wait_event(landed[k])
+            outs = [b[:e - s] for b in bufs_out[k]]
+            body(s, e, *ins, outs)
+            ran[k] = torch.cuda.Event()
+            ran[k].record(s_run)
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(ran[k])
+            for b, t in zip(outs, host_outputs):
+                t[s:e].copy_(b, non_blocking=True)
+            landed[k] = torch.cuda.Event()
+            landed[k].record(s_out)
+    for st in (s_in, s_run, s_out):
+        st.synchronize()
+
+
 def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None, streams=2):
     """ColorFilteringAgent.forward(frame, mask, iters=0) for every frame of
     frames[N,H,W,3] / segmasks[N,H,W] with the agent's current mixtures
@@ -105,11 +160,11 @@ def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None, streams=2):
     return alpha
 
 
-def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None):
+def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None, work_size=None):
     """nearest down (+ ensemble clearing) -> dilate/erode/classify -> bilinear up + snap (+ fuzzy override); written into
-    ``out`` when given"""
+    ``out`` when given.  ``work_size`` overrides the working resolution (row tiles of a frame: the WHOLE frame decides it)."""
     n, h, w = masks.shape
-    ih, iw = get_target_size(h, w, agent.input_long_side)
+    ih, iw = work_size if work_size is not None else get_target_size(h, w, agent.input_long_side)
     if agent.kernelsize == 3 and ops.trimap_bits_supported(masks, ih, iw, agent.iters, fuzzy):
         # exact 2x / 4x working resolution (1080p, 4K): the whole tail in bit logic, two launches
         return ops.trimap_bits(masks, ih, iw, agent.iters, fuzzy, flags, out=out)
@@ -128,7 +183,7 @@ def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None):
     return ops.resize_up(tri, h, w, mode=1, fuzzy=fuzzy, flags=flags, out=out)
 
 
-def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None, streams=2):
+def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None, streams=2, work_size=None):
     """TrimapAgent.forward for every frame: mask-only (trimap/agent.py:35-61) or,
     with ``frames`` and ``bg`` ((3,) colour or [H,W,3] / [N,H,W,3] image), the
     background-gated variant (:63-101) with its per-frame ratio test decided on
@@ -140,7 +195,7 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None, streams=
     def body(s, e):
         m = masks[s:e]
         if frames is None:
-            _trimap_tail(m, agent, out=tri[s:e])
+            _trimap_tail(m, agent, out=tri[s:e], work_size=work_size)
             return
         fr = frames[s:e]
         if isinstance(bg, np.ndarray) and bg.ndim == 1:
@@ -153,7 +208,7 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None, streams=
             fuzzy = ops.mask_and01(m, bgmask)
         flags = ops.ratio_flags(counts, 0.1)       # 0: ensemble, 1: trust mask, 2: empty mask
         # an empty mask is returned as is (all zeros); the plain branch of an all-zero mask is all zeros too
-        _trimap_tail(m, agent, fuzzy, flags, out=tri[s:e])
+        _trimap_tail(m, agent, fuzzy, flags, out=tri[s:e], work_size=work_size)
     _overlap_chunks(n, chunk, body, streams)
     return tri
 
@@ -218,7 +273,7 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None
     return alpha, tri, fg, bgo
 
 
-def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None):
+def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None, out=None):
     """tools/replace/replace.py:69-76 for a whole clip; ``bg`` is [H,W,3] (shared) or [N,H,W,3].  With ``dx``/``dy``
     and/or ``scale`` the foreground and its mask first go through shift_fg / rescale_fg (:69-72) like in the script;
     without them this is the blend of :74-76 alone (BASELINE config 4).  Whole-clip launches: these kernels fill the
@@ -230,14 +285,15 @@ def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None):
     if scale is not None:
         fg = ops.rescale_cubic(fg, scale, 3)
         alpha = ops.rescale_cubic(alpha, scale, ach)
-    return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg)
+    return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg, out=out)
 
 
-def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2):
+def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_size=None):
     """bg_step: exact temporal-median background, then per frame the difference
     gate (bg_offline.py:154-160), mask-only trimap (:166) and get_fg with the
     alpha==0 patch (:171-172), CNN stage skipped (alpha := gated mask).
-    Returns background, alpha, trimap, fg."""
+    Returns background, alpha, trimap, fg.  ``work_size``: the trimap's working
+    resolution when ``frames`` is a row tile (see bgstep_clip_tile)."""
     n, h, w, _ = frames.shape
     dev = frames.device
     bg = ops.temporal_median(frames)
@@ -251,29 +307,48 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2):
         else:
             a = ops.gate(masks[s:e], ops.dilate(ops.bgdiff_gray(frames[s:e], bg, thr), 4, 2))
             alpha[s:e] = a
-        trimap_clip(a, trimap_agent, chunk=chunk, out=tri[s:e])
+        trimap_clip(a, trimap_agent, chunk=chunk, out=tri[s:e], work_size=work_size)
         ops.get_fg(frames[s:e], a, bg, _lib.PATCH_ALPHA_EQ0, out=fg[s:e])
     _overlap_chunks(n, chunk, body, streams)
     return bg, alpha, tri, fg
 
 
-BGSTEP_HALO = 24   # full-resolution rows: 6 working-resolution rows at 1/4 scale (r=5 diamond + one bilinear tap); covers dilate(4,2)
+def bgstep_tile_geometry(h, w, trimap_agent, rank, world):
+    """row tile of rank ``rank`` for bgstep_clip_tile on h x w frames: (r0, r1, halo_top, halo_bottom, scale, (th, tw)).
+    The working resolution comes from the WHOLE frame (trimap/agent.py:44-46 via get_target_size) and must be an exact
+    integer fraction of it (1080p -> 540x960: 2, 4K: 4): only then does a tile that starts on a multiple of the scale
+    sample the pixels the whole frame's nearest / bilinear resizes do.  Anything else raises."""
+    from . import shard
+    th, tw = get_target_size(h, w, trimap_agent.input_long_side)
+    scale = h // th if th else 0
+    if scale < 1 or h != scale * th or w != scale * tw:
+        raise ValueError(f"row-tile sharding needs a working resolution that divides the frame exactly: {h}x{w} -> {th}x{tw}")
+    if trimap_agent.kernelsize != 3:
+        raise ValueError("row-tile sharding: halo arithmetic is for the 3x3 trimap kernel")
+    r0, r1, ht, hb = shard.my_row_tile(h, rank, world, halo=shard.bgstep_halo(scale, trimap_agent.iters), align=scale)
+    return r0, r1, ht, hb, scale, (th, tw)
 
 
-def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24, scale=4):
+def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24, rows=None, streams=2):
     """bgstep_clip on this rank's ROW TILE of the clip (BASELINE config 5: spatial-tile sharding):
     the temporal median of the tile's rows (every pixel is independent), then the per-frame stages on the tile plus a
-    halo of BGSTEP_HALO rows read from the local frames, cropped back.  ``frames`` / ``masks`` are the WHOLE frames here
-    (the caller may hold only rows [r0 - halo, r1 + halo) and pass those with the matching offsets instead).  Tile
-    boundaries are multiples of ``scale`` (frame size / working size), so the tile's down-scales sample the pixels the
-    whole frame's do: the results equal the corresponding rows of bgstep_clip on the whole clip, bit for bit.
-    Returns (r0, r1), background, alpha, trimap, fg for rows [r0, r1)."""
-    from . import shard
-    n, h, w, _ = frames.shape
-    r0, r1, ht, hb = shard.my_row_tile(h, rank, world, halo=BGSTEP_HALO, align=scale)
+    halo (shard.bgstep_halo: 28 rows above, 24 below at 4K) read from the local frames, cropped back.  ``frames`` /
+    ``masks`` are the WHOLE frames, or -- ``rows`` = (a0, a1, H) -- only rows [a0, a1) of H-row frames, which must
+    cover the tile plus its halo (what a rank that holds just its share of the clip passes).  Tile and halo boundaries
+    are multiples of the scale (frame size / working size, decided by the WHOLE frame), so the tile's down-scales sample
+    the pixels the whole frame's do: the results equal the corresponding rows of bgstep_clip on the whole clip, bit for
+    bit.  Returns (r0, r1), background, alpha, trimap, fg for rows [r0, r1)."""
+    n, hh, w, _ = frames.shape
+    base, h = (rows[0], rows[2]) if rows is not None else (0, hh)
+    r0, r1, ht, hb, scale, (th, tw) = bgstep_tile_geometry(h, w, trimap_agent, rank, world)
     a0, a1 = r0 - ht, r1 + hb
-    ftile = frames[:, a0:a1].contiguous()
-    mtile = masks[:, a0:a1].contiguous()
-    bg_t, alpha_t, tri_t, fg_t = bgstep_clip(ftile, mtile, trimap_agent, thr=thr, chunk=chunk)
+    if a0 < base or a1 > base + hh:
+        raise ValueError(f"rows [{base}, {base + hh}) do not cover the tile plus halo [{a0}, {a1})")
+    ftile = frames[:, a0 - base:a1 - base]
+    mtile = masks[:, a0 - base:a1 - base]
+    ftile = ftile if ftile.is_contiguous() else ftile.contiguous()
+    mtile = mtile if mtile.is_contiguous() else mtile.contiguous()
+    bg_t, alpha_t, tri_t, fg_t = bgstep_clip(ftile, mtile, trimap_agent, thr=thr, chunk=chunk, streams=streams,
+                                             work_size=((a1 - a0) // scale, tw))
     lo, hi = ht, ht + (r1 - r0)
     return (r0, r1), bg_t[lo:hi], alpha_t[:, lo:hi], tri_t[:, lo:hi], fg_t[:, lo:hi]

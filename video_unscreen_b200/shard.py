@@ -24,23 +24,40 @@ def frame_ranges(n_frames, world, align=1):
     return out
 
 
+def bgstep_halo(scale, trimap_iters=5):
+    """(top, bottom) halo rows a row tile needs so that the bg_step per-frame stages (difference gate -> mask-only trimap
+    -> get_fg) on the tile equal the same rows of the whole frame, for a working resolution of 1/``scale``:
+
+    * trimap row y of a tile starting at r0 (a multiple of ``scale``) takes the bilinear taps r0/scale - 1 and r0/scale
+      of the working-resolution trimap; a working-resolution row j looks ``trimap_iters`` rows up and down (3x3 cross);
+      working row j is full-resolution row j*scale (nearest): the gated alpha is read from row r0 - scale*(iters+1) on;
+    * that alpha row comes out of dilate_mask(gray, 4, 2), which reaches 4 rows up and 2 rows down (anchor (2,2) of the
+      4x4 ellipse, twice).
+
+    top = scale*(iters+1) + 4; bottom = scale*iters + 2 (+1: rows, not offsets), both rounded up to multiples of
+    ``scale`` so that the tile plus halo still starts and ends on the working-resolution grid.  scale 4, iters 5 (4K):
+    (28, 24); scale 2 (1080p): (16, 14)."""
+    up = lambda v: -(-v // scale) * scale
+    return up(scale * (trimap_iters + 1) + 4), up(scale * trimap_iters + 3)
+
+
 def row_tiles(height, world, halo=0, align=1):
     """[(row_start, row_stop, halo_top, halo_bottom)] per rank.  ``halo`` rows
-    of neighbouring tiles are needed when a tile is later pushed through the
-    stencil stages without gathering (dilate(4,2) reaches -4..+2 rows, the
-    r=5 trimap at 1/4 scale ~20 rows + bilinear taps: 24 covers both).
-    Interior boundaries are multiples of ``align`` (the down-scale factor of
+    (one number, or (top, bottom): see ``bgstep_halo``) of neighbouring tiles
+    are needed when a tile is later pushed through the stencil stages without
+    gathering.  Interior boundaries are multiples of ``align`` (the down-scale factor of
     the working resolution, 4 at 4K, so that a tile's nearest / area
     down-scale samples the same pixels as the whole frame's); halos are
     clipped to the image."""
-    if world < 1 or height < 0 or halo < 0 or align < 1:
+    top, bottom = (halo, halo) if isinstance(halo, int) else halo
+    if world < 1 or height < 0 or top < 0 or bottom < 0 or align < 1:
         raise ValueError("bad arguments")
     units = -(-height // align)
     out, start = [], 0
     for r in range(world):
         u = units // world + (1 if r < units % world else 0)
         stop = min(height, start + u * align)
-        out.append((start, stop, min(halo, start), min(halo, height - stop)))
+        out.append((start, stop, min(top, start), min(bottom, height - stop)))
         start = stop
     return out
 
