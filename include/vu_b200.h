@@ -180,6 +180,31 @@ int vu_trimap_src_lo(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* f
 size_t vu_trimap_bits_workspace_bytes(int n, int th, int tw);
 int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* flags, int n, int h, int w, int th, int tw,
                    int iters, uint8_t* out, void* workspace, size_t workspace_bytes, vu_stream_t stream);
+
+/* The same tail from bit planes (no full-resolution byte map is read): mask_bits [n][th][tw/8] = (nearest-sampled
+ * mask >= 128) at the working resolution, fuzzy_bits [n][h][w/8] = one bit per full-resolution pixel (bit i of byte j =
+ * pixel 8j + i), as vu_cf_alpha_up_fuzzy writes them; fuzzy_bits / flags may both be NULL.  tw % 16 == 0. */
+int vu_trimap_bits_packed(const uint8_t* mask_bits, const uint8_t* fuzzy_bits, const uint8_t* flags, int n, int h, int w,
+                          int th, int tw, int iters, uint8_t* out, void* workspace, size_t workspace_bytes,
+                          vu_stream_t stream);
+
+/* The second full-resolution pass of the green-screen loop for frames that are an exact 2x / 4x of the working
+ * resolution th x tw (tw % 16 == 0), in one kernel:
+ *   alpha      = cv2.resize(alpha_lo, (w, h)), colorfiltering/agent.py:342; frames with alt_flags[i] != 0 (the
+ *                early-outs of :303-307) are copied from alt_src [n][h][w] instead (both NULL or both set);
+ *   fuzzy_bits = (alpha > 0) && lo <= BGR2HSV(frame) <= hi, trimap/agent.py:84-91 (is_pixel_inrange with a background
+ *                colour, utils/fgfuncs.py:55-64), one bit per pixel, [n][h][w/8];
+ *   counts2[i] = {#fuzzy, #(alpha > 0)}, trimap/agent.py:92-94;
+ *   mask_bits  = alpha[SC*y][SC*x] >= 128, the nearest down-scale of trimap/agent.py:52 as bits, [n][th][tw/8];
+ *   fg_out / bg_out (both NULL or both set, with bg_bgr = 3 HOST bytes): tools/unscreen/green.py:125-126,
+ *                bgimg = bg colour, bgimg[alpha < 128] = frame[alpha < 128], fg = get_fg(frame, alpha, bgimg)
+ *                (utils/fgfuncs.py:84-110).
+ * The frame is only read where the matte is non-zero (everywhere when fg_out is set).  Feed mask_bits / fuzzy_bits /
+ * ratio flags of counts2 to vu_trimap_bits_packed. */
+int vu_cf_alpha_up_fuzzy(const uint8_t* alpha_lo, int n, int th, int tw, int h, int w, const uint8_t* alt_src,
+                         const uint8_t* alt_flags, const uint8_t* frames, const int32_t lo[3], const int32_t hi[3],
+                         uint8_t* alpha, uint8_t* fuzzy_bits, uint8_t* mask_bits, uint64_t* counts2,
+                         const uint8_t* bg_bgr, uint8_t* fg_out, uint8_t* bg_out, vu_stream_t stream);
 int vu_trimap_classify(const uint8_t* dilated, const uint8_t* eroded, uint8_t* out, int64_t count,
                        vu_stream_t stream);
 /* trimap/agent.py:60: values strictly between 0 and 255 become 128 */

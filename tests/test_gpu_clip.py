@@ -197,3 +197,57 @@ def test_row_tile_halo_regression(env):
             assert (q0, q1) == (r0, r1) and torch.equal(a_l, a_t) and torch.equal(t_l, t_t) and torch.equal(f_l, f_t)
     with pytest.raises(ValueError):
         env.clip.bgstep_tile_geometry(250, 130, ta, 0, 2)       # 250x130 -> 64x33: no exact scale
+
+
+@pytest.mark.parametrize("tag,h,w,L", [("x2", 270, 480, 240), ("x4", 384, 640, 160), ("x2", 64, 96, 48)])
+def test_fused_green_chunk_equals_staged(env, tag, h, w, L):
+    """the two-pass chunk (vu_cf_alpha_up_fuzzy + vu_trimap_bits_packed, clip._fused_green_chunk) against the
+    stage-by-stage kernels: alpha, trimap, fg, bg, for ordinary frames, both early-outs, an all-zero matte and
+    soft mattes (random working-resolution alpha through the second pass alone)."""
+    n = 9
+    frames, segs = synth.green_clip(n, h, w, seed=21)
+    segs[2] = 0
+    segs[4] = 255
+    frames[6] = np.array(synth.GREEN_BG, np.uint8)          # nothing but background: alpha all zero -> empty-mask branch
+    lb, lf, bgh = env.tables[tag]
+    cf = env.CF(input_long_side=L)
+    cf.set_tables(lb, lf, bgh)
+    ta = env.TA(input_long_side=L)
+    f_d, s_d = dev(frames), dev(segs)
+    assert env.clip._fused_green_supported(f_d, s_d, cf, ta)
+    a1, t1 = env.clip.cf_trimap_clip(f_d, s_d, cf, ta, chunk=4, fused=True)
+    a0, t0 = env.clip.cf_trimap_clip(f_d, s_d, cf, ta, chunk=4, fused=False)
+    assert torch.equal(a1, a0) and torch.equal(t1, t0)
+    g1 = env.clip.green_clip(f_d, s_d, cf, ta, chunk=4, fused=True)
+    g0 = env.clip.green_clip(f_d, s_d, cf, ta, chunk=4, fused=False)
+    for x, y, name in zip(g1, g0, ("alpha", "trimap", "fg", "bg")):
+        assert torch.equal(x, y), name
+    # the second pass alone on soft, noisy working-resolution mattes (every interpolation phase and weight, borders)
+    from video_unscreen_b200.unscreen.utils.fgfuncs import bgr2hsv_pixel
+    th, tw = h // (2 if tag == "x2" else 4), w // (2 if tag == "x2" else 4)
+    rng = np.random.default_rng(5)
+    a_lo = rng.integers(0, 256, (n, th, tw), dtype=np.uint8)
+    a_lo[:, : th // 3] = 0
+    a_lo[:, th // 2:, : tw // 2] = 255
+    col = cf.bg_color_bgr()
+    hsv = bgr2hsv_pixel(col)
+    half = np.array(ta.color_winsize) // 2
+    lo, hi = np.clip(hsv - half, 10, 255), np.clip(hsv + half, 10, 255)
+    deg = dev(np.array([0, 0, 1, 0, 0, 0, 0, 1, 0], np.uint8))
+    alpha, fzb, mb, counts, fg, bg = env.ops.cf_alpha_up_fuzzy(dev(a_lo), h, w, f_d, lo, hi, alt_src=s_d, alt_flags=deg, bg_bgr=col)
+    want_a = env.ops.resize_up(dev(a_lo), h, w, alt_src=s_d, alt_flags=deg)
+    assert torch.equal(alpha, want_a)
+    fz, cnt = env.ops.fuzzy_count(f_d, want_a, lo, hi)
+    assert torch.equal(counts, cnt)
+    bits = np.unpackbits(fzb.cpu().numpy(), axis=-1, bitorder="little").reshape(n, h, w)
+    assert np.array_equal(bits, fz.cpu().numpy())
+    sc = h // th
+    mbits = np.unpackbits(mb.cpu().numpy(), axis=-1, bitorder="little").reshape(n, th, tw)
+    assert np.array_equal(mbits, (want_a.cpu().numpy()[:, ::sc, ::sc] >= 128).astype(np.uint8))
+    tile = torch.from_numpy(np.tile(col, (1, 4, 1))).cuda()
+    fg0, bg0 = env.ops.get_fg(f_d, want_a, tile, 1, want_bg=True)
+    assert torch.equal(fg, fg0) and torch.equal(bg, bg0)
+    flags = env.ops.ratio_flags(cnt, 0.1)
+    tri = env.ops.trimap_bits_packed(mb, fzb, flags, h, w, th, tw, 5)
+    assert torch.equal(tri, env.ops.trimap_bits(want_a, th, tw, 5, fz, flags))
+    assert torch.equal(env.ops.trimap_bits_packed(mb, None, None, h, w, th, tw, 3), env.ops.trimap_bits(want_a, th, tw, 3))

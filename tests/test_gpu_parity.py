@@ -104,6 +104,46 @@ def test_cross_chain_and_trimap_core(vu, shape):
     assert np.array_equal(got, np.stack([R.cf_postprocess(x, y) for x, y in zip(a, m3)]))
 
 
+def test_cross_march_flat_units(vu):
+    """the marching kernels' shortcut for units (112-column strips x 64-row bands) whose input is one value after the
+    threshold: mattes made of constant blocks (0, below / above the threshold, 127 / 128, 255), blocks with a single
+    odd pixel (in the strip's halo columns and lead-in rows too), against the oracle's morphology"""
+    rng = np.random.default_rng(11)
+    h, w = 200, 480
+    frames = []
+    for _ in range(6):
+        m = np.zeros((h, w), np.uint8)
+        for y0 in range(0, h, 50):
+            for x0 in range(0, w, 60):
+                m[y0:y0 + 50, x0:x0 + 60] = rng.choice([0, 0, 0, 60, 127, 128, 200, 255])
+        for _ in range(3):
+            m[rng.integers(0, h), rng.integers(0, w)] = rng.integers(0, 256)
+        frames.append(m)
+    frames.append(np.full((h, w), 255, np.uint8))
+    frames.append(np.zeros((h, w), np.uint8))
+    m3 = np.stack(frames)
+    D, E = 0, 1
+    for segs in ([(D, 2), (E, 2), (E, 2), (D, 2)], [(D, 5)], [(E, 5)], [(D, 2)], [(E, 1)]):
+        want = []
+        for x in m3:
+            for op, it in segs:
+                x = M.dilate(x, 3, it) if op == D else M.erode(x, 3, it)
+            want.append(x)
+        assert np.array_equal(host(vu.ops.cross_chain(dev(m3), segs)), np.stack(want)), segs
+    for r in (1, 3, 5):
+        want = []
+        for x in m3:
+            dil, ero = M.dilate(x, 3, r), M.erode(x, 3, r)
+            t = np.full(x.shape, 128, np.uint8)
+            t[ero > 127] = 255
+            t[dil < 128] = 0
+            want.append(t)
+        assert np.array_equal(host(vu.ops.trimap_core(dev(m3), r)), np.stack(want)), r
+    masks = np.where(rng.random(m3.shape) < 0.7, 255, 0).astype(np.uint8)
+    got = host(vu.ops.cf_postprocess(dev(m3), dev(masks)))
+    assert np.array_equal(got, np.stack([R.cf_postprocess(x, y) for x, y in zip(m3, masks)]))
+
+
 @pytest.mark.parametrize("sh,sw,dh,dw", [(270, 480, 135, 240), (360, 640, 90, 160), (135, 240, 270, 480), (90, 160, 360, 640),
                                          (250, 333, 150, 200), (150, 200, 250, 333), (480, 270, 240, 135), (61, 47, 122, 94), (9, 7, 4, 3)])
 def test_resize(vu, sh, sw, dh, dw):

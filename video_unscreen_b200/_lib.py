@@ -55,6 +55,8 @@ SIGNATURES = {
     "vu_mask_and01": (_i, [_p, _p, _p, _i64, _p]),
     "vu_trimap_bits_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i]),
     "vu_trimap_bits": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p]),
+    "vu_trimap_bits_packed": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, ctypes.c_size_t, _p]),
+    "vu_cf_alpha_up_fuzzy": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i3, _i3, _p, _p, _p, _p, _p, _p, _p, _p]),
     "vu_trimap_classify": (_i, [_p, _p, _p, _i64, _p]),
     "vu_trimap_snap": (_i, [_p, _i64, _p, _p]),
     "vu_ratio_flags": (_i, [_p, _i, _d, _p, _p]),

@@ -213,19 +213,52 @@ def trimap_clip(masks, agent, frames=None, bg=None, chunk=64, out=None, streams=
     return tri
 
 
-def cf_trimap_clip(frames, segmasks, cf_agent, trimap_agent, bg_color=None, chunk=50, out_alpha=None, out_trimap=None, streams=2):
+def _fused_green_supported(frames, segmasks, cf_agent, trimap_agent):
+    """the two-pass green-screen chunk (vu_cf_lowres -> postprocess -> vu_cf_alpha_up_fuzzy -> vu_trimap_bits_packed):
+    both agents at the same working resolution, an exact 2x / 4x of it, the 3x3 trimap kernel"""
+    n, h, w, _ = frames.shape
+    th, tw = get_target_size(h, w, cf_agent.input_long_side)
+    return (trimap_agent.input_long_side == cf_agent.input_long_side and trimap_agent.kernelsize == 3 and 0 <= trimap_agent.iters <= 12
+            and ops.cf_lowres_supported(h, w, th, tw) and ops.cf_lowres_counts_supported(frames, segmasks, th, tw)
+            and ops.cf_up_supported(frames, None, h, w, th, tw, segmasks))
+
+
+def _fused_green_chunk(fr, sm, cf_agent, trimap_agent, bg_color, alpha_out, tri_out, fg_out=None, bg_out=None):
+    """one chunk of green.py:99-114 (+ :125-126 when fg_out / bg_out are given) in five launches and ~7P bytes per frame:
+    pass 1 reads the frame and the mask once (HSV, down-scale, mixtures, statistics, early-out counts), the working-
+    resolution matte is post-processed in L2, pass 2 writes the full-resolution matte and - from the frame, where the matte
+    is non-zero - the fuzzy area and its counts as bits, and the trimap comes out of those bit planes."""
+    n, h, w, _ = fr.shape
+    th, tw = get_target_size(h, w, cf_agent.input_long_side)
+    fg_min, bg_min = max(cf_agent.fg_ncomp) * 5, max(cf_agent.bg_ncomp) * 5
+    a_lo, stats, mc = ops.cf_lowres(fr, sm, th, tw, cf_agent.lut3d_dev(), want_mask_counts=True)
+    deg = ops.degenerate_flags_from_counts(mc, fg_min, bg_min)
+    a_lo = ops.cross_chain(a_lo, [(_lib.DILATE, 2), (_lib.ERODE, 2), (_lib.ERODE, 2), (_lib.DILATE, 2)], stats, 0.8)
+    hsv = bgr2hsv_pixel(bg_color)
+    half = np.array(trimap_agent.color_winsize) // 2
+    res = ops.cf_alpha_up_fuzzy(a_lo, h, w, fr, np.clip(hsv - half, 10, 255), np.clip(hsv + half, 10, 255), alt_src=sm, alt_flags=deg,
+                                out=alpha_out, bg_bgr=bg_color if fg_out is not None else None, fg_out=fg_out, bg_out=bg_out)
+    _, fzb, mb, counts = res[:4]
+    flags = ops.ratio_flags(counts, 0.1)       # 0: ensemble, 1: trust mask, 2: empty mask (its trimap is all zeros either way)
+    ops.trimap_bits_packed(mb, fzb, flags, h, w, th, tw, trimap_agent.iters, out=tri_out)
+
+
+def cf_trimap_clip(frames, segmasks, cf_agent, trimap_agent, bg_color=None, chunk=50, out_alpha=None, out_trimap=None, streams=2, fused=True):
     """BASELINE config 1: ColorFilteringAgent.forward(iters=0) then TrimapAgent.forward(alpha, frame, bg colour) for every
-    frame, chunk by chunk.  Chunks bound the temporaries (about 12 bytes per pixel and frame); make them as large as memory
-    allows: 300 x 1080p takes 4.1 ms in chunks of 30, 3.6 ms in chunks of 100, 3.4 ms in one piece (launch gaps and the
-    partial last wave of every kernel); with ``streams`` = 2 consecutive chunks overlap on two streams and fill each
-    other's gaps: 3.05 ms in chunks of 50.  Returns alpha, trimap."""
+    frame, chunk by chunk.  Chunks bound the temporaries; with ``streams`` = 2 consecutive chunks overlap on two streams and
+    fill each other's launch gaps and partial last waves.  ``fused`` (default): the two-pass chunk of _fused_green_chunk
+    where the sizes allow it (1080p, 4K), else the stage-by-stage kernels.  Returns alpha, trimap."""
     n, h, w, _ = frames.shape
     dev = frames.device
     alpha = out_alpha if out_alpha is not None else torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     tri = out_trimap if out_trimap is not None else torch.empty((n, h, w), dtype=torch.uint8, device=dev)
     if bg_color is None:
         bg_color = cf_agent.bg_color_bgr()
+    use_fused = fused and _fused_green_supported(frames, segmasks, cf_agent, trimap_agent)
     def body(s, e):
+        if use_fused:
+            _fused_green_chunk(frames[s:e], segmasks[s:e], cf_agent, trimap_agent, bg_color, alpha[s:e], tri[s:e])
+            return
         a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
         trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
     cf_agent.tables_dev(), cf_agent.lut3d_dev()      # built (once) on the current stream, not on a side stream
@@ -244,7 +277,7 @@ def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0
     return out
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2):
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2, fused=True):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
     stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
     [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.
@@ -261,10 +294,18 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None
         bg_color = cf_agent.bg_color_bgr()
     if bg_tile is None:
         bg_tile = torch.from_numpy(np.tile(bg_color, (1, 4, 1))).to(dev)     # constant background: a 4-pixel periodic image
+    use_fused = fused and _fused_green_supported(frames, segmasks, cf_agent, trimap_agent)
     def body(s, e):
         # every stage writes straight into its slice of the clip-sized results
-        a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
-        trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
+        if use_fused and not color_correct:      # get_fg rides along in the second pass (one BGR2HSV per pixel for both)
+            _fused_green_chunk(frames[s:e], segmasks[s:e], cf_agent, trimap_agent, bg_color, alpha[s:e], tri[s:e], fg[s:e], bgo[s:e])
+            return
+        if use_fused:
+            _fused_green_chunk(frames[s:e], segmasks[s:e], cf_agent, trimap_agent, bg_color, alpha[s:e], tri[s:e])
+            a = alpha[s:e]
+        else:
+            a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk, out=alpha[s:e])
+            trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
         if color_correct:
             a = color_correct_clip(frames[s:e], a.clone(), bg_color, chunk=chunk, out=alpha[s:e])
         ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True, out=fg[s:e], bg_out=bgo[s:e])

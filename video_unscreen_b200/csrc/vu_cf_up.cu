@@ -1,0 +1,288 @@
+// The second full-resolution pass of the green-screen path, for frames that are an exact 2x or 4x of the working
+// resolution (1080p and 4K at input_long_side 960):
+//
+//   alpha  = cv2.resize(alpha_lo, (W, H))                                   colorfiltering/agent.py:342 (early-out frames,
+//                                                                           :303-307, are copied from the segmentation mask)
+//   bgmask = is_pixel_inrange(frame, bg_colour, color_winsize)              trimap/agent.py:84 -> utils/fgfuncs.py:55-64
+//   fuzzy  = (alpha > 0) & bgmask;  counts = (#fuzzy, #(alpha > 0))         trimap/agent.py:90-94
+//   B      = nearest-down(alpha) >= 128                                     trimap/agent.py:52 (what the bit-logic trimap needs)
+//   [FG]   bgimg[alpha < 128] = frame[alpha < 128];  fg = get_fg(frame, alpha, bgimg)      tools/unscreen/green.py:125-126
+//
+// in ONE pass: the working-resolution alpha is L2-resident (0.5 MB per frame), the full-resolution alpha is written
+// once and never read back, fuzzy and B leave as bit planes (1/8 and 1/32 .. 1/128 byte per pixel), and the frame is
+// only read where the matte is non-zero (everywhere in the FG variant, whose patched background needs it).  This
+// replaces resize_up + fuzzy_count (+ get_fg) and the strided full-resolution reads of the trimap kernel: per frame
+// the chunk moves about 7P bytes instead of 14P (P = pixels), see DESIGN.md section 4.
+//
+// A thread owns 16 destination columns and walks down `run` rows: the horizontal pass of a source row is computed once
+// for all the destination rows that use it; where every tap of both source rows has one value the interpolation is
+// that value (most of a matte is 0 or 255).  Arithmetic = cv2's fixed-point bilinear, as in
+// resize_up_int_kernel; HSV / get_fg arithmetic as in vu_composite.cu.
+#include "vu_common.cuh"
+
+namespace vu {
+namespace {
+
+constexpr int UT = 256;
+
+__device__ __forceinline__ int trunc_clamp255_(float x) { return f32_trunc_nonneg(fminf(fmaxf(x, 0.f), 255.f)); }
+
+template <int SC>
+__device__ __forceinline__ int wleft(int ph) {   // weight of the left / upper tap of phase ph, in 1/2048
+  return SC == 2 ? (ph == 0 ? 512 : 1536) : (ph == 0 ? 768 : (ph == 1 ? 256 : (ph == 2 ? 1792 : 1280)));
+}
+
+__device__ __forceinline__ void block_add2(unsigned a, unsigned b, unsigned long long* dst) {
+  __shared__ unsigned sh[2][UT / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(0xffffffffu, a, o);
+    b += __shfl_down_sync(0xffffffffu, b, o);
+  }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = a; sh[1][threadIdx.x >> 5] = b; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long sa = 0, sb = 0;
+#pragma unroll
+    for (int i = 0; i < UT / 32; ++i) { sa += sh[0][i]; sb += sh[1][i]; }
+    if (sa) atomicAdd(dst, sa);
+    if (sb) atomicAdd(dst + 1, sb);
+  }
+}
+
+template <int SC, bool FG>
+__global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __restrict__ alpha_lo, int th, int tw, const uint8_t* __restrict__ alt_src,
+                                                            const uint8_t* __restrict__ alt_flags, const uint8_t* __restrict__ frames, int lo0, int lo1,
+                                                            int lo2, int hi0, int hi1, int hi2, uint8_t* __restrict__ alpha,
+                                                            uint8_t* __restrict__ fzbits, uint8_t* __restrict__ mbits,
+                                                            unsigned long long* __restrict__ counts2, int run, int bgB, int bgG, int bgR,
+                                                            uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
+  __shared__ HsvTab tab;
+  __shared__ float ktab[FG ? 256 : 1];   // 1 - alpha/255. for every alpha byte
+  hsv_tab_init(tab);
+  if (FG)
+    for (int a = threadIdx.x; a < 256; a += UT) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
+  __syncthreads();
+  constexpr int NS = 16 / SC;   // source columns under the 16 destination columns
+  const int n = blockIdx.z;
+  const int h = SC * th, w = SC * tw;
+  const int lane = threadIdx.x & 31;
+  const int tx = blockIdx.x * 32 + lane;
+  const int ry = blockIdx.y * (UT / 32) + (threadIdx.x >> 5);
+  const int x0 = 16 * tx, y0 = ry * run;
+  const bool act = x0 < w;
+  const int y1 = min(h, y0 + run);
+  const bool alt = alt_flags && alt_flags[n] != 0;
+  const uint8_t* s = alpha_lo + (int64_t)n * th * tw;
+  const int c0 = NS * tx;
+  int h0 = 0, s0 = 0, v0 = 0;
+  if (FG) bgr2hsv_px(bgB, bgG, bgR, tab, h0, s0, v0);
+
+  // horizontal pass of source row sy (>> 4, as the vertical pass wants it); returns the common value of its taps or -1
+  auto hrow = [&](int sy, int (&R)[16]) -> int {
+    int t[NS + 2];   // source columns c0-1 .. c0+NS, replicated at the borders
+    const uint8_t* r = s + (int64_t)sy * tw;
+    if (SC == 2) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(r + c0));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        t[1 + k] = (int)((v.x >> (8 * k)) & 255u);
+        t[5 + k] = (int)((v.y >> (8 * k)) & 255u);
+      }
+    } else {
+      const unsigned v = __ldg(reinterpret_cast<const unsigned*>(r + c0));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t[1 + k] = (int)((v >> (8 * k)) & 255u);
+    }
+    t[0] = (int)__ldg(r + max(c0 - 1, 0));
+    t[NS + 1] = (int)__ldg(r + min(c0 + NS, tw - 1));
+    bool same = true;
+#pragma unroll
+    for (int k = 1; k < NS + 2; ++k) same = same && t[k] == t[0];
+    if (same) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) R[k] = t[0] << 7;
+      return t[0];
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int c = k / SC, ph = k % SC;
+      const int il = ph < SC / 2 ? c : c + 1;   // index into t of the left tap (t[c+1] is column c0 + c)
+      R[k] = (t[il] * wleft<SC>(ph) + t[il + 1] * (2048 - wleft<SC>(ph))) >> 4;
+    }
+    return -1;
+  };
+
+  int Ra[16], Rb[16];
+  int ya = -1, yb = -1, ua = -1, ub = -1;
+  unsigned cnt_f = 0, cnt_p = 0;
+  for (int y = y0; y < y1; ++y) {   // warp-uniform trip count: the shuffles below see the whole warp
+    const int r = y / SC, ph = y % SC;
+    unsigned aw[4] = {0u, 0u, 0u, 0u};
+    if (act) {
+      if (alt) {
+        const uint4 v = ldg_stream16(alt_src + ((int64_t)n * h + y) * w + x0);
+        aw[0] = v.x; aw[1] = v.y; aw[2] = v.z; aw[3] = v.w;
+      } else {
+        const int ia = ph < SC / 2 ? max(r - 1, 0) : r, ib = ph < SC / 2 ? r : min(r + 1, th - 1);
+        if (ia != ya) {
+          if (ia == yb) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) Ra[k] = Rb[k];
+            ua = ub;
+          } else {
+            ua = hrow(ia, Ra);
+          }
+          ya = ia;
+        }
+        if (ib != yb) {
+          if (ib == ya) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) Rb[k] = Ra[k];
+            ub = ua;
+          } else {
+            ub = hrow(ib, Rb);
+          }
+          yb = ib;
+        }
+        if (ua >= 0 && ua == ub) {
+          // every tap is ua and the weights sum to 2048 on both axes: the two halves lose less than 2 of 4 ua + 2 together
+          aw[0] = aw[1] = aw[2] = aw[3] = (unsigned)ua * 0x01010101u;
+        } else {
+          const int b0 = wleft<SC>(ph), b1 = 2048 - b0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const unsigned v = (unsigned)((((b0 * Ra[k]) >> 16) + ((b1 * Rb[k]) >> 16) + 2) >> 2);   // <= 255 by construction
+            aw[k >> 2] |= v << (8 * (k & 3));
+          }
+        }
+      }
+      stg_stream16(alpha + ((int64_t)n * h + y) * w + x0, make_uint4(aw[0], aw[1], aw[2], aw[3]));
+    }
+    // ---- B bits of the trimap source: pixels (SC*r, SC*c) of rows with y % SC == 0 ----
+    if (ph == 0) {   // warp-uniform
+      unsigned mb = 0;
+#pragma unroll
+      for (int c = 0; c < NS; ++c) {
+        const int k = SC * c;
+        mb |= ((aw[k >> 2] >> (8 * (k & 3) + 7)) & 1u) << c;
+      }
+      if (SC == 2) {
+        if (act) mbits[((int64_t)n * th + r) * (tw >> 3) + tx] = (uint8_t)mb;
+      } else {
+        const unsigned hi = __shfl_down_sync(0xffffffffu, mb, 1);
+        if (act && !(lane & 1)) mbits[((int64_t)n * th + r) * (tw >> 3) + (tx >> 1)] = (uint8_t)(mb | (hi << 4));
+      }
+    }
+    if (!act) continue;
+    // ---- fuzzy bits (+ fg / patched bg) ----
+    const unsigned any = aw[0] | aw[1] | aw[2] | aw[3];
+    unsigned fz = 0;
+    const int64_t fo = (((int64_t)n * h + y) * w + x0) * 3;
+    if (FG || any) {
+      uint4 fv[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frames + fo + 16 * k);
+      const unsigned* fw = reinterpret_cast<const unsigned*>(fv);
+      if (FG && !any) {
+        // alpha == 0 everywhere: patched background = the frame, fg = HSV2BGR(hsv - 1.0 * hsv) = black
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          stg_stream16(fg_out + fo + 16 * k, make_uint4(0u, 0u, 0u, 0u));
+          stg_stream16(bg_out + fo + 16 * k, fv[k]);
+        }
+      } else {
+        uint4 ov[3], bv[3];
+        unsigned* ow = reinterpret_cast<unsigned*>(ov);
+        unsigned* bw = reinterpret_cast<unsigned*>(bv);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (aw[g] == 0u) {
+            if (FG) {
+              ow[3 * g] = ow[3 * g + 1] = ow[3 * g + 2] = 0u;
+              bw[3 * g] = fw[3 * g]; bw[3 * g + 1] = fw[3 * g + 1]; bw[3 * g + 2] = fw[3 * g + 2];
+            }
+            continue;
+          }
+          int c[12], o[12], q[12];
+          unpack12(fw[3 * g], fw[3 * g + 1], fw[3 * g + 2], c);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int a = (int)((aw[g] >> (8 * i)) & 255u);
+            int ih, is, iv;
+            bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
+            const bool in = (ih >= lo0) & (ih <= hi0) & (is >= lo1) & (is <= hi1) & (iv >= lo2) & (iv <= hi2);
+            const bool pos = a != 0;
+            cnt_p += pos;
+            fz |= (unsigned)(pos && in) << (4 * g + i);
+            if (FG) {
+              const bool patch = a < 128;   // green.py:125
+              q[3 * i] = patch ? c[3 * i] : bgB;
+              q[3 * i + 1] = patch ? c[3 * i + 1] : bgG;
+              q[3 * i + 2] = patch ? c[3 * i + 2] : bgR;
+              const int bh = patch ? ih : h0, bs = patch ? is : s0, bvv = patch ? iv : v0;
+              const float k = ktab[a];
+              const int fh = trunc_clamp255_(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
+              const int fs = trunc_clamp255_(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
+              const int fv2 = trunc_clamp255_(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bvv))));
+              hsv2bgr_px(fh, fs, fv2, tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
+            }
+          }
+          if (FG) {
+            pack12(o, ow[3 * g], ow[3 * g + 1], ow[3 * g + 2]);
+            pack12(q, bw[3 * g], bw[3 * g + 1], bw[3 * g + 2]);
+          }
+        }
+        if (FG) {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            stg_stream16(fg_out + fo + 16 * k, ov[k]);
+            stg_stream16(bg_out + fo + 16 * k, bv[k]);
+          }
+        }
+      }
+    }
+    cnt_f += __popc(fz);
+    *reinterpret_cast<unsigned short*>(fzbits + (((int64_t)n * h + y) * w + x0) / 8) = (unsigned short)fz;
+  }
+  block_add2(cnt_f, cnt_p, counts2 + 2 * n);
+}
+
+}  // namespace
+}  // namespace vu
+
+using namespace vu;
+
+extern "C" int vu_cf_alpha_up_fuzzy(const uint8_t* alpha_lo, int n, int th, int tw, int h, int w, const uint8_t* alt_src, const uint8_t* alt_flags,
+                                    const uint8_t* frames, const int32_t lo[3], const int32_t hi[3], uint8_t* alpha, uint8_t* fuzzy_bits,
+                                    uint8_t* mask_bits, uint64_t* counts2, const uint8_t* bg_bgr, uint8_t* fg_out, uint8_t* bg_out,
+                                    vu_stream_t stream) {
+  VU_REQUIRE(alpha_lo && frames && lo && hi && alpha && fuzzy_bits && mask_bits && counts2 && n >= 0 && th > 0 && tw > 0);
+  VU_REQUIRE((alt_src == nullptr) == (alt_flags == nullptr));
+  VU_REQUIRE((fg_out == nullptr) == (bg_out == nullptr) && (fg_out == nullptr) == (bg_bgr == nullptr));
+  const int sc = (w == 2 * tw && h == 2 * th) ? 2 : ((w == 4 * tw && h == 4 * th) ? 4 : 0);
+  if (sc == 0 || tw % 16 != 0 || n > 65535) return VU_ERR_UNSUPPORTED;
+  const void* p16[] = {frames, alpha, alt_src, fg_out, bg_out};
+  for (const void* p : p16)
+    if (reinterpret_cast<uintptr_t>(p) & 15) return VU_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(alpha_lo) & 7) || (reinterpret_cast<uintptr_t>(fuzzy_bits) & 1)) return VU_ERR_UNSUPPORTED;
+  if (n == 0) return VU_OK;
+  int e = record_cuda(cudaMemsetAsync(counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
+  if (e) return e;
+  const int run = 8 * sc;   // destination rows per thread: 8 source rows
+  dim3 g((w / 16 + 31) / 32, ((h + run - 1) / run + UT / 32 - 1) / (UT / 32), n);
+  auto* c2 = reinterpret_cast<unsigned long long*>(counts2);
+  const int B = bg_bgr ? bg_bgr[0] : 0, G = bg_bgr ? bg_bgr[1] : 0, R = bg_bgr ? bg_bgr[2] : 0;
+#define VU_CALL(SCV, FGV)                                                                                                                       \
+  alpha_up_fuzzy_kernel<SCV, FGV><<<g, UT, 0, S(stream)>>>(alpha_lo, th, tw, alt_src, alt_flags, frames, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], \
+                                                           alpha, fuzzy_bits, mask_bits, c2, run, B, G, R, fg_out, bg_out)
+  if (sc == 2) {
+    if (fg_out) VU_CALL(2, true);
+    else VU_CALL(2, false);
+  } else {
+    if (fg_out) VU_CALL(4, true);
+    else VU_CALL(4, false);
+  }
+#undef VU_CALL
+  VU_RETURN_LAUNCH();
+}

@@ -43,8 +43,25 @@ __device__ __forceinline__ unsigned pick4(const uint8_t* p) {
   }
 }
 
+// bits 0, 2, 4 .. 30 of x -> bits 0 .. 15;  bits 0, 4, 8 .. 28 -> bits 0 .. 7
+__device__ __forceinline__ unsigned compress2(unsigned x) {
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0F0F0F0Fu;
+  x = (x | (x >> 4)) & 0x00FF00FFu;
+  return (x | (x >> 8)) & 0xFFFFu;
+}
+__device__ __forceinline__ unsigned compress4(unsigned x) {
+  x &= 0x11111111u;
+  x = (x | (x >> 3)) & 0x03030303u;
+  x = (x | (x >> 6)) & 0x000F000Fu;
+  return (x | (x >> 12)) & 0xFFu;
+}
+
 // plane p of frame n: planes[((p * nframes + n) * th + y) * wpr + j]
-template <int SC>
+// PACKED: the source arrives as bit planes written by vu_cf_alpha_up_fuzzy: mask = B bits at the working resolution
+// [n][th][tw/8] (nearest-sampled alpha >= 128), fuzzy = one bit per FULL-resolution pixel [n][h][w/8]; tw % 16 == 0.
+template <int SC, bool PACKED>
 __global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ fuzzy,
                                                                  const uint8_t* __restrict__ flags, int h, int w, int th, int tw, int passes,
                                                                  unsigned* __restrict__ planes, int nframes, int wpr) {
@@ -59,6 +76,27 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* 
   const uint8_t* mk = mask + (int64_t)n * h * w;
   const uint8_t* fz = fuzzy ? fuzzy + (int64_t)n * h * w : nullptr;
   // ---- B = (nearest-sampled mask >= 128, fuzzy pixels cleared), one bit per working-resolution pixel ----
+  if (PACKED) {
+    const uint8_t* mb = mask + (int64_t)n * th * (tw >> 3);
+    const uint8_t* fb = fuzzy ? fuzzy + (int64_t)n * h * (w >> 3) : nullptr;
+    for (int i = threadIdx.x; i < rows * TB_WORDS * 2; i += TB_THREADS) {   // 16 working-resolution pixels per item
+      const int r = i / (TB_WORDS * 2), hw = i % (TB_WORDS * 2);
+      const int y = Y0 + r, x = X0 + 16 * hw;
+      unsigned b = 0, in = 0;
+      if ((unsigned)y < (unsigned)th && x >= 0 && x < tw) {   // tw % 16 == 0: inside or outside as a whole
+        b = __ldg(reinterpret_cast<const unsigned short*>(mb + (int64_t)y * (tw >> 3) + (x >> 3)));
+        if (ens) {   // fuzzy bits of the full-resolution pixels (SC*y, SC*x .. SC*(x+15)): SC*16 bits, every SC-th one
+          const unsigned* f = reinterpret_cast<const unsigned*>(fb + (int64_t)SC * y * (w >> 3) + ((SC * x) >> 3));
+          const unsigned fz = SC == 2 ? compress2(__ldg(f)) : (compress4(__ldg(f)) | (compress4(__ldg(f + 1)) << 8));
+          b &= ~fz;
+        }
+        in = 0xFFFFu;
+      }
+      reinterpret_cast<unsigned short*>(&Db[0][r][0])[hw] = (unsigned short)b;
+      reinterpret_cast<unsigned short*>(&Eb[0][r][0])[hw] = (unsigned short)(b | (~in & 0xFFFFu));
+      reinterpret_cast<unsigned short*>(&In[r][0])[hw] = (unsigned short)in;
+    }
+  } else
   for (int r = warp; r < rows; r += TB_THREADS / 32) {
     const int y = Y0 + r, x = X0 + 4 * lane;
     unsigned nib = 0, inb = 0;
@@ -146,7 +184,8 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* 
 // plane index: (Z left, Z right, F left, F right) x (pair with the row above, pair with the row below) -> 2 * k + below.
 // NG groups of 4 output pixels per thread (4: 128-bit fuzzy loads and stores - a streaming kernel needs the bytes in
 // flight; 1: widths that are not a multiple of 16).  The NG groups of a thread read the same four plane words.
-template <int SC, int NG>
+// PACKED (NG == 4 only): fuzzy is the bit plane [n][h][w/8] of vu_cf_alpha_up_fuzzy
+template <int SC, int NG, bool PACKED>
 __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsigned* __restrict__ planes, int nframes, int th, int tw, int wpr,
                                                                     const uint8_t* __restrict__ fuzzy, const uint8_t* __restrict__ flags,
                                                                     uint8_t* __restrict__ out) {
@@ -167,12 +206,37 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
     const unsigned fl = __ldg(row + (4 + below) * psz + j) >> b, fr = __ldg(row + (6 + below) * psz + j) >> b;
     const int64_t o = ((int64_t)n * h + y) * w + (int64_t)t * 4 * NG;
     unsigned fz[NG];
-    if (ens) {
+    if (ens && PACKED) {
+      const unsigned bits = __ldg(reinterpret_cast<const unsigned short*>(fuzzy + (o >> 3)));
+#pragma unroll
+      for (int k = 0; k < NG; ++k) {
+        const unsigned nib = (bits >> (4 * k)) & 15u;
+        fz[k] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);   // 0 / 1 bytes, like the byte map
+      }
+    } else if (ens) {
       if (NG == 4) {
         const uint4 v = ldg_stream16(fuzzy + o);
         fz[0] = v.x; fz[1 % NG] = v.y; fz[2 % NG] = v.z; fz[3 % NG] = v.w;
       } else {
         fz[0] = __ldg(reinterpret_cast<const unsigned*>(fuzzy + o));
+      }
+    }
+    // flat runs (most of a trimap): every pixel of the thread's 4 * NG is 0 / 255 / 128 as soon as both halves' bits of
+    // its NG * CPG working-resolution columns agree - one test instead of the bit shuffling below (the kernel is bound
+    // by instruction issue, not by the bytes it writes)
+    constexpr unsigned CM = (1u << (NG * CPG)) - 1u;
+    bool anyfz = false;
+    if (ens) {
+#pragma unroll
+      for (int k = 0; k < NG; ++k) anyfz = anyfz || fz[k] != 0u;
+    }
+    if (!anyfz) {
+      const unsigned za = zl & zr & CM, fa = fl & fr & CM, un = (zl | zr | fl | fr) & CM;
+      if (za == CM || fa == CM || un == 0u) {
+        const unsigned v = za == CM ? 0u : (fa == CM ? 0xFFFFFFFFu : 0x80808080u);
+        if (NG == 4) stg_stream16(out + o, make_uint4(v, v, v, v));
+        else *reinterpret_cast<unsigned*>(out + o) = v;
+        continue;
       }
     }
     unsigned words[NG];
@@ -235,13 +299,45 @@ extern "C" int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const u
   dim3 gb((unsigned)(bx < 1 ? 1 : bx), n);
 #define VU_UP(SCV)                                                                                                                   \
   do {                                                                                                                               \
-    trimap_bits_kernel<SCV><<<ga, TB_THREADS, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, iters, planes, n, wpr);              \
-    if (ng == 4) trimap_up_bits_kernel<SCV, 4><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);          \
-    else trimap_up_bits_kernel<SCV, 1><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);                  \
+    trimap_bits_kernel<SCV, false><<<ga, TB_THREADS, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, iters, planes, n, wpr);       \
+    if (ng == 4) trimap_up_bits_kernel<SCV, 4, false><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);   \
+    else trimap_up_bits_kernel<SCV, 1, false><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);           \
   } while (0)
   if (sc == 2) VU_UP(2);
   else VU_UP(4);
 #undef VU_UP
+  note_launch();
+  VU_RETURN_LAUNCH();
+}
+
+// The same tail from the bit planes vu_cf_alpha_up_fuzzy leaves behind: mask_bits [n][th][tw/8] = nearest-sampled
+// alpha >= 128 at the working resolution, fuzzy_bits [n][h][w/8] = one bit per full-resolution pixel (may be NULL
+// together with flags: mask-only trimap).  No full-resolution byte map is read at all.  tw % 16 == 0.
+extern "C" int vu_trimap_bits_packed(const uint8_t* mask_bits, const uint8_t* fuzzy_bits, const uint8_t* flags, int n, int h, int w, int th, int tw,
+                                     int iters, uint8_t* out, void* workspace, size_t workspace_bytes, vu_stream_t stream) {
+  VU_REQUIRE(mask_bits && out && workspace && n >= 0 && h > 0 && w > 0 && th > 0 && tw > 0 && iters >= 0);
+  VU_REQUIRE((fuzzy_bits == nullptr) == (flags == nullptr));
+  const int sc = (w == 2 * tw && h == 2 * th) ? 2 : ((w == 4 * tw && h == 4 * th) ? 4 : 0);
+  if (sc == 0 || tw % 16 != 0 || iters > TB_MAXR || n > 65535) return VU_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) || (reinterpret_cast<uintptr_t>(mask_bits) & 1) || (reinterpret_cast<uintptr_t>(fuzzy_bits) & 3))
+    return VU_ERR_UNSUPPORTED;
+  if (workspace_bytes < vu_trimap_bits_workspace_bytes(n, th, tw) || (reinterpret_cast<uintptr_t>(workspace) & 3)) return VU_ERR_WORKSPACE;
+  if (n == 0) return VU_OK;
+  const int wpr = (tw + 31) / 32;
+  unsigned* planes = static_cast<unsigned*>(workspace);
+  dim3 ga((tw + TB_OW - 1) / TB_OW, (th + TB_OH - 1) / TB_OH, n);
+  const int64_t items = (int64_t)h * (w / 16);
+  int64_t bx = (items + TB_THREADS - 1) / TB_THREADS;
+  const int64_t cap = ((int64_t)device_sms() * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  dim3 gb((unsigned)(bx < 1 ? 1 : bx), n);
+  if (sc == 2) {
+    trimap_bits_kernel<2, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr);
+    trimap_up_bits_kernel<2, 4, true><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy_bits, flags, out);
+  } else {
+    trimap_bits_kernel<4, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr);
+    trimap_up_bits_kernel<4, 4, true><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy_bits, flags, out);
+  }
   note_launch();
   VU_RETURN_LAUNCH();
 }

@@ -154,6 +154,44 @@ def trimap_bits(masks, th, tw, iters, fuzzy=None, flags=None, out=None):
     return out
 
 
+def cf_up_supported(frames, alpha_lo, h, w, th, tw, *others):
+    """vu_cf_alpha_up_fuzzy / vu_trimap_bits_packed: exact 2x / 4x working resolution, tw % 16 == 0, 16-byte aligned clips"""
+    exact = (h == 2 * th and w == 2 * tw) or (h == 4 * th and w == 4 * tw)
+    return exact and tw % 16 == 0 and all(t is None or t.data_ptr() % 16 == 0 for t in (frames, alpha_lo) + others)
+
+
+def cf_alpha_up_fuzzy(alpha_lo, h, w, frames, lo, hi, alt_src=None, alt_flags=None, out=None, bg_bgr=None, fg_out=None, bg_out=None):
+    """colorfiltering/agent.py:342 + trimap/agent.py:84-94 (+ green.py:125-126 with ``bg_bgr``) in one pass, see
+    vu_cf_alpha_up_fuzzy.  -> alpha [n,h,w], fuzzy bits [n,h,w/8], mask bits [n,th,tw/8], counts [n,2] (+ fg, bg)."""
+    alpha_lo, frames = _mask(alpha_lo), _img(frames)
+    n = 1 if alpha_lo.ndim == 2 else alpha_lo.shape[0]
+    th, tw = alpha_lo.shape[-2:]
+    dev = alpha_lo.device
+    alpha = _out(out, (h, w) if alpha_lo.ndim == 2 else (n, h, w), dev)
+    fzb = torch.empty((n, h, w // 8), dtype=u8, device=dev)
+    mb = torch.empty((n, th, tw // 8), dtype=u8, device=dev)
+    counts = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    col = None
+    if bg_bgr is not None:
+        col = np.ascontiguousarray(np.asarray(bg_bgr, dtype=np.uint8).reshape(3))
+        fg_out = _out(fg_out, frames.shape, dev)
+        bg_out = _out(bg_out, frames.shape, dev)
+    check(lib().vu_cf_alpha_up_fuzzy(_p(alpha_lo), n, th, tw, int(h), int(w), _p(alt_src), _p(alt_flags), _p(frames), i3(lo), i3(hi), _p(alpha),
+                                     _p(fzb), _p(mb), _p(counts), col.ctypes.data if col is not None else None, _p(fg_out), _p(bg_out), _stream()))
+    return (alpha, fzb, mb, counts) + ((fg_out, bg_out) if col is not None else ())
+
+
+def trimap_bits_packed(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, out=None):
+    """the trimap tail from the bit planes of cf_alpha_up_fuzzy (vu_trimap_bits_packed) -> trimaps [n,h,w]"""
+    n = mask_bits.shape[0]
+    out = _out(out, (n, h, w), mask_bits.device)
+    ws_bytes = int(lib().vu_trimap_bits_workspace_bytes(n, int(th), int(tw)))
+    ws = torch.empty(ws_bytes, dtype=u8, device=mask_bits.device)
+    check(lib().vu_trimap_bits_packed(_p(_dev(mask_bits)), _p(fuzzy_bits), _p(flags), n, int(h), int(w), int(th), int(tw), int(iters), _p(out),
+                                      _p(ws), ws_bytes, _stream()))
+    return out
+
+
 def dilate(x, ksize, iters):
     return morph(x, ksize, iters, _lib.DILATE)
 
