@@ -277,7 +277,7 @@ def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0
     return out
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2, fused=True):
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2, fused=True, out=None):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
     stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
     [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.
@@ -286,10 +286,13 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None
     in when the call is captured into a CUDA graph (fetching them synchronises)."""
     n, h, w, _ = frames.shape
     dev = frames.device
-    alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-    tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-    fg = torch.empty_like(frames)
-    bgo = torch.empty_like(frames)
+    if out is not None:      # (alpha, trimap, fg, bg) of an earlier call: steady-state callers reuse their result buffers
+        alpha, tri, fg, bgo = out
+    else:
+        alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        fg = torch.empty_like(frames)
+        bgo = torch.empty_like(frames)
     if bg_color is None:
         bg_color = cf_agent.bg_color_bgr()
     if bg_tile is None:
@@ -329,7 +332,7 @@ def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None, out=None):
     return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg, out=out)
 
 
-def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_size=None):
+def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_size=None, out=None):
     """bg_step: exact temporal-median background, then per frame the difference
     gate (bg_offline.py:154-160), mask-only trimap (:166) and get_fg with the
     alpha==0 patch (:171-172), CNN stage skipped (alpha := gated mask).
@@ -337,10 +340,14 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_s
     resolution when ``frames`` is a row tile (see bgstep_clip_tile)."""
     n, h, w, _ = frames.shape
     dev = frames.device
-    bg = ops.temporal_median(frames)
-    alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-    tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
-    fg = torch.empty_like(frames)
+    if out is not None:      # (background, alpha, trimap, fg) of an earlier call, reused
+        bg, alpha, tri, fg = out
+        ops.temporal_median(frames, out=bg)
+    else:
+        bg = ops.temporal_median(frames)
+        alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
+        fg = torch.empty_like(frames)
     def body(s, e):
         # every stage writes straight into its slice of the clip-sized results
         if ops.bgdiff_gate_supported(frames[s:e], bg, masks[s:e]):
@@ -370,7 +377,7 @@ def bgstep_tile_geometry(h, w, trimap_agent, rank, world):
     return r0, r1, ht, hb, scale, (th, tw)
 
 
-def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24, rows=None, streams=2):
+def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24, rows=None, streams=2, out=None):
     """bgstep_clip on this rank's ROW TILE of the clip (BASELINE config 5: spatial-tile sharding):
     the temporal median of the tile's rows (every pixel is independent), then the per-frame stages on the tile plus a
     halo (shard.bgstep_halo: 28 rows above, 24 below at 4K) read from the local frames, cropped back.  ``frames`` /
@@ -378,7 +385,8 @@ def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24,
     cover the tile plus its halo (what a rank that holds just its share of the clip passes).  Tile and halo boundaries
     are multiples of the scale (frame size / working size, decided by the WHOLE frame), so the tile's down-scales sample
     the pixels the whole frame's do: the results equal the corresponding rows of bgstep_clip on the whole clip, bit for
-    bit.  Returns (r0, r1), background, alpha, trimap, fg for rows [r0, r1)."""
+    bit.  Returns (r0, r1), background, alpha, trimap, fg for rows [r0, r1) (views of the tile-plus-halo results;
+    ``out`` = those tile-plus-halo buffers of an earlier call - ``x._base`` of the returned views - to reuse them)."""
     n, hh, w, _ = frames.shape
     base, h = (rows[0], rows[2]) if rows is not None else (0, hh)
     r0, r1, ht, hb, scale, (th, tw) = bgstep_tile_geometry(h, w, trimap_agent, rank, world)
@@ -390,6 +398,6 @@ def bgstep_clip_tile(frames, masks, trimap_agent, rank, world, thr=25, chunk=24,
     ftile = ftile if ftile.is_contiguous() else ftile.contiguous()
     mtile = mtile if mtile.is_contiguous() else mtile.contiguous()
     bg_t, alpha_t, tri_t, fg_t = bgstep_clip(ftile, mtile, trimap_agent, thr=thr, chunk=chunk, streams=streams,
-                                             work_size=((a1 - a0) // scale, tw))
+                                             work_size=((a1 - a0) // scale, tw), out=out)
     lo, hi = ht, ht + (r1 - r0)
     return (r0, r1), bg_t[lo:hi], alpha_t[:, lo:hi], tri_t[:, lo:hi], fg_t[:, lo:hi]

@@ -14,9 +14,10 @@
 // replaces resize_up + fuzzy_count (+ get_fg) and the strided full-resolution reads of the trimap kernel: per frame
 // the chunk moves about 7P bytes instead of 14P (P = pixels), see DESIGN.md section 4.
 //
-// A thread owns 16 destination columns and walks down `run` rows: the horizontal pass of a source row is computed once
-// for all the destination rows that use it; where every tap of both source rows has one value the interpolation is
-// that value (most of a matte is 0 or 255).  Arithmetic = cv2's fixed-point bilinear, as in
+// A thread owns 16 destination columns of ONE row (a warp: 512 columns of it), so that every load of the kernel is
+// independent of every other thread's (a first version walked 16 rows per thread to reuse the horizontal pass and
+// spent its time waiting: one DRAM round trip per row, 830 GB/s); where every tap of both source rows has one value
+// the interpolation is that value (most of a matte is 0 or 255).  Arithmetic = cv2's fixed-point bilinear, as in
 // resize_up_int_kernel; HSV / get_fg arithmetic as in vu_composite.cu.
 #include "vu_common.cuh"
 
@@ -24,6 +25,7 @@ namespace vu {
 namespace {
 
 constexpr int UT = 256;
+constexpr int UP_ROWS = 4;   // destination rows per warp of alpha_up_fuzzy_kernel
 
 __device__ __forceinline__ int trunc_clamp255_(float x) { return f32_trunc_nonneg(fminf(fmaxf(x, 0.f), 255.f)); }
 
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
                                                             const uint8_t* __restrict__ alt_flags, const uint8_t* __restrict__ frames, int lo0, int lo1,
                                                             int lo2, int hi0, int hi1, int hi2, uint8_t* __restrict__ alpha,
                                                             uint8_t* __restrict__ fzbits, uint8_t* __restrict__ mbits,
-                                                            unsigned long long* __restrict__ counts2, int run, int bgB, int bgG, int bgR,
+                                                            unsigned long long* __restrict__ counts2, int bgB, int bgG, int bgR,
                                                             uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
   __shared__ HsvTab tab;
   __shared__ float ktab[FG ? 256 : 1];   // 1 - alpha/255. for every alpha byte
@@ -68,182 +70,161 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
   const int h = SC * th, w = SC * tw;
   const int lane = threadIdx.x & 31;
   const int tx = blockIdx.x * 32 + lane;
-  const int ry = blockIdx.y * (UT / 32) + (threadIdx.x >> 5);
-  const int x0 = 16 * tx, y0 = ry * run;
-  const bool act = x0 < w;
-  const int y1 = min(h, y0 + run);
+  const int x0 = 16 * tx;
   const bool alt = alt_flags && alt_flags[n] != 0;
   const uint8_t* s = alpha_lo + (int64_t)n * th * tw;
   const int c0 = NS * tx;
-  int h0 = 0, s0 = 0, v0 = 0;
-  if (FG) bgr2hsv_px(bgB, bgG, bgR, tab, h0, s0, v0);
-
-  // horizontal pass of source row sy (>> 4, as the vertical pass wants it); returns the common value of its taps or -1
-  auto hrow = [&](int sy, int (&R)[16]) -> int {
-    int t[NS + 2];   // source columns c0-1 .. c0+NS, replicated at the borders
-    const uint8_t* r = s + (int64_t)sy * tw;
-    if (SC == 2) {
-      const uint2 v = __ldg(reinterpret_cast<const uint2*>(r + c0));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        t[1 + k] = (int)((v.x >> (8 * k)) & 255u);
-        t[5 + k] = (int)((v.y >> (8 * k)) & 255u);
-      }
-    } else {
-      const unsigned v = __ldg(reinterpret_cast<const unsigned*>(r + c0));
-#pragma unroll
-      for (int k = 0; k < 4; ++k) t[1 + k] = (int)((v >> (8 * k)) & 255u);
-    }
-    t[0] = (int)__ldg(r + max(c0 - 1, 0));
-    t[NS + 1] = (int)__ldg(r + min(c0 + NS, tw - 1));
-    bool same = true;
-#pragma unroll
-    for (int k = 1; k < NS + 2; ++k) same = same && t[k] == t[0];
-    if (same) {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) R[k] = t[0] << 7;
-      return t[0];
-    }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
-      const int c = k / SC, ph = k % SC;
-      const int il = ph < SC / 2 ? c : c + 1;   // index into t of the left tap (t[c+1] is column c0 + c)
-      R[k] = (t[il] * wleft<SC>(ph) + t[il + 1] * (2048 - wleft<SC>(ph))) >> 4;
-    }
-    return -1;
-  };
-
-  int Ra[16], Rb[16];
-  int ya = -1, yb = -1, ua = -1, ub = -1;
+  int h0v = 0, s0v = 0, v0v = 0;
+  if (FG) bgr2hsv_px(bgB, bgG, bgR, tab, h0v, s0v, v0v);
   unsigned cnt_f = 0, cnt_p = 0;
-  for (int y = y0; y < y1; ++y) {   // warp-uniform trip count: the shuffles below see the whole warp
-    const int r = y / SC, ph = y % SC;
-    unsigned aw[4] = {0u, 0u, 0u, 0u};
-    if (act) {
-      if (alt) {
-        const uint4 v = ldg_stream16(alt_src + ((int64_t)n * h + y) * w + x0);
-        aw[0] = v.x; aw[1] = v.y; aw[2] = v.z; aw[3] = v.w;
-      } else {
-        const int ia = ph < SC / 2 ? max(r - 1, 0) : r, ib = ph < SC / 2 ? r : min(r + 1, th - 1);
-        if (ia != ya) {
-          if (ia == yb) {
+  // a warp takes one destination row at a time (UP_ROWS of them, interleaved with the CTA's other warps: the table set-up
+  // above is paid once per UP_ROWS * 8 rows); the rows of a thread do not depend on each other
+#pragma unroll 1
+  for (int it = 0; it < UP_ROWS; ++it) {
+  const int y = (blockIdx.y * UP_ROWS + it) * (UT / 32) + (threadIdx.x >> 5);
+  if (y >= h) break;   // warp-uniform
+  const bool act = x0 < w;
+  const int r = y / SC, ph = y % SC;
+  unsigned aw[4] = {0u, 0u, 0u, 0u};
+  const int64_t fo = (((int64_t)n * h + y) * w + x0) * 3;
+  uint4 fv[3];
+  if (FG && act) {   // the patched background needs the frame everywhere: fetch it before anything else
 #pragma unroll
-            for (int k = 0; k < 16; ++k) Ra[k] = Rb[k];
-            ua = ub;
-          } else {
-            ua = hrow(ia, Ra);
-          }
-          ya = ia;
-        }
-        if (ib != yb) {
-          if (ib == ya) {
+    for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frames + fo + 16 * k);
+  }
+  if (act) {
+    if (alt) {
+      const uint4 v = ldg_stream16(alt_src + ((int64_t)n * h + y) * w + x0);
+      aw[0] = v.x; aw[1] = v.y; aw[2] = v.z; aw[3] = v.w;
+    } else {
+      // taps: source columns c0-1 .. c0+NS (replicated at the borders) of the two source rows
+      const int ia = ph < SC / 2 ? max(r - 1, 0) : r, ib = ph < SC / 2 ? r : min(r + 1, th - 1);
+      int t[2][NS + 2];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) Rb[k] = Ra[k];
-            ub = ua;
-          } else {
-            ub = hrow(ib, Rb);
+      for (int j = 0; j < 2; ++j) {
+        const uint8_t* row = s + (int64_t)(j ? ib : ia) * tw;
+        if (SC == 2) {
+          const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + c0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            t[j][1 + k] = (int)((v.x >> (8 * k)) & 255u);
+            t[j][5 + k] = (int)((v.y >> (8 * k)) & 255u);
           }
-          yb = ib;
-        }
-        if (ua >= 0 && ua == ub) {
-          // every tap is ua and the weights sum to 2048 on both axes: the two halves lose less than 2 of 4 ua + 2 together
-          aw[0] = aw[1] = aw[2] = aw[3] = (unsigned)ua * 0x01010101u;
         } else {
-          const int b0 = wleft<SC>(ph), b1 = 2048 - b0;
+          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(row + c0));
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const unsigned v = (unsigned)((((b0 * Ra[k]) >> 16) + ((b1 * Rb[k]) >> 16) + 2) >> 2);   // <= 255 by construction
-            aw[k >> 2] |= v << (8 * (k & 3));
-          }
+          for (int k = 0; k < 4; ++k) t[j][1 + k] = (int)((v >> (8 * k)) & 255u);
+        }
+        t[j][0] = (int)__ldg(row + max(c0 - 1, 0));
+        t[j][NS + 1] = (int)__ldg(row + min(c0 + NS, tw - 1));
+      }
+      bool same = true;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int k = 0; k < NS + 2; ++k) same = same && t[j][k] == t[0][0];
+      if (same) {
+        // every tap has one value and the weights sum to 2048 on both axes: the two halves lose less than 2 of 4v + 2 together
+        aw[0] = aw[1] = aw[2] = aw[3] = (unsigned)t[0][0] * 0x01010101u;
+      } else {
+        const int b0 = wleft<SC>(ph), b1 = 2048 - b0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int c = k / SC, p = k % SC;
+          const int il = p < SC / 2 ? c : c + 1;   // index into t of the left tap (t[c+1] is column c0 + c)
+          const int Ra = (t[0][il] * wleft<SC>(p) + t[0][il + 1] * (2048 - wleft<SC>(p))) >> 4;
+          const int Rb = (t[1][il] * wleft<SC>(p) + t[1][il + 1] * (2048 - wleft<SC>(p))) >> 4;
+          const unsigned v = (unsigned)((((b0 * Ra) >> 16) + ((b1 * Rb) >> 16) + 2) >> 2);   // <= 255 by construction
+          aw[k >> 2] |= v << (8 * (k & 3));
         }
       }
-      stg_stream16(alpha + ((int64_t)n * h + y) * w + x0, make_uint4(aw[0], aw[1], aw[2], aw[3]));
     }
-    // ---- B bits of the trimap source: pixels (SC*r, SC*c) of rows with y % SC == 0 ----
-    if (ph == 0) {   // warp-uniform
-      unsigned mb = 0;
+    stg_stream16(alpha + ((int64_t)n * h + y) * w + x0, make_uint4(aw[0], aw[1], aw[2], aw[3]));
+  }
+  // ---- B bits of the trimap source: pixels (SC*r, SC*c) of rows with y % SC == 0 (warp-uniform: a warp is one row) ----
+  if (ph == 0) {
+    unsigned mb = 0;
 #pragma unroll
-      for (int c = 0; c < NS; ++c) {
-        const int k = SC * c;
-        mb |= ((aw[k >> 2] >> (8 * (k & 3) + 7)) & 1u) << c;
-      }
-      if (SC == 2) {
-        if (act) mbits[((int64_t)n * th + r) * (tw >> 3) + tx] = (uint8_t)mb;
-      } else {
-        const unsigned hi = __shfl_down_sync(0xffffffffu, mb, 1);
-        if (act && !(lane & 1)) mbits[((int64_t)n * th + r) * (tw >> 3) + (tx >> 1)] = (uint8_t)(mb | (hi << 4));
-      }
+    for (int c = 0; c < NS; ++c) {
+      const int k = SC * c;
+      mb |= ((aw[k >> 2] >> (8 * (k & 3) + 7)) & 1u) << c;
     }
-    if (!act) continue;
-    // ---- fuzzy bits (+ fg / patched bg) ----
+    if (SC == 2) {
+      if (act) mbits[((int64_t)n * th + r) * (tw >> 3) + tx] = (uint8_t)mb;
+    } else {
+      const unsigned hi = __shfl_down_sync(0xffffffffu, mb, 1);
+      if (act && !(lane & 1)) mbits[((int64_t)n * th + r) * (tw >> 3) + (tx >> 1)] = (uint8_t)(mb | (hi << 4));
+    }
+  }
+  // ---- fuzzy bits (+ fg / patched bg) ----
+  if (act) {
     const unsigned any = aw[0] | aw[1] | aw[2] | aw[3];
     unsigned fz = 0;
-    const int64_t fo = (((int64_t)n * h + y) * w + x0) * 3;
-    if (FG || any) {
-      uint4 fv[3];
+    if (!FG && any) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frames + fo + 16 * k);
+    }
+    if (FG && !any) {
+      // alpha == 0 everywhere: patched background = the frame, fg = HSV2BGR(hsv - 1.0 * hsv) = black
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        stg_stream16(fg_out + fo + 16 * k, make_uint4(0u, 0u, 0u, 0u));
+        stg_stream16(bg_out + fo + 16 * k, fv[k]);
+      }
+    } else if (any) {
       const unsigned* fw = reinterpret_cast<const unsigned*>(fv);
-      if (FG && !any) {
-        // alpha == 0 everywhere: patched background = the frame, fg = HSV2BGR(hsv - 1.0 * hsv) = black
+      uint4 ov[3], bv[3];
+      unsigned* ow = reinterpret_cast<unsigned*>(ov);
+      unsigned* bw = reinterpret_cast<unsigned*>(bv);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          stg_stream16(fg_out + fo + 16 * k, make_uint4(0u, 0u, 0u, 0u));
-          stg_stream16(bg_out + fo + 16 * k, fv[k]);
-        }
-      } else {
-        uint4 ov[3], bv[3];
-        unsigned* ow = reinterpret_cast<unsigned*>(ov);
-        unsigned* bw = reinterpret_cast<unsigned*>(bv);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (aw[g] == 0u) {
-            if (FG) {
-              ow[3 * g] = ow[3 * g + 1] = ow[3 * g + 2] = 0u;
-              bw[3 * g] = fw[3 * g]; bw[3 * g + 1] = fw[3 * g + 1]; bw[3 * g + 2] = fw[3 * g + 2];
-            }
-            continue;
-          }
-          int c[12], o[12], q[12];
-          unpack12(fw[3 * g], fw[3 * g + 1], fw[3 * g + 2], c);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int a = (int)((aw[g] >> (8 * i)) & 255u);
-            int ih, is, iv;
-            bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
-            const bool in = (ih >= lo0) & (ih <= hi0) & (is >= lo1) & (is <= hi1) & (iv >= lo2) & (iv <= hi2);
-            const bool pos = a != 0;
-            cnt_p += pos;
-            fz |= (unsigned)(pos && in) << (4 * g + i);
-            if (FG) {
-              const bool patch = a < 128;   // green.py:125
-              q[3 * i] = patch ? c[3 * i] : bgB;
-              q[3 * i + 1] = patch ? c[3 * i + 1] : bgG;
-              q[3 * i + 2] = patch ? c[3 * i + 2] : bgR;
-              const int bh = patch ? ih : h0, bs = patch ? is : s0, bvv = patch ? iv : v0;
-              const float k = ktab[a];
-              const int fh = trunc_clamp255_(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
-              const int fs = trunc_clamp255_(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
-              const int fv2 = trunc_clamp255_(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bvv))));
-              hsv2bgr_px(fh, fs, fv2, tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
-            }
-          }
+      for (int g = 0; g < 4; ++g) {
+        if (aw[g] == 0u) {
           if (FG) {
-            pack12(o, ow[3 * g], ow[3 * g + 1], ow[3 * g + 2]);
-            pack12(q, bw[3 * g], bw[3 * g + 1], bw[3 * g + 2]);
+            ow[3 * g] = ow[3 * g + 1] = ow[3 * g + 2] = 0u;
+            bw[3 * g] = fw[3 * g]; bw[3 * g + 1] = fw[3 * g + 1]; bw[3 * g + 2] = fw[3 * g + 2];
+          }
+          continue;
+        }
+        int c[12], o[12], q[12];
+        unpack12(fw[3 * g], fw[3 * g + 1], fw[3 * g + 2], c);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int a = (int)((aw[g] >> (8 * i)) & 255u);
+          int ih, is, iv;
+          bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
+          const bool in = (ih >= lo0) & (ih <= hi0) & (is >= lo1) & (is <= hi1) & (iv >= lo2) & (iv <= hi2);
+          const bool pos = a != 0;
+          cnt_p += pos;
+          fz |= (unsigned)(pos && in) << (4 * g + i);
+          if (FG) {
+            const bool patch = a < 128;   // green.py:125
+            q[3 * i] = patch ? c[3 * i] : bgB;
+            q[3 * i + 1] = patch ? c[3 * i + 1] : bgG;
+            q[3 * i + 2] = patch ? c[3 * i + 2] : bgR;
+            const int bh = patch ? ih : h0v, bs = patch ? is : s0v, bvv = patch ? iv : v0v;
+            const float k = ktab[a];
+            const int fh = trunc_clamp255_(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
+            const int fs = trunc_clamp255_(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
+            const int fv2 = trunc_clamp255_(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bvv))));
+            hsv2bgr_px(fh, fs, fv2, tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
           }
         }
         if (FG) {
+          pack12(o, ow[3 * g], ow[3 * g + 1], ow[3 * g + 2]);
+          pack12(q, bw[3 * g], bw[3 * g + 1], bw[3 * g + 2]);
+        }
+      }
+      if (FG) {
 #pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            stg_stream16(fg_out + fo + 16 * k, ov[k]);
-            stg_stream16(bg_out + fo + 16 * k, bv[k]);
-          }
+        for (int k = 0; k < 3; ++k) {
+          stg_stream16(fg_out + fo + 16 * k, ov[k]);
+          stg_stream16(bg_out + fo + 16 * k, bv[k]);
         }
       }
     }
     cnt_f += __popc(fz);
     *reinterpret_cast<unsigned short*>(fzbits + (((int64_t)n * h + y) * w + x0) / 8) = (unsigned short)fz;
+  }
   }
   block_add2(cnt_f, cnt_p, counts2 + 2 * n);
 }
@@ -269,13 +250,12 @@ extern "C" int vu_cf_alpha_up_fuzzy(const uint8_t* alpha_lo, int n, int th, int 
   if (n == 0) return VU_OK;
   int e = record_cuda(cudaMemsetAsync(counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
   if (e) return e;
-  const int run = 8 * sc;   // destination rows per thread: 8 source rows
-  dim3 g((w / 16 + 31) / 32, ((h + run - 1) / run + UT / 32 - 1) / (UT / 32), n);
+  dim3 g((w / 16 + 31) / 32, (h + UP_ROWS * (UT / 32) - 1) / (UP_ROWS * (UT / 32)), n);
   auto* c2 = reinterpret_cast<unsigned long long*>(counts2);
   const int B = bg_bgr ? bg_bgr[0] : 0, G = bg_bgr ? bg_bgr[1] : 0, R = bg_bgr ? bg_bgr[2] : 0;
 #define VU_CALL(SCV, FGV)                                                                                                                       \
   alpha_up_fuzzy_kernel<SCV, FGV><<<g, UT, 0, S(stream)>>>(alpha_lo, th, tw, alt_src, alt_flags, frames, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], \
-                                                           alpha, fuzzy_bits, mask_bits, c2, run, B, G, R, fg_out, bg_out)
+                                                           alpha, fuzzy_bits, mask_bits, c2, B, G, R, fg_out, bg_out)
   if (sc == 2) {
     if (fg_out) VU_CALL(2, true);
     else VU_CALL(2, false);
