@@ -463,3 +463,95 @@ def temporal_median(frames):
     lo = part[k].astype(np.uint16)
     hi = part[n // 2].astype(np.uint16)
     return ((lo + hi) >> 1).astype(np.uint8)
+
+
+# --------------------------------------------------------------------------
+# BackgroundAgent: 'mean' and 'pcov' branches; 'rf' (sparse
+# Laplace solve with scipy) is not restated
+# --------------------------------------------------------------------------
+
+def get_fgbox(fgmask, padsize=5):
+    """unscreen/utils/maskprocess.py:37-53 (rows first: 'left/right' are row bounds, 'top/bottom' column bounds)."""
+    h, w = fgmask.shape
+    x, y = np.where(fgmask > 0)
+    left, right, top, bottom = np.min(x), np.max(x), np.min(y), np.max(y)
+    return max(left - padsize, 0), min(right + padsize, h), max(top - padsize, 0), min(bottom + padsize, w)
+
+
+def box_sum(a, k):
+    """k x k window sums with cv2's default BORDER_REFLECT_101; a is [H,W] or [H,W,C] int64.  A window reaches k//2
+    up / left and k - 1 - k//2 down / right of its anchor (cv2's default anchor: the window centre)."""
+    r0, r1 = k // 2, k - 1 - k // 2
+    pad = ((r0, r1), (r0, r1)) + ((0, 0),) * (a.ndim - 2)
+    p = np.pad(a, pad, mode="reflect")
+    h, w = a.shape[:2]
+    s = np.zeros(a.shape, np.int64)
+    for dy in range(k):
+        for dx in range(k):
+            s += p[dy:dy + h, dx:dx + w]
+    return s
+
+
+def box_filter_u8(img, k):
+    """cv2.boxFilter(uint8, -1, (k,k)): the rounded window mean (k*k odd: the mean is never a tie)"""
+    s = box_sum(img.astype(np.int64), k)
+    return ((2 * s + k * k) // (2 * k * k)).astype(np.uint8)
+
+
+def bg_mean_hsv(img_hsv, mask, boundary_ksize=7, boundary_iters=10):
+    """BackgroundAgent.get_mean_bg, unscreen/bgmodel/agent.py:66-93 -> the HSV colour (3 uint8)."""
+    boundary = get_outer_boundary(mask, boundary_ksize, boundary_iters) > 0
+    n = int(boundary.sum())
+    if n == 0:
+        col = np.mean(img_hsv, axis=(0, 1))                  # float64, truncated by the uint8 assignment of :91
+    else:
+        col = (img_hsv * boundary[..., None]).sum(axis=(0, 1)) / n
+    return col.astype(np.uint8)
+
+
+def bg_by_pcov(img, mask, ksize=5):
+    """BackgroundAgent.get_bg_by_pcov, unscreen/bgmodel/agent.py:95-131: iterated normalised box filters of the image
+    with the hole zeroed and of the 0/1 validity map; pixels whose window saw a valid pixel take mean / validity
+    (float64 division, clipped, truncated by the uint8 store) and become valid; stops once every pixel of the box
+    around the hole is valid, after at most 100 rounds.  EVERY round re-filters the whole box, valid pixels too."""
+    bgimg = img.copy()
+    bgimg[mask > 0] = 0
+    count = (mask == 0).astype(np.float64)
+    x0, x1, y0, y1 = get_fgbox(mask, padsize=ksize)
+    num_pixels = (x1 - x0) * (y1 - y0)
+    count = count[x0:x1, y0:y1]
+    roi = bgimg[x0:x1, y0:y1]
+    for _ in range(100):
+        roi = box_filter_u8(roi, ksize)
+        count = box_sum(count.astype(np.int64), ksize).astype(np.float64) * (1.0 / (ksize * ksize))
+        sel = count > 0
+        roi[sel] = np.clip(roi[sel] / count[sel][..., None], 0, 255)      # float64 -> uint8 store truncates
+        count[sel] = 1
+        if count.sum() >= num_pixels:
+            break
+    bgimg[x0:x1, y0:y1] = roi
+    return bgimg
+
+
+def background_forward(img, mask, method="rf", input_long_side=540, dilation_ksize=5, dilation_iters=3, boundary_ksize=7,
+                       boundary_iters=10, pcov_ksize=5):
+    """BackgroundAgent.forward, unscreen/bgmodel/agent.py:159-208, methods 'mean' and 'pcov'."""
+    oh, ow = mask.shape
+    if (mask == 0).sum() == 0:
+        return np.zeros(img.shape)                         # float64 zeros, as the reference returns them (:178)
+    if mask.sum() == 0:
+        return img
+    ih, iw = get_target_size(oh, ow, input_long_side)
+    img = cvm.resize_linear(img, iw, ih)
+    mask = cvm.resize_linear(mask, iw, ih)
+    dil = dilate_mask(mask, dilation_ksize, dilation_iters)
+    if method == "mean":
+        col = bg_mean_hsv(cvm.bgr2hsv(img), dil, boundary_ksize, boundary_iters)
+        bg_hsv = np.empty(img.shape, np.uint8)
+        bg_hsv[:] = col
+        bgimg = fuse_fgbg(cvm.hsv2bgr(bg_hsv), img, dil)
+    elif method == "pcov":
+        bgimg = fuse_fgbg(bg_by_pcov(img, dil, pcov_ksize), img, dil)
+    else:
+        raise NameError(f"No such method for background inpainting: {method}")
+    return cvm.resize_linear(bgimg, ow, oh)

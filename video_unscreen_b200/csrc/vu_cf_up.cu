@@ -25,7 +25,7 @@ namespace vu {
 namespace {
 
 constexpr int UT = 256;
-constexpr int UP_ROWS = 4;   // destination rows per warp of alpha_up_fuzzy_kernel
+constexpr int UP_ROWS = 8;   // destination rows per warp of alpha_up_fuzzy_kernel
 
 __device__ __forceinline__ int trunc_clamp255_(float x) { return f32_trunc_nonneg(fminf(fmaxf(x, 0.f), 255.f)); }
 
@@ -61,7 +61,8 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
                                                             uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
   __shared__ HsvTab tab;
   __shared__ float ktab[FG ? 256 : 1];   // 1 - alpha/255. for every alpha byte
-  hsv_tab_init(tab);
+  if (FG) hsv_tab_init(tab);
+  else hsv_tab_init_fwd(tab);
   if (FG)
     for (int a = threadIdx.x; a < 256; a += UT) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
   __syncthreads();
@@ -97,36 +98,37 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
       const uint4 v = ldg_stream16(alt_src + ((int64_t)n * h + y) * w + x0);
       aw[0] = v.x; aw[1] = v.y; aw[2] = v.z; aw[3] = v.w;
     } else {
-      // taps: source columns c0-1 .. c0+NS (replicated at the borders) of the two source rows
+      // taps: source columns c0-1 .. c0+NS (replicated at the borders) of the two source rows, NS bytes as one word (pair)
       const int ia = ph < SC / 2 ? max(r - 1, 0) : r, ib = ph < SC / 2 ? r : min(r + 1, th - 1);
-      int t[2][NS + 2];
+      unsigned wv[2][2], ev[2][2];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const uint8_t* row = s + (int64_t)(j ? ib : ia) * tw;
         if (SC == 2) {
           const uint2 v = __ldg(reinterpret_cast<const uint2*>(row + c0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            t[j][1 + k] = (int)((v.x >> (8 * k)) & 255u);
-            t[j][5 + k] = (int)((v.y >> (8 * k)) & 255u);
-          }
+          wv[j][0] = v.x; wv[j][1] = v.y;
         } else {
-          const unsigned v = __ldg(reinterpret_cast<const unsigned*>(row + c0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k) t[j][1 + k] = (int)((v >> (8 * k)) & 255u);
+          wv[j][0] = wv[j][1] = __ldg(reinterpret_cast<const unsigned*>(row + c0));
         }
-        t[j][0] = (int)__ldg(row + max(c0 - 1, 0));
-        t[j][NS + 1] = (int)__ldg(row + min(c0 + NS, tw - 1));
+        ev[j][0] = __ldg(row + max(c0 - 1, 0));
+        ev[j][1] = __ldg(row + min(c0 + NS, tw - 1));
       }
-      bool same = true;
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int k = 0; k < NS + 2; ++k) same = same && t[j][k] == t[0][0];
+      // one value everywhere (most of a matte): a handful of word compares, no unpacking
+      const unsigned u = ev[0][0], splat = u * 0x01010101u;
+      const bool same = (wv[0][0] == splat) & (wv[0][1] == splat) & (wv[1][0] == splat) & (wv[1][1] == splat) & (ev[0][1] == u) & (ev[1][0] == u) &
+                        (ev[1][1] == u);
       if (same) {
         // every tap has one value and the weights sum to 2048 on both axes: the two halves lose less than 2 of 4v + 2 together
-        aw[0] = aw[1] = aw[2] = aw[3] = (unsigned)t[0][0] * 0x01010101u;
+        aw[0] = aw[1] = aw[2] = aw[3] = splat;
       } else {
+        int t[2][NS + 2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          t[j][0] = (int)ev[j][0];
+          t[j][NS + 1] = (int)ev[j][1];
+#pragma unroll
+          for (int k = 0; k < NS; ++k) t[j][1 + k] = (int)((wv[j][k >> 2] >> (8 * (k & 3))) & 255u);
+        }
         const int b0 = wleft<SC>(ph), b1 = 2048 - b0;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -144,10 +146,12 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
   // ---- B bits of the trimap source: pixels (SC*r, SC*c) of rows with y % SC == 0 (warp-uniform: a warp is one row) ----
   if (ph == 0) {
     unsigned mb = 0;
+    if ((aw[0] | aw[1] | aw[2] | aw[3]) & 0x80808080u) {   // some pixel >= 128 (else all bits are zero)
 #pragma unroll
-    for (int c = 0; c < NS; ++c) {
-      const int k = SC * c;
-      mb |= ((aw[k >> 2] >> (8 * (k & 3) + 7)) & 1u) << c;
+      for (int c = 0; c < NS; ++c) {
+        const int k = SC * c;
+        mb |= ((aw[k >> 2] >> (8 * (k & 3) + 7)) & 1u) << c;
+      }
     }
     if (SC == 2) {
       if (act) mbits[((int64_t)n * th + r) * (tw >> 3) + tx] = (uint8_t)mb;

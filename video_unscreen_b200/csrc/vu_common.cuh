@@ -71,17 +71,24 @@ __device__ __forceinline__ void hsv_tab_init(HsvTab& t) {
     t.hfac[i] = (sec & 1) ? h : __fsub_rn(1.f, h);
   }
 }
+// the BGR2HSV half alone (kernels that never convert back)
+__device__ __forceinline__ void hsv_tab_init_fwd(HsvTab& t) {
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    t.sdiv[i] = i ? (2 * 1044480 + i) / (2 * i) : 0;
+    t.hdiv[i] = i ? (2 * 122880 + i) / (2 * i) : 0;
+  }
+}
 __device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const HsvTab& t, int& h, int& s, int& v) {
   v = max(b, max(g, r));
   const int mn = min(b, min(g, r));
   const int d = v - mn;
   s = (d * t.sdiv[v] + 2048) >> 12;
-  // hue numerator by priority r, g, b of the maximum: x - y + k*d, selected without a (divergent) branch
-  const bool vr = v == r, vg = v == g;
-  const int x = vr ? g : (vg ? b : r), y = vr ? b : (vg ? r : g), k = vr ? 0 : (vg ? 2 : 4);
-  int hh = x - y + k * d;
+  // hue numerator by priority r, g, b of the maximum: the three candidates cost subtractions and multiply-adds on the
+  // (idle) FMA pipe, the choice two selects on the (busy) ALU pipe - instead of five selects for x, y and k of x - y + k*d
+  const int nr = g - b, ng = (b - r) + 2 * d, nb = (r - g) + 4 * d;
+  int hh = v == r ? nr : (v == g ? ng : nb);
   hh = (hh * t.hdiv[d] + 2048) >> 12;  // arithmetic shift on a signed value
-  h = hh < 0 ? hh + 180 : hh;
+  h = hh - 180 * (hh >> 31);           // hh < 0 ? hh + 180 : hh
 }
 
 // uint8 <-> float32 without the conversion unit (16 lanes/clk/SM against 64 for an FADD): 2^23 + i has i in its

@@ -225,8 +225,10 @@ __global__ void __launch_bounds__(WARPS * 32) cross_march_kernel(const uint8_t* 
 
 // rows a warp owns: enough warps to fill the machine, little enough lead-in overhead
 inline int pick_band_rows(int h, int np) {
-  int rows = 64;
-  if (rows < 6 * np) rows = 6 * np;
+  // short bands: more warps in flight (a 540 x 960 matte in 64-row bands left the SMs at 16 % occupancy with a ragged
+  // last wave) and more of them flat (see the shortcut above), for 2 * np rows of lead-in per band
+  int rows = 32;
+  if (rows < 4 * np) rows = 4 * np;
   if (rows > h) rows = h;
   return rows;
 }

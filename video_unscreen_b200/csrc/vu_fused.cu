@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(FT) cf_lowres_kernel(const uint8_t* __restrict
 
 // S = 2, 16 full-resolution columns per thread (w % 16 == 0, 16-byte aligned rows): 128-bit loads, eight outputs,
 // all the loads of a thread in flight before the first conversion
-__global__ void __launch_bounds__(FT) cf_lowres2_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
+__global__ void __launch_bounds__(FT, 4) cf_lowres2_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
                                                              int tw, const uint8_t* __restrict__ lut3d, uint8_t* __restrict__ alpha_lo,
                                                              unsigned long long* __restrict__ stats2, unsigned long long* __restrict__ mcounts2) {
   __shared__ HsvTab tab;

@@ -64,14 +64,14 @@ __device__ __forceinline__ unsigned compress4(unsigned x) {
 template <int SC, bool PACKED>
 __global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ fuzzy,
                                                                  const uint8_t* __restrict__ flags, int h, int w, int th, int tw, int passes,
-                                                                 unsigned* __restrict__ planes, int nframes, int wpr) {
+                                                                 unsigned* __restrict__ planes, int nframes, int wpr, int oh) {
   __shared__ unsigned Db[2][TB_ROWS_MAX][TB_WORDS], Eb[2][TB_ROWS_MAX][TB_WORDS], In[TB_ROWS_MAX][TB_WORDS];
   __shared__ unsigned ZL[TB_ROWS_MAX][TB_WORDS], ZR[TB_ROWS_MAX][TB_WORDS], FL[TB_ROWS_MAX][TB_WORDS], FR[TB_ROWS_MAX][TB_WORDS];
   const int n = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int halo = passes + 1;
-  const int rows = TB_OH + 2 * halo;
-  const int X0 = blockIdx.x * TB_OW - TB_HX, Y0 = blockIdx.y * TB_OH - halo;   // staged origin
+  const int rows = oh + 2 * halo;   // oh <= TB_OH output rows per tile
+  const int X0 = blockIdx.x * TB_OW - TB_HX, Y0 = blockIdx.y * oh - halo;   // staged origin
   const bool ens = fuzzy && flags && flags[n] == 0;
   const uint8_t* mk = mask + (int64_t)n * h * w;
   const uint8_t* fz = fuzzy ? fuzzy + (int64_t)n * h * w : nullptr;
@@ -166,10 +166,10 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* 
   }
   __syncthreads();
   // ---- the eight quadrant planes of the tile's rows: {Z,F} x {left,right} x {row above, row below}, 3 words per row ----
-  for (int i = threadIdx.x; i < TB_OH * 3 * 8; i += TB_THREADS) {
-    const int pl = i / (TB_OH * 3), rem = i % (TB_OH * 3);
-    const int ty = rem / 3, jo = rem % 3;
-    const int y = blockIdx.y * TB_OH + ty;
+  for (int i = threadIdx.x; i < oh * 3 * 8; i += TB_THREADS) {
+    const int pl = i / (oh * 3), rem = i - pl * (oh * 3);
+    const int ty = rem / 3, jo = rem - 3 * ty;
+    const int y = blockIdx.y * oh + ty;
     const int xw = blockIdx.x * 3 + jo;      // word of the plane row
     if (y >= th || xw >= wpr) continue;
     const int r = ty + halo;
@@ -193,11 +193,17 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
   const int h = SC * th, w = SC * tw;
   const bool ens = fuzzy && flags && flags[n] == 0;
   const int tpr = w / (4 * NG);   // threads per row
-  const int64_t total = (int64_t)h * tpr;
   const int64_t psz = (int64_t)nframes * th * wpr;   // words per plane
   constexpr int CPG = 4 / SC;                        // working-resolution columns per group: 1 (4x) or 2 (2x)
-  for (int64_t i = (int64_t)blockIdx.x * TB_THREADS + threadIdx.x; i < total; i += (int64_t)gridDim.x * TB_THREADS) {
-    const int y = (int)(i / tpr), t = (int)(i - (int64_t)y * tpr);
+  // (y, t) of the thread's items without a division in the loop: the kernel is bound by instruction issue
+  const int i0 = blockIdx.x * TB_THREADS + threadIdx.x, step = gridDim.x * TB_THREADS;
+  const int dy = step / tpr, dt = step - dy * tpr;
+  int y = i0 / tpr, t = i0 - y * tpr;
+  for (; y < h; y += dy, t += dt) {
+    if (t >= tpr) {
+      t -= tpr;
+      if (++y >= h) break;
+    }
     const int r = y / SC, below = (y % SC) >= SC / 2;
     const unsigned* row = planes + ((int64_t)n * th + r) * wpr;
     const int c0 = t * NG * CPG;                     // first working-resolution column of the thread: NG * CPG <= 8 bits, one word
@@ -267,6 +273,13 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
   }
 }
 
+// output rows per tile: with 64 staged rows (x 4 words) every pass of the cross is exactly one cell per thread; tiles of
+// 64 output rows (76 staged rows for 5 passes) left 208 of the 256 threads idle in every second sweep
+inline int tile_rows(int passes) {
+  const int oh = 64 - 2 * (passes + 1);
+  return oh >= 32 ? oh : TB_OH;
+}
+
 }  // namespace
 }  // namespace vu
 
@@ -290,7 +303,8 @@ extern "C" int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const u
   if (n == 0) return VU_OK;
   const int wpr = (tw + 31) / 32;
   unsigned* planes = static_cast<unsigned*>(workspace);
-  dim3 ga((tw + TB_OW - 1) / TB_OW, (th + TB_OH - 1) / TB_OH, n);
+  const int oh = tile_rows(iters);
+  dim3 ga((tw + TB_OW - 1) / TB_OW, (th + oh - 1) / oh, n);
   const int ng = (w % 16 == 0) ? 4 : 1;
   const int64_t items = (int64_t)h * (w / (4 * ng));
   int64_t bx = (items + TB_THREADS - 1) / TB_THREADS;
@@ -299,7 +313,7 @@ extern "C" int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const u
   dim3 gb((unsigned)(bx < 1 ? 1 : bx), n);
 #define VU_UP(SCV)                                                                                                                   \
   do {                                                                                                                               \
-    trimap_bits_kernel<SCV, false><<<ga, TB_THREADS, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, iters, planes, n, wpr);       \
+    trimap_bits_kernel<SCV, false><<<ga, TB_THREADS, 0, S(stream)>>>(mask, fuzzy, flags, h, w, th, tw, iters, planes, n, wpr, oh);      \
     if (ng == 4) trimap_up_bits_kernel<SCV, 4, false><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);   \
     else trimap_up_bits_kernel<SCV, 1, false><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy, flags, out);           \
   } while (0)
@@ -325,17 +339,18 @@ extern "C" int vu_trimap_bits_packed(const uint8_t* mask_bits, const uint8_t* fu
   if (n == 0) return VU_OK;
   const int wpr = (tw + 31) / 32;
   unsigned* planes = static_cast<unsigned*>(workspace);
-  dim3 ga((tw + TB_OW - 1) / TB_OW, (th + TB_OH - 1) / TB_OH, n);
+  const int oh = tile_rows(iters);
+  dim3 ga((tw + TB_OW - 1) / TB_OW, (th + oh - 1) / oh, n);
   const int64_t items = (int64_t)h * (w / 16);
   int64_t bx = (items + TB_THREADS - 1) / TB_THREADS;
   const int64_t cap = ((int64_t)device_sms() * 8 + n - 1) / n;
   if (bx > cap) bx = cap;
   dim3 gb((unsigned)(bx < 1 ? 1 : bx), n);
   if (sc == 2) {
-    trimap_bits_kernel<2, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr);
+    trimap_bits_kernel<2, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr, oh);
     trimap_up_bits_kernel<2, 4, true><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy_bits, flags, out);
   } else {
-    trimap_bits_kernel<4, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr);
+    trimap_bits_kernel<4, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr, oh);
     trimap_up_bits_kernel<4, 4, true><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy_bits, flags, out);
   }
   note_launch();
