@@ -318,6 +318,22 @@ int vu_masked_temporal_mean(const uint8_t* frames, const uint8_t* masks, int n, 
 int vu_masked_temporal_mean_dilate32(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int min_count,
                                      uint8_t* bg_out, uint8_t* mask_always_out, vu_stream_t stream);
 
+/* ---- BackgroundAgent (unscreen/bgmodel/agent.py), methods 'mean' and 'pcov' ---- */
+/* get_fgbox (utils/maskprocess.py:37-53): out4 = {min row, max row, min column, max column} of mask > 0
+ * ({INT_MAX, -1, INT_MAX, -1} for an empty mask) */
+int vu_mask_bbox(const uint8_t* mask, int h, int w, int32_t* out4, vu_stream_t stream);
+/* get_mean_bg (bgmodel/agent.py:80-88): out4 = {sum ch0, sum ch1, sum ch2, count} of img [npix][3] over mask > 0
+ * (mask NULL: all pixels) */
+int vu_masked_sum3(const uint8_t* img, const uint8_t* mask, int64_t npix, uint64_t* out4, vu_stream_t stream);
+/* one round of get_bg_by_pcov (bgmodel/agent.py:118-129) on the rh x rw box around the hole: normalised ksize x ksize
+ * cv2.boxFilter (BORDER_REFLECT_101) of the image and of the validity map, mean / validity where the window saw a
+ * valid pixel.  first != 0: img_in / valid_in are the image and the DILATED MASK at the box's origin (row pitch
+ * in_pitch_px pixels; mask > 0 = hole: zero, invalid); later rounds read the dense rh x rw outputs of the round before
+ * (in_pitch_px = rw).  flags [101] uint32, zeroed by the caller before round 0: round r sets flags[r + 1] when it
+ * leaves an invalid pixel and returns at once when flags[r] == 0 (r > 0), so rounds can be enqueued ahead. */
+int vu_pcov_round(const uint8_t* img_in, const uint8_t* valid_in, int in_pitch_px, int first, int rh, int rw, int ksize,
+                  uint8_t* img_out, uint8_t* valid_out, uint32_t* flags, int round, vu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -229,6 +229,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "temporal.npz"), **tmp)
 
     geometry(U)
+    bgmodel(BA)
     write_manifest()
 
 
@@ -267,6 +268,35 @@ def geometry(U):
     np.savez_compressed(os.path.join(HERE, "geometry.npz"), **geo)
 
 
+def bgmodel_case(h, w, seed, kind):
+    """image + person-like mask for the BackgroundAgent fixtures: blurred random image; kind 1 adds isolated mask pixels,
+    kind 2 a block touching the image corner (the hole's box is clipped by the image)"""
+    import cv2
+    rng = np.random.default_rng(seed)
+    img = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3), dtype=np.uint8), (0, 0), 3)
+    yy, xx = np.mgrid[0:h, 0:w]
+    m = ((((xx - w * 0.5) / (w * 0.2)) ** 2 + ((yy - h * 0.55) / (h * 0.3)) ** 2) <= 1).astype(np.uint8) * 255
+    if kind == 1:
+        m[rng.random((h, w)) < 0.002] = 255
+    if kind == 2:
+        m[:h // 3, :w // 4] = 255
+    return img, m
+
+
+def bgmodel(BA):
+    """BackgroundAgent.forward, methods 'mean' and 'pcov' (SURVEY.md 8f rank 4).  `python make_golden.py bgmodel`."""
+    out = {}
+    cases = [(108, 192, 96, 0), (108, 192, 96, 1), (135, 240, 270, 2), (150, 100, 75, 0), (96, 160, 160, 1)]
+    out["cases"] = np.array(cases)
+    for i, (h, w, L, kind) in enumerate(cases):
+        img, m = bgmodel_case(h, w, 100 + i, kind)
+        out[f"img_{i}"], out[f"mask_{i}"] = img, m
+        ag = BA(input_long_side=L)
+        for method in ("mean", "pcov"):
+            out[f"{method}_{i}"] = ag.forward(img.copy(), m.copy(), method)
+    np.savez_compressed(os.path.join(HERE, "bgmodel.npz"), **out)
+
+
 def write_manifest():
     import cv2
     import sklearn
@@ -287,6 +317,9 @@ def write_manifest():
 if __name__ == "__main__":
     if sys.argv[1:] == ["geometry"]:
         geometry(load_reference()[0])
+        write_manifest()
+    elif sys.argv[1:] == ["bgmodel"]:
+        bgmodel(load_reference()[3])
         write_manifest()
     else:
         main()

@@ -661,3 +661,33 @@ def test_color_correct_full_size(vu, h, w):
     got = host(vu.ops.color_correct(dev(frames), dev(alpha), col, th, tw))
     assert np.array_equal(got[1], R.color_correct(frames[1], alpha[1], col))
     assert bool((got <= alpha).all())
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_background_agent_golden(vu, golden, i):
+    """BackgroundAgent.forward 'pcov' and 'mean' on the device: bit-exact against the oracle; against the
+    reference's goldens 'pcov' bit-exact, 'mean' within the HSV2BGR tolerance (<= 2 LSB after the final resize)."""
+    from video_unscreen_b200.unscreen.bgmodel import BackgroundAgent
+    g = golden("bgmodel")
+    h, w, L, kind = (int(v) for v in g["cases"][i])
+    img, m = g[f"img_{i}"], g[f"mask_{i}"]
+    ag = BackgroundAgent(input_long_side=L)
+    got = ag.forward(img, m, "pcov")
+    assert np.array_equal(got, R.background_forward(img, m, "pcov", input_long_side=L))
+    assert np.array_equal(got, g[f"pcov_{i}"])
+    got = ag.forward(img, m, "mean")
+    assert np.array_equal(got, R.background_forward(img, m, "mean", input_long_side=L))
+    assert maxdiff(got, g[f"mean_{i}"]) <= 2
+    # early-outs, error behaviour, device tensors in -> device tensors out
+    assert ag.forward(img, np.zeros_like(m), "pcov") is img
+    z = ag.forward(img, np.full_like(m, 255), "mean")
+    assert z.dtype == np.float64 and z.shape == img.shape and not z.any()
+    with pytest.raises(NameError):
+        ag.forward(img, m, "telea")
+    with pytest.raises(NotImplementedError):
+        ag.forward(img, m, "rf")
+    t = ag.forward(dev(img), dev(m), "pcov")
+    assert t.is_cuda and np.array_equal(host(t), g[f"pcov_{i}"])
+    ag3 = BackgroundAgent(input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3)
+    assert np.array_equal(ag3.forward(img, m, "pcov"),
+                          R.background_forward(img, m, "pcov", input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3))

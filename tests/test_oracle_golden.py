@@ -145,3 +145,23 @@ def test_color_correct(golden):
             for i in range(2):
                 got = R.color_correct(g["cc_frames"][i], g["cc_alpha"][i], col, target_long_side=int(L))
                 assert np.array_equal(got, g[f"cc_{ci}_{int(L)}_{i}"]), (ci, int(L), i)
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_background_agent_mean_pcov(golden, i):
+    """BackgroundAgent.forward (bgmodel/agent.py:159-208): 'pcov' bit-exact; 'mean' ends in cv2's HSV2BGR of a constant
+    image, whose scalar tail (the last columns of every row) rounds where the SIMD body truncates: <= 1 LSB
+    there before, <= 2 LSB after the final resize."""
+    g = golden("bgmodel")
+    h, w, L, kind = (int(v) for v in g["cases"][i])
+    img, m = g[f"img_{i}"], g[f"mask_{i}"]
+    assert np.array_equal(R.background_forward(img, m, "pcov", input_long_side=L), g[f"pcov_{i}"])
+    got = R.background_forward(img, m, "mean", input_long_side=L)
+    d = np.abs(got.astype(int) - g[f"mean_{i}"].astype(int))
+    assert d.max() <= 2      # where: the hole pixels of the scalar-tail columns (image width mod the SIMD width)
+    # the early-outs
+    assert R.background_forward(img, np.zeros_like(m), "mean") is img
+    z = R.background_forward(img, np.full_like(m, 255), "pcov")
+    assert z.dtype == np.float64 and z.shape == img.shape and not z.any()
+    with pytest.raises(NameError):
+        R.background_forward(img, m, "telea")

@@ -131,3 +131,19 @@ def test_color_correct(ref, h, w, L):
             want = ref.U.color_correct(frames[i].copy(), alpha.copy(), c.copy(), target_long_side=L)
             got = R.color_correct(frames[i], alpha, c, target_long_side=L)
             assert np.array_equal(got, want), (i, col, int((got != want).sum()))
+
+
+@pytest.mark.parametrize("h,w,L,kind", [(120, 200, 100, 0), (216, 384, 192, 1), (270, 480, 540, 2), (200, 130, 90, 1)])
+def test_background_agent(h, w, L, kind):
+    """BackgroundAgent.forward 'pcov' (bit-exact) and 'mean' (<= 2 LSB: cv2's HSV2BGR tail) against the live reference"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import bgmodel_case, load_reference
+    BA = load_reference(REF_ROOT)[3]
+    img, m = bgmodel_case(h, w, h * 7 + kind, kind)
+    ag = BA(input_long_side=L)
+    assert np.array_equal(R.background_forward(img, m, "pcov", input_long_side=L), ag.forward(img.copy(), m.copy(), "pcov"))
+    d = np.abs(R.background_forward(img, m, "mean", input_long_side=L).astype(int) - ag.forward(img.copy(), m.copy(), "mean").astype(int))
+    assert d.max() <= 2      # where: the hole pixels of the scalar-tail columns (image width mod the SIMD width)
+    ag2 = BA(input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3)
+    want = ag2.forward(img.copy(), m.copy(), "pcov")
+    assert np.array_equal(R.background_forward(img, m, "pcov", input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3), want)

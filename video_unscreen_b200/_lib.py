@@ -75,6 +75,9 @@ SIGNATURES = {
     "vu_cf_alpha_lut3d_u8": (_i, [_p, _i64, _p, _p, _p]),
     "vu_cf_threshold_stats": (_i, [_p, _p, _i, _i64, _p, _p]),
     "vu_cf_threshold_apply": (_i, [_p, _i, _i64, _p, _d, _p, _p]),
+    "vu_mask_bbox": (_i, [_p, _i, _i, _p, _p]),
+    "vu_masked_sum3": (_i, [_p, _p, _i64, _p, _p]),
+    "vu_pcov_round": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "vu_get_fg": (_i, [_p, _p, _p, _i64, _i64, _i, _p, _p, _p]),
     "vu_get_bg": (_i, [_p, _p, _i64, _p, _p]),
     "vu_blend": (_i, [_i, _p, _p, _i, _p, _i64, _i64, _p, _p]),

@@ -14,7 +14,7 @@
 // replaces resize_up + fuzzy_count (+ get_fg) and the strided full-resolution reads of the trimap kernel: per frame
 // the chunk moves about 7P bytes instead of 14P (P = pixels), see DESIGN.md section 4.
 //
-// A thread owns 16 destination columns of ONE row (a warp: 512 columns of it), so that every load of the kernel is
+// A thread owns 16 destination columns of ONE row (a warp: 128 columns x 4 rows), so that every load of the kernel is
 // independent of every other thread's (a first version walked 16 rows per thread to reuse the horizontal pass and
 // spent its time waiting: one DRAM round trip per row, 830 GB/s); where every tap of both source rows has one value
 // the interpolation is that value (most of a matte is 0 or 255).  Arithmetic = cv2's fixed-point bilinear, as in
@@ -25,7 +25,7 @@ namespace vu {
 namespace {
 
 constexpr int UT = 256;
-constexpr int UP_ROWS = 8;   // destination rows per warp of alpha_up_fuzzy_kernel
+constexpr int UP_ROWS = 4;   // destination rows per warp of alpha_up_fuzzy_kernel
 
 __device__ __forceinline__ int trunc_clamp255_(float x) { return f32_trunc_nonneg(fminf(fmaxf(x, 0.f), 255.f)); }
 
@@ -69,8 +69,10 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
   constexpr int NS = 16 / SC;   // source columns under the 16 destination columns
   const int n = blockIdx.z;
   const int h = SC * th, w = SC * tw;
+  // a warp = 8 column groups x 4 rows (128 x 4 pixels), not 512 pixels of one row: the matte-dependent branches below
+  // diverge per warp, and a compact footprint leaves far fewer warps straddling the matte's outline
   const int lane = threadIdx.x & 31;
-  const int tx = blockIdx.x * 32 + lane;
+  const int tx = blockIdx.x * 8 + (lane & 7);
   const int x0 = 16 * tx;
   const bool alt = alt_flags && alt_flags[n] != 0;
   const uint8_t* s = alpha_lo + (int64_t)n * th * tw;
@@ -82,9 +84,9 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
   // above is paid once per UP_ROWS * 8 rows); the rows of a thread do not depend on each other
 #pragma unroll 1
   for (int it = 0; it < UP_ROWS; ++it) {
-  const int y = (blockIdx.y * UP_ROWS + it) * (UT / 32) + (threadIdx.x >> 5);
-  if (y >= h) break;   // warp-uniform
-  const bool act = x0 < w;
+  const int y = ((blockIdx.y * UP_ROWS + it) * (UT / 32) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  if (y - (lane >> 3) >= h) break;   // warp-uniform
+  const bool act = x0 < w && y < h;
   const int r = y / SC, ph = y % SC;
   unsigned aw[4] = {0u, 0u, 0u, 0u};
   const int64_t fo = (((int64_t)n * h + y) * w + x0) * 3;
@@ -143,8 +145,8 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
     }
     stg_stream16(alpha + ((int64_t)n * h + y) * w + x0, make_uint4(aw[0], aw[1], aw[2], aw[3]));
   }
-  // ---- B bits of the trimap source: pixels (SC*r, SC*c) of rows with y % SC == 0 (warp-uniform: a warp is one row) ----
-  if (ph == 0) {
+  // ---- B bits of the trimap source: pixels (SC*r, SC*c) of rows with y % SC == 0 (the shuffle runs on every lane) ----
+  {
     unsigned mb = 0;
     if ((aw[0] | aw[1] | aw[2] | aw[3]) & 0x80808080u) {   // some pixel >= 128 (else all bits are zero)
 #pragma unroll
@@ -154,10 +156,10 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
       }
     }
     if (SC == 2) {
-      if (act) mbits[((int64_t)n * th + r) * (tw >> 3) + tx] = (uint8_t)mb;
+      if (act && ph == 0) mbits[((int64_t)n * th + r) * (tw >> 3) + tx] = (uint8_t)mb;
     } else {
-      const unsigned hi = __shfl_down_sync(0xffffffffu, mb, 1);
-      if (act && !(lane & 1)) mbits[((int64_t)n * th + r) * (tw >> 3) + (tx >> 1)] = (uint8_t)(mb | (hi << 4));
+      const unsigned hi = __shfl_down_sync(0xffffffffu, mb, 1);   // the neighbour in x: lanes 2j, 2j + 1 share a row
+      if (act && ph == 0 && !(lane & 1)) mbits[((int64_t)n * th + r) * (tw >> 3) + (tx >> 1)] = (uint8_t)(mb | (hi << 4));
     }
   }
   // ---- fuzzy bits (+ fg / patched bg) ----
@@ -194,9 +196,13 @@ __global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __res
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int a = (int)((aw[g] >> (8 * i)) & 255u);
-          int ih, is, iv;
-          bgr2hsv_px(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, ih, is, iv);
-          const bool in = (ih >= lo0) & (ih <= hi0) & (is >= lo1) & (is <= hi1) & (iv >= lo2) & (iv <= hi2);
+          int ih = 0, is, iv, id;
+          bgr2hsv_sv(c[3 * i], c[3 * i + 1], c[3 * i + 2], tab, is, iv, id);
+          bool in = (is >= lo1) & (is <= hi1) & (iv >= lo2) & (iv <= hi2);
+          if (FG || in) {   // the hue is the expensive third: a pixel whose saturation or value is out of range needs none
+            ih = bgr2hsv_hue(c[3 * i], c[3 * i + 1], c[3 * i + 2], iv, id, tab);
+            in = in & (ih >= lo0) & (ih <= hi0);
+          }
           const bool pos = a != 0;
           cnt_p += pos;
           fz |= (unsigned)(pos && in) << (4 * g + i);
@@ -254,7 +260,7 @@ extern "C" int vu_cf_alpha_up_fuzzy(const uint8_t* alpha_lo, int n, int th, int 
   if (n == 0) return VU_OK;
   int e = record_cuda(cudaMemsetAsync(counts2, 0, sizeof(uint64_t) * 2 * n, S(stream)));
   if (e) return e;
-  dim3 g((w / 16 + 31) / 32, (h + UP_ROWS * (UT / 32) - 1) / (UP_ROWS * (UT / 32)), n);
+  dim3 g((w / 16 + 7) / 8, (h + UP_ROWS * (UT / 32) * 4 - 1) / (UP_ROWS * (UT / 32) * 4), n);
   auto* c2 = reinterpret_cast<unsigned long long*>(counts2);
   const int B = bg_bgr ? bg_bgr[0] : 0, G = bg_bgr ? bg_bgr[1] : 0, R = bg_bgr ? bg_bgr[2] : 0;
 #define VU_CALL(SCV, FGV)                                                                                                                       \

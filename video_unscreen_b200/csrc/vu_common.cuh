@@ -78,17 +78,24 @@ __device__ __forceinline__ void hsv_tab_init_fwd(HsvTab& t) {
     t.hdiv[i] = i ? (2 * 122880 + i) / (2 * i) : 0;
   }
 }
-__device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const HsvTab& t, int& h, int& s, int& v) {
+// value, saturation (and the chroma d the hue needs) of one pixel
+__device__ __forceinline__ void bgr2hsv_sv(int b, int g, int r, const HsvTab& t, int& s, int& v, int& d) {
   v = max(b, max(g, r));
-  const int mn = min(b, min(g, r));
-  const int d = v - mn;
+  d = v - min(b, min(g, r));
   s = (d * t.sdiv[v] + 2048) >> 12;
-  // hue numerator by priority r, g, b of the maximum: the three candidates cost subtractions and multiply-adds on the
-  // (idle) FMA pipe, the choice two selects on the (busy) ALU pipe - instead of five selects for x, y and k of x - y + k*d
+}
+// its hue.  The numerator by priority r, g, b of the maximum: the three candidates cost subtractions and multiply-adds
+// on the (idle) FMA pipe, the choice two selects on the (busy) ALU pipe - instead of five selects for x, y and k of x - y + k*d
+__device__ __forceinline__ int bgr2hsv_hue(int b, int g, int r, int v, int d, const HsvTab& t) {
   const int nr = g - b, ng = (b - r) + 2 * d, nb = (r - g) + 4 * d;
   int hh = v == r ? nr : (v == g ? ng : nb);
   hh = (hh * t.hdiv[d] + 2048) >> 12;  // arithmetic shift on a signed value
-  h = hh - 180 * (hh >> 31);           // hh < 0 ? hh + 180 : hh
+  return hh - 180 * (hh >> 31);        // hh < 0 ? hh + 180 : hh
+}
+__device__ __forceinline__ void bgr2hsv_px(int b, int g, int r, const HsvTab& t, int& h, int& s, int& v) {
+  int d;
+  bgr2hsv_sv(b, g, r, t, s, v, d);
+  h = bgr2hsv_hue(b, g, r, v, d, t);
 }
 
 // uint8 <-> float32 without the conversion unit (16 lanes/clk/SM against 64 for an FADD): 2^23 + i has i in its

@@ -195,15 +195,15 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
   const int tpr = w / (4 * NG);   // threads per row
   const int64_t psz = (int64_t)nframes * th * wpr;   // words per plane
   constexpr int CPG = 4 / SC;                        // working-resolution columns per group: 1 (4x) or 2 (2x)
-  // (y, t) of the thread's items without a division in the loop: the kernel is bound by instruction issue
-  const int i0 = blockIdx.x * TB_THREADS + threadIdx.x, step = gridDim.x * TB_THREADS;
-  const int dy = step / tpr, dt = step - dy * tpr;
-  int y = i0 / tpr, t = i0 - y * tpr;
-  for (; y < h; y += dy, t += dt) {
-    if (t >= tpr) {
-      t -= tpr;
-      if (++y >= h) break;
-    }
+  // a warp = 8 thread-groups x 4 rows (a compact footprint: the flat test below diverges per warp, and a warp that
+  // covers 4 * NG * 8 columns of 4 rows straddles the unknown band far less often than one that covers 32 groups of one
+  // row); warp tiles in a grid-stride loop, one 32-bit division per tile
+  const int lane = threadIdx.x & 31;
+  const int tiles_x = (tpr + 7) >> 3, tiles = tiles_x * ((h + 3) >> 2);
+  for (int tile = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * (TB_THREADS / 32)) {
+    const int tyy = tile / tiles_x, txx = tile - tyy * tiles_x;
+    const int y = tyy * 4 + (lane >> 3), t = txx * 8 + (lane & 7);
+    if (y >= h || t >= tpr) continue;
     const int r = y / SC, below = (y % SC) >= SC / 2;
     const unsigned* row = planes + ((int64_t)n * th + r) * wpr;
     const int c0 = t * NG * CPG;                     // first working-resolution column of the thread: NG * CPG <= 8 bits, one word

@@ -665,3 +665,56 @@ def set128_unflagged(a, b, flags):
     out = torch.empty_like(a)
     check(lib().vu_set128_unflagged(_p(a), _p(b), _p(flags), n, a.numel() // n, _p(out), _stream()))
     return out
+
+
+# ---- BackgroundAgent pieces (bgmodel/agent.py 'mean' / 'pcov') ------------------------------------
+
+def mask_bbox(mask):
+    """(min row, max row, min col, max col) of mask > 0 as python ints, or None for an empty mask (one host read-back)"""
+    mask = _mask(mask)
+    h, w = mask.shape
+    out = torch.empty(4, dtype=torch.int32, device=mask.device)
+    check(lib().vu_mask_bbox(_p(mask), h, w, _p(out), _stream()))
+    r0, r1, c0, c1 = (int(v) for v in out.cpu())
+    return None if r1 < 0 else (r0, r1, c0, c1)
+
+
+def masked_sum3(img, mask=None):
+    """-> (sums [3] python ints, count) of img [H,W,3] over mask > 0 (all pixels without a mask); one host read-back"""
+    img = _img(img)
+    out = torch.empty(4, dtype=torch.int64, device=img.device)
+    check(lib().vu_masked_sum3(_p(img), _p(_mask(mask)) if mask is not None else None, img.numel() // 3, _p(out), _stream()))
+    v = [int(x) for x in out.cpu()]
+    return v[:3], v[3]
+
+
+def pcov_fill(img, hole_mask, box, ksize=5, max_rounds=100, batch=8):
+    """get_bg_by_pcov's loop (bgmodel/agent.py:118-129) on box = (x0, x1, y0, y1) (rows, columns) of img [H,W,3] with the
+    hole = hole_mask > 0.  Returns the filled box [x1-x0, y1-y0, 3].  Rounds are enqueued ``batch`` at a time; finished
+    rounds return at once on the device."""
+    img, hole_mask = _img(img), _mask(hole_mask)
+    h, w = hole_mask.shape
+    x0, x1, y0, y1 = box
+    rh, rw = x1 - x0, y1 - y0
+    dev = img.device
+    bufs = [torch.empty((rh, rw, 3), dtype=u8, device=dev) for _ in range(2)]
+    valid = [torch.empty((rh, rw), dtype=u8, device=dev) for _ in range(2)]
+    flags = torch.zeros(max_rounds + 1, dtype=torch.int32, device=dev)
+    off = x0 * w + y0
+    done_after = max_rounds
+    r = 0
+    while r < max_rounds:
+        for _ in range(min(batch, max_rounds - r)):
+            if r == 0:
+                src_i, src_v, pitch = ctypes.c_void_p(img.data_ptr() + 3 * off), ctypes.c_void_p(hole_mask.data_ptr() + off), w
+            else:
+                src_i, src_v, pitch = _p(bufs[r % 2]), _p(valid[r % 2]), rw
+            check(lib().vu_pcov_round(src_i, src_v, pitch, int(r == 0), rh, rw, int(ksize), _p(bufs[(r + 1) % 2]), _p(valid[(r + 1) % 2]),
+                                      _p(flags), r, _stream()))
+            r += 1
+        f = flags[1:r + 1].cpu().numpy()
+        zero = np.flatnonzero(f == 0)
+        if len(zero):                       # flags[k + 1] == 0: round k left no invalid pixel -> k + 1 rounds ran
+            done_after = int(zero[0]) + 1
+            break
+    return bufs[done_after % 2]

@@ -1,11 +1,13 @@
-"""BackgroundAgent: signature kept, body out of scope.
+"""BackgroundAgent (reference: unscreen/bgmodel/agent.py:9-208): single-image background inpainting under a
+foreground mask.  SURVEY.md section 8 keeps its signature (row a25) and ranks its bodies as "next" row f-4: the 'mean'
+and 'pcov' methods run on the device here; 'rf' (region fill: a sparse Laplace solve with scipy, bgmodel/region_fill.py)
+is not a streaming per-pixel kernel and stays with the reference (``install()`` keeps the reference's own method)."""
+import numpy as np
+import torch
 
-The reference's agent (unscreen/bgmodel/agent.py:9-208) is single-image
-spatial inpainting (boundary mean colour / iterated box filters / a sparse
-Laplace solve with scipy).  It has no caller in tools/, is not a streaming
-per-pixel kernel, and SURVEY.md section 8 (row a25) keeps only its signature
-importable.  The temporal background estimators of the bg_step path live in
-``unscreen.utils.temporal`` (temporal_median, masked_temporal_mean)."""
+from ... import _lib, ops
+from ..._io import back, to_dev
+from ..utils.imgprocess import get_target_size
 
 
 class BackgroundAgent():
@@ -19,9 +21,65 @@ class BackgroundAgent():
         self.boundary_iters = boundary_iters
         self.pcov_ksize = pcov_ksize
 
+    # ---- device-side bodies (CUDA tensors in, CUDA tensors out) ----
+
+    def _mean_color_hsv(self, img_hsv, mask):
+        """get_mean_bg (reference :66-93): the mean HSV colour over the outer boundary of the mask, truncated to uint8
+        (over the whole image when the boundary is empty)"""
+        boundary = ops.sub_wrap(ops.dilate(mask, self.boundary_ksize, self.boundary_iters), mask)
+        sums, n = ops.masked_sum3(img_hsv, boundary)
+        if n == 0:
+            sums, n = ops.masked_sum3(img_hsv, None)
+        return (np.array(sums, dtype=np.float64) / n).astype(np.uint8)
+
+    def get_mean_bg(self, img_hsv, mask):
+        t, as_np = to_dev(img_hsv)
+        m, _ = to_dev(mask)
+        col = self._mean_color_hsv(t, m)
+        out = torch.from_numpy(np.broadcast_to(col, tuple(t.shape)).copy()).to(t.device)
+        return back(out, as_np)
+
+    def _pcov_dev(self, img, mask):
+        """get_bg_by_pcov (reference :95-131) on device tensors"""
+        box = ops.mask_bbox(mask)
+        h, w = mask.shape
+        p = self.pcov_ksize
+        x0, x1, y0, y1 = max(box[0] - p, 0), min(box[1] + p, h), max(box[2] - p, 0), min(box[3] + p, w)   # get_fgbox(mask, padsize=p)
+        roi = ops.pcov_fill(img, mask, (x0, x1, y0, y1), p)
+        out = img.clone()            # outside the box there is no hole pixel: the zeroed image is the image there
+        out[x0:x1, y0:y1] = roi
+        return out
+
+    def get_bg_by_pcov(self, img, mask):
+        t, as_np = to_dev(img)
+        m, _ = to_dev(mask)
+        return back(self._pcov_dev(t, m), as_np)
+
     def forward(self, img, mask, method='rf'):
+        """reference :159-208.  'mean': boundary mean colour; 'pcov': iterated partial convolutions; 'rf': not here."""
         if method not in ('mean', 'pcov', 'rf'):
             raise NameError(f'No such method for background inpainting: {method}')
-        raise NotImplementedError(
-            "BackgroundAgent.forward (single-image inpainting, reference bgmodel/agent.py:159-208) is outside the "
-            "B200 hot path (SURVEY.md section 8 a25); use the reference's own implementation for it")
+        if method == 'rf':
+            raise NotImplementedError(
+                "BackgroundAgent.forward(method='rf') (region fill: scipy sparse solve, reference bgmodel/region_fill.py) "
+                "is outside the B200 hot path; use the reference's implementation (video_unscreen_b200.install() keeps it)")
+        t, as_np = to_dev(img)
+        m, _ = to_dev(mask)
+        ori_h, ori_w = m.shape
+        n_pos = int(ops.count_cmp(m, _lib.CMP_NE, 0).item())
+        if n_pos == ori_h * ori_w:        # no background (:177-178): float64 zeros, as the reference returns them
+            return np.zeros(tuple(t.shape)) if as_np else torch.zeros(tuple(t.shape), dtype=torch.float64, device=t.device)
+        if n_pos == 0:                    # no foreground (:180-181)
+            return img
+        ih, iw = get_target_size(ori_h, ori_w, self.input_long_side)
+        img_lo = ops.resize_linear_image(t, ih, iw)
+        mask_lo = ops.resize_linear_mask(m, ih, iw)
+        dil = ops.dilate(mask_lo, self.dilation_ksize, self.dilation_iters)
+        if method == 'mean':
+            col_hsv = self._mean_color_hsv(ops.bgr2hsv(img_lo), dil)
+            col_bgr = ops.hsv2bgr(torch.from_numpy(np.tile(col_hsv, (1, 4, 1))).to(t.device))[0, 0].cpu().numpy()
+            bgimg = torch.from_numpy(np.broadcast_to(col_bgr, (ih, iw, 3)).copy()).to(t.device)
+        else:
+            bgimg = self._pcov_dev(img_lo, dil)
+        bgimg = ops.blend(_lib.BLEND_FUSE, bgimg, dil, img_lo)       # fuse_fgbg(bgimg, img, dilated_mask), :194 / :197
+        return back(ops.resize_linear_image(bgimg, ori_h, ori_w), as_np)
