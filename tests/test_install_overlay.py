@@ -78,7 +78,9 @@ for f in (parallel_read_img, save_img, save_video, remove_invalid_objects, regio
           return_date):
     assert f.__module__.startswith("unscreen."), (f, f.__module__)
 assert VMattingAgent.__module__ == "unscreen.vmatting.agent" and STMAgent.__module__.startswith("unscreen.stm")
-assert BackgroundAgent.__module__ == "unscreen.bgmodel.agent"
+import unscreen.bgmodel.agent as ref_bg
+assert issubclass(BackgroundAgent, ref_bg.BackgroundAgent.__mro__[1]) and BackgroundAgent._vu_b200_hybrid   # 'rf' stays the reference's
+assert BackgroundAgent(input_long_side=100).pcov_ksize == 5
 assert "unscreen.utils.fgfuncs.get_fg" in vu.installed_names()
 print("overlay ok", len(vu.installed_names()))
 """)

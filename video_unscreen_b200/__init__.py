@@ -43,8 +43,9 @@ def install(name="unscreen", overlay=None):
     * The reference package is importable (its checkout is on ``sys.path``) -> OVERLAY: the reference is imported as it
       is and the hot-path names of this mirror are patched over the reference's in ``unscreen.utils`` (and the
       sub-modules that define them, so the reference's internal callers pick them up too), ``unscreen.colorfiltering``
-      and ``unscreen.trimap``.  Everything else -- file I/O, region fill, ``unscreen.bgmodel``'s single-image
-      inpainting, the CNN agents -- stays the reference's, so ``tools/unscreen/green.py``, ``bg.py``, ``bg_offline.py`` and ``tools/replace/replace.py``
+      and ``unscreen.trimap``; ``unscreen.bgmodel.BackgroundAgent`` becomes a subclass of the reference's whose
+      'mean' and 'pcov' methods run on the device.  Everything else -- file I/O, region fill ('rf'), the CNN
+      agents -- stays the reference's, so ``tools/unscreen/green.py``, ``bg.py``, ``bg_offline.py`` and ``tools/replace/replace.py``
       import and run unchanged.
     * No reference package around -> ALIAS: ``sys.modules['unscreen'...]`` point at the mirror (hot-path names only).
 
@@ -75,6 +76,27 @@ def install(name="unscreen", overlay=None):
             setattr(target, n, obj)
             setattr(parent, n, obj)
             patched.append(f"{name}.{ref_sub}.{n}")
+    # unscreen.bgmodel: 'mean' and 'pcov' run on the device, 'rf' (scipy region fill) stays the reference's
+    ref_bg = importlib.import_module(f"{name}.bgmodel.agent")
+    mine_bg = importlib.import_module(f"{base}.bgmodel.agent").BackgroundAgent
+    if not getattr(ref_bg.BackgroundAgent, "_vu_b200_hybrid", False):
+        ref_cls = ref_bg.BackgroundAgent
+
+        class BackgroundAgent(ref_cls):
+            __doc__ = ref_cls.__doc__
+            _vu_b200_hybrid = True
+
+            def forward(self, img, mask, method='rf'):
+                if method in ('mean', 'pcov'):
+                    return mine_bg.forward(self, img, mask, method)
+                return ref_cls.forward(self, img, mask, method)
+
+            _mean_color_hsv = mine_bg._mean_color_hsv
+            _pcov_dev = mine_bg._pcov_dev
+        BackgroundAgent.__module__ = mine_bg.__module__
+        ref_bg.BackgroundAgent = BackgroundAgent
+        importlib.import_module(f"{name}.bgmodel").BackgroundAgent = BackgroundAgent
+        patched.append(f"{name}.bgmodel.agent.BackgroundAgent[mean,pcov]")
     _PATCHED[name] = patched
     return ref
 
