@@ -334,6 +334,20 @@ int vu_masked_sum3(const uint8_t* img, const uint8_t* mask, int64_t npix, uint64
 int vu_pcov_round(const uint8_t* img_in, const uint8_t* valid_in, int in_pitch_px, int first, int rh, int rw, int ksize,
                   uint8_t* img_out, uint8_t* valid_out, uint32_t* flags, int round, vu_stream_t stream);
 
+/* ---- remove_invalid_objects (unscreen/utils/maskprocess.py:77-152; green.py:106-109, bg.py:67,93, bg_offline.py:76,165) ----
+ * out = alpha with every pixel cleared that no valid contour paints: the contours of cv2.findContours(alpha, RETR_LIST)
+ * (outer borders of the 8-connected components of alpha > 0 and the borders of their holes) with contourArea >= 100 whose
+ * filled polygon scores saliency = sum(score_map under it) / (h w) and consensus = mean(segmask under it) / 255 with
+ * (saliency > saliency_thr && consensus > consensus_thr) || saliency > 10 saliency_thr.  alpha, segmask, out: [n][h][w]
+ * (segmask = alpha for the one-argument form of the reference); score_map: [h][w] float64 (get_score_map, :155-178), shared by
+ * the frames.  status[i] = number of contours of frame i; a frame with more than max_objects contours (or nested deeper
+ * than 65 levels) has status[i] > max_objects and an undefined output: call again with a larger workspace.  Everything
+ * stays on the device.  workspace: vu_remove_objects_workspace_bytes(n, h, w, max_objects), 16-byte aligned. */
+size_t vu_remove_objects_workspace_bytes(int n, int h, int w, int max_objects);
+int vu_remove_invalid_objects(const uint8_t* alpha, const uint8_t* segmask, const double* score_map, int n, int h, int w,
+                              double saliency_thr, double consensus_thr, uint8_t* out, int32_t* status, void* workspace,
+                              size_t workspace_bytes, int max_objects, vu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -555,3 +555,97 @@ def background_forward(img, mask, method="rf", input_long_side=540, dilation_ksi
     else:
         raise NameError(f"No such method for background inpainting: {method}")
     return cvm.resize_linear(bgimg, ow, oh)
+
+
+# --------------------------------------------------------------------------
+# remove_invalid_objects: closed-form model of
+# cv2.findContours(RETR_LIST) + contourArea + drawContours(FILLED)
+# --------------------------------------------------------------------------
+
+def get_score_map(map_size, center):
+    """unscreen/utils/maskprocess.py:155-178."""
+    score_map = np.ones(map_size, np.float64)
+    h, w = map_size
+    y, x = int(h * center[0]), int(w * center[1])
+    score_map[:, x:w] = np.linspace(0, 1, w - x)[np.newaxis, ...] ** 2
+    score_map[:, 0:x] = np.linspace(1, 0, x)[np.newaxis, ...] ** 2
+    score_map[y:h] += np.linspace(0, 1, h - y)[..., np.newaxis] ** 2
+    score_map[0:y] += np.linspace(1, 0, y)[..., np.newaxis] ** 2
+    score_map = np.sqrt(score_map)
+    return (score_map.max() - score_map) / score_map.max()
+
+
+def build_score_map(h, w, config):
+    """unscreen/utils/maskprocess.py:181-189."""
+    centers = config['objectremoval']['score_map_center']
+    return get_score_map((h, w), centers['landscape'] if w > h else centers['portrait'])
+
+
+def contour_objects(X):
+    """Every contour cv2.findContours(X, RETR_LIST) returns, as (fill, area): ``fill`` = the pixels
+    drawContours(.., FILLED) paints for it, ``area`` = cv2.contourArea of it.  X: bool [h,w].
+
+    Foreground components are 8-connected, background components 4-connected, everything outside the image is one
+    background component.  Two kinds of contour:
+      * the outer border of a foreground component C.  Its polygon runs through C's border pixels; filled, it covers
+        F = C and everything C encloses (holes, islands inside holes, ...).
+      * the border of a hole H (a background component other than the outside), traced on the pixels of the surrounding
+        component that are 4-adjacent to H (the ring).  Filled: H, the ring, and everything inside H.
+    The polygon's vertices are pixel centres, so Pick's theorem gives its area from lattice-point counts, and the number
+    B of chain steps of a border is a local count on the region it bounds: B = L - n1 for an outer border (L = pixel
+    edges between F and its complement, n1 = 2x2 windows holding exactly one pixel of F) and B = L - n3 for a hole
+    (edges between H' = H plus its inside and the ring; n3 = windows holding exactly three pixels of H').  Outer:
+    area = |F| - B/2 - 1; hole: area = |H'| + B/2 - 1.  Checked against cv2 on thousands of random shapes
+    (tests/test_oracle_vs_reference.py)."""
+    from scipy import ndimage as ndi
+    S8, S4 = np.ones((3, 3), int), np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]])
+    P = np.pad(np.asarray(X, bool), 2)
+    fl, nf = ndi.label(P, S8)
+    bl, nb = ndi.label(~P, S4)
+
+    def local(F):
+        F = F.astype(np.int8)
+        q = F[:-1, :-1] + F[:-1, 1:] + F[1:, :-1] + F[1:, 1:]
+        L = int((F[:, :-1] != F[:, 1:]).sum() + (F[:-1, :] != F[1:, :]).sum())
+        return L, int((q == 1).sum()), int((q == 3).sum())
+    objs = []
+    for c in range(1, nf + 1):
+        comp = fl == c
+        rest, _ = ndi.label(~comp, S4)
+        fill = rest != rest[0, 0]
+        L, n1, _ = local(fill)
+        objs.append((fill[2:-2, 2:-2], fill.sum() - (L - n1) / 2.0 - 1))
+    for b in range(1, nb + 1):
+        if b == bl[0, 0]:
+            continue
+        hole = bl == b
+        ys, xs = np.nonzero(hole)
+        parent = fl[ys[0], xs[ys == ys[0]].min() - 1]     # the pixel left of the hole's first pixel (raster order)
+        ring = (fl == parent) & ndi.binary_dilation(hole, S4)
+        outside, _ = ndi.label(~hole, S8)
+        inner = (outside != outside[0, 0]) & ~hole        # islands inside the hole
+        hp = hole | inner
+        L, _, n3 = local(hp)
+        objs.append(((hp | ring)[2:-2, 2:-2], hp.sum() + (L - n3) / 2.0 - 1))
+    return objs
+
+
+def remove_invalid_objects(cfg, alpha, segmask=None):
+    """unscreen/utils/maskprocess.py:77-152 on the closed-form contour model above (does not mutate ``alpha``)."""
+    saliency_thr = cfg['objectremoval']['saliency_thr']
+    consensus_thr = cfg['objectremoval']['consensus_thr']
+    if segmask is None:
+        segmask = alpha
+    h, w = alpha.shape
+    score_map = build_score_map(h, w, cfg)
+    valid = np.zeros((h, w), bool)
+    for fill, area in contour_objects(alpha > 0):
+        if area < 100:
+            continue
+        saliency = score_map[fill].sum() / float(h * w)
+        consensus = segmask[fill].astype(np.float64).mean() / 255.
+        if (saliency > saliency_thr and consensus > consensus_thr) or saliency > saliency_thr * 10:
+            valid |= fill
+    out = alpha.copy()
+    out[~valid] = 0
+    return out

@@ -230,6 +230,7 @@ def main():
 
     geometry(U)
     bgmodel(BA)
+    objects(U)
     write_manifest()
 
 
@@ -297,6 +298,41 @@ def bgmodel(BA):
     np.savez_compressed(os.path.join(HERE, "bgmodel.npz"), **out)
 
 
+OBJ_CFGS = [{'objectremoval': {'score_map_center': {'landscape': [0.5, 0.5], 'portrait': [0.6, 0.5]}, 'saliency_thr': t, 'consensus_thr': 0.5}}
+            for t in (0.005, 0.00001, 0.001)]      # configs/green.json, configs/bg.json, the function's default
+
+
+def objects_case(h, w, seed):
+    """blobby matte (thresholded low-pass noise, grey values, sometimes salted with isolated pixels) + an unrelated blobby
+    segmentation mask: components of every size, holes, islands in holes, contours with area around 100"""
+    import cv2
+    rng = np.random.default_rng(seed)
+    x = cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), float(rng.choice([2, 4, 8])))
+    on = x > np.quantile(x, rng.choice([0.5, 0.7, 0.9]))
+    a = on.astype(np.uint8) * rng.integers(1, 256, (h, w), dtype=np.uint8)
+    if seed % 3 == 0:
+        a[rng.random((h, w)) < 0.01] = 200
+    if seed % 4 == 1:
+        a[h // 4: h // 2, w // 4: w // 2] = 0           # a big hole with whatever is left inside
+        a[h // 3, w // 3] = 99
+    seg = (cv2.GaussianBlur(rng.random((h, w)).astype(np.float32), (0, 0), 8) > 0.5).astype(np.uint8) * 255
+    return a, seg
+
+
+def objects(U):
+    """remove_invalid_objects.  `python make_golden.py objects`."""
+    out = {}
+    sizes = [(120, 200), (200, 120), (135, 240), (96, 96), (64, 300), (180, 320)]
+    out["sizes"] = np.array(sizes)
+    for i, (h, w) in enumerate(sizes):
+        a, seg = objects_case(h, w, 40 + i)
+        out[f"alpha_{i}"], out[f"seg_{i}"] = a, seg
+        for c, cfg in enumerate(OBJ_CFGS):
+            out[f"self_{i}_{c}"] = U.remove_invalid_objects(cfg, a.copy())
+            out[f"seg_{i}_{c}"] = U.remove_invalid_objects(cfg, a.copy(), seg.copy())
+    np.savez_compressed(os.path.join(HERE, "objects.npz"), **out)
+
+
 def write_manifest():
     import cv2
     import sklearn
@@ -317,6 +353,9 @@ def write_manifest():
 if __name__ == "__main__":
     if sys.argv[1:] == ["geometry"]:
         geometry(load_reference()[0])
+        write_manifest()
+    elif sys.argv[1:] == ["objects"]:
+        objects(load_reference()[0])
         write_manifest()
     elif sys.argv[1:] == ["bgmodel"]:
         bgmodel(load_reference()[3])

@@ -691,3 +691,59 @@ def test_background_agent_golden(vu, golden, i):
     ag3 = BackgroundAgent(input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3)
     assert np.array_equal(ag3.forward(img, m, "pcov"),
                           R.background_forward(img, m, "pcov", input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3))
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_remove_invalid_objects_golden(vu, golden, i):
+    """remove_invalid_objects on the device (union-find labelling of both classes, nesting tree, local
+    boundary counts, one CTA per frame for the tree) against the reference's goldens and the oracle, bit-exact; the three
+    configurations as one batched call; a table that is too small is redone"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import OBJ_CFGS
+    g = golden("objects")
+    a, seg = g[f"alpha_{i}"], g[f"seg_{i}"]
+    for c, cfg in enumerate(OBJ_CFGS):
+        assert np.array_equal(vu.U.remove_invalid_objects(cfg, a), g[f"self_{i}_{c}"]), c
+        assert np.array_equal(vu.U.remove_invalid_objects(cfg, a, seg), g[f"seg_{i}_{c}"]), c
+    cfg = OBJ_CFGS[1]
+    clip_a = np.stack([a, np.zeros_like(a), np.full_like(a, 255), a[::-1].copy()])
+    clip_s = np.stack([seg, seg, seg, seg[::-1].copy()])
+    got = vu.U.remove_invalid_objects(cfg, clip_a, clip_s)
+    for k in range(4):
+        assert np.array_equal(got[k], R.remove_invalid_objects(cfg, clip_a[k], clip_s[k])), k
+    assert np.array_equal(vu.U.remove_invalid_objects(cfg, a, seg, max_objects=4), g[f"seg_{i}_1"])
+    t = vu.U.remove_invalid_objects(cfg, dev(a), dev(seg))
+    assert t.is_cuda and np.array_equal(host(t), g[f"seg_{i}_1"])
+
+
+def test_remove_invalid_objects_shapes(vu):
+    """hand-made nesting: ring with an island that has its own hole, 1-pixel-wide parts, objects on the image border,
+    diagonal contacts (8-connected foreground / 4-connected background), areas either side of 100"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import OBJ_CFGS
+    h, w = 96, 128
+    a = np.zeros((h, w), np.uint8)
+    a[10:70, 10:90] = 200
+    a[20:60, 20:80] = 0            # hole
+    a[30:50, 30:60] = 150          # island in the hole
+    a[35:45, 38:52] = 0            # its own hole
+    a[38:42, 42:48] = 90           # island in that
+    a[0:12, 100:128] = 255         # touches the border: area (11 * 27) > 100
+    a[80:90, 5:15] = 77            # 10 x 10: contour area 81 < 100
+    a[80:91, 30:41] = 77           # 11 x 11: contour area 100
+    for k in range(15):            # diagonal chain: 8-connected, area 0
+        a[75 + k, 60 + k] = 255
+    a[70, 95] = 255                # diagonal contact with the big ring's corner pixel (69, 89)?  no: isolated pixel
+    a[70, 90] = 255                # this one touches (69, 89) diagonally: joins the ring
+    seg = np.zeros((h, w), np.uint8)
+    seg[:, :70] = 255
+    for cfg in OBJ_CFGS:
+        for s in (None, seg):
+            assert np.array_equal(vu.U.remove_invalid_objects(cfg, a, s), R.remove_invalid_objects(cfg, a, s)), (cfg, s is None)
+    rng = np.random.default_rng(3)
+    for trial in range(6):         # salt and pepper: thousands of components
+        x = (rng.random((72, 100)) < (0.35 + 0.08 * trial)).astype(np.uint8) * 255
+        cfg = {'objectremoval': {'score_map_center': {'landscape': [0.5, 0.5], 'portrait': [0.6, 0.5]}, 'saliency_thr': 1e-7, 'consensus_thr': 0.1}}
+        assert np.array_equal(vu.U.remove_invalid_objects(cfg, x, max_objects=256), R.remove_invalid_objects(cfg, x)), trial

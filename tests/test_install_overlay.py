@@ -67,15 +67,14 @@ import unscreen, unscreen.utils.maskprocess as ref_mp
 assert unscreen.__file__.startswith({REF!r}), unscreen.__file__
 # hot-path names are the B200 mirror's ...
 for name in ("get_fg", "get_bg", "dilate_mask", "exist_foreground", "color_correct", "adaptive_resize", "rescale_fg",
-             "shift_fg"):
+             "shift_fg", "remove_invalid_objects", "build_score_map"):
     assert globals()[name] is getattr(mine, name), name
 assert ColorFilteringAgent is mine_cf.ColorFilteringAgent and TrimapAgent is mine_tri.TrimapAgent
 # ... also inside the reference's own modules (remove_invalid_objects calls its module's dilate_mask)
 assert ref_mp.dilate_mask is mine.dilate_mask
 assert unscreen.utils.temporal_median is mine.temporal_median
 # ... and everything else is still the reference's
-for f in (parallel_read_img, save_img, save_video, remove_invalid_objects, regionfill, build_score_map, get_center,
-          return_date):
+for f in (parallel_read_img, save_img, save_video, regionfill, get_center, return_date):
     assert f.__module__.startswith("unscreen."), (f, f.__module__)
 assert VMattingAgent.__module__ == "unscreen.vmatting.agent" and STMAgent.__module__.startswith("unscreen.stm")
 import unscreen.bgmodel.agent as ref_bg

@@ -165,3 +165,25 @@ def test_background_agent_mean_pcov(golden, i):
     assert z.dtype == np.float64 and z.shape == img.shape and not z.any()
     with pytest.raises(NameError):
         R.background_forward(img, m, "telea")
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_remove_invalid_objects(golden, i):
+    """the closed-form contour model (oracle/refport.py:contour_objects) against the reference's cv2.findContours /
+    contourArea / drawContours loop: bit-exact for the three configurations the repository ships"""
+    sys_path_golden()
+    from make_golden import OBJ_CFGS
+    g = golden("objects")
+    a, seg = g[f"alpha_{i}"], g[f"seg_{i}"]
+    for c, cfg in enumerate(OBJ_CFGS):
+        assert np.array_equal(R.remove_invalid_objects(cfg, a), g[f"self_{i}_{c}"]), c
+        assert np.array_equal(R.remove_invalid_objects(cfg, a, seg), g[f"seg_{i}_{c}"]), c
+    assert any((g[f"self_{i}_{c}"] != a).any() for c in range(3))      # something was removed
+
+
+def sys_path_golden():
+    import os
+    import sys
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    if p not in sys.path:
+        sys.path.insert(0, p)

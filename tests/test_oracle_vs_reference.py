@@ -147,3 +147,29 @@ def test_background_agent(h, w, L, kind):
     ag2 = BA(input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3)
     want = ag2.forward(img.copy(), m.copy(), "pcov")
     assert np.array_equal(R.background_forward(img, m, "pcov", input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3), want)
+
+
+def test_contour_model_vs_cv2():
+    """every contour of cv2.findContours(RETR_LIST): its drawContours(FILLED) paint and its contourArea, against the
+    closed-form model, as multisets, on random small shapes (dense, sparse, closed)"""
+    import cv2
+    rng = np.random.default_rng(5)
+    for trial in range(400):
+        h, w = rng.integers(3, 16, 2)
+        X = rng.random((h, w)) < rng.choice([0.3, 0.5, 0.7, 0.85])
+        img = X.astype(np.uint8) * 255
+        cs, _ = cv2.findContours(img, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+        want = sorted((cv2.drawContours(np.zeros_like(img), cs, i, 255, cv2.FILLED).tobytes(), cv2.contourArea(cs[i])) for i in range(len(cs)))
+        got = sorted(((f.astype(np.uint8) * 255).tobytes(), float(a)) for f, a in R.contour_objects(X))
+        assert want == got, trial
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_remove_invalid_objects(ref, seed):
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import OBJ_CFGS, objects_case
+    h, w = [(100, 160), (160, 100), (90, 90), (120, 210)][seed % 4]
+    a, seg = objects_case(h, w, 900 + seed)
+    for cfg in OBJ_CFGS:
+        assert np.array_equal(R.remove_invalid_objects(cfg, a), ref.U.remove_invalid_objects(cfg, a.copy()))
+        assert np.array_equal(R.remove_invalid_objects(cfg, a, seg), ref.U.remove_invalid_objects(cfg, a.copy(), seg.copy()))

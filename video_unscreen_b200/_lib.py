@@ -78,6 +78,8 @@ SIGNATURES = {
     "vu_mask_bbox": (_i, [_p, _i, _i, _p, _p]),
     "vu_masked_sum3": (_i, [_p, _p, _i64, _p, _p]),
     "vu_pcov_round": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "vu_remove_objects_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i]),
+    "vu_remove_invalid_objects": (_i, [_p, _p, _p, _i, _i, _i, _d, _d, _p, _p, _p, ctypes.c_size_t, _i, _p]),
     "vu_get_fg": (_i, [_p, _p, _p, _i64, _i64, _i, _p, _p, _p]),
     "vu_get_bg": (_i, [_p, _p, _i64, _p, _p]),
     "vu_blend": (_i, [_i, _p, _p, _i, _p, _i64, _i64, _p, _p]),

@@ -718,3 +718,25 @@ def pcov_fill(img, hole_mask, box, ksize=5, max_rounds=100, batch=8):
             done_after = int(zero[0]) + 1
             break
     return bufs[done_after % 2]
+
+
+# ---- remove_invalid_objects (utils/maskprocess.py:77-152) -----------------------------------------
+
+def remove_invalid_objects(alpha, segmask, score_map, saliency_thr, consensus_thr, max_objects=16384, out=None):
+    """alpha / segmask [H,W] or [N,H,W]; score_map [H,W] float64 device tensor.  -> (out, status): status [n] int32 device
+    tensor = contours per frame, > max_objects where a frame overflowed (output undefined there; the caller checks)."""
+    alpha, segmask = _mask(alpha), _mask(segmask)
+    if segmask.shape != alpha.shape:
+        raise ValueError("segmask must have alpha's shape")
+    score_map = _dev(score_map, torch.float64)
+    h, w = alpha.shape[-2:]
+    if tuple(score_map.shape) != (h, w):
+        raise ValueError("score_map must be [H,W]")
+    n = 1 if alpha.ndim == 2 else alpha.shape[0]
+    out = _out(out, alpha.shape, alpha.device)
+    status = torch.empty(n, dtype=torch.int32, device=alpha.device)
+    ws_bytes = int(lib().vu_remove_objects_workspace_bytes(n, h, w, int(max_objects)))
+    ws = torch.empty(ws_bytes, dtype=u8, device=alpha.device)
+    check(lib().vu_remove_invalid_objects(_p(alpha), _p(segmask), _p(score_map), n, h, w, float(saliency_thr), float(consensus_thr), _p(out),
+                                          _p(status), _p(ws), ws_bytes, int(max_objects), _stream()))
+    return out, status

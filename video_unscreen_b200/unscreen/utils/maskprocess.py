@@ -4,7 +4,10 @@ import torch
 from ... import _lib, ops
 from ..._io import back, to_dev
 
-__all__ = ["dilate_mask", "erode_mask", "exist_foreground", "get_outer_boundary"]
+import numpy as np
+
+__all__ = ["dilate_mask", "erode_mask", "exist_foreground", "get_outer_boundary", "remove_invalid_objects", "get_score_map",
+           "build_score_map"]
 
 
 def _morph(mask, kernelsize, iters, op):
@@ -41,3 +44,58 @@ def get_outer_boundary(mask, kernelsize=7, iters=10):
     t, as_np = to_dev(mask)
     d = ops.dilate(t, kernelsize, iters)
     return back(ops.sub_wrap(d, t), as_np)
+
+
+def get_score_map(map_size, center):
+    """reference maskprocess.py:155-178: 1 at ``center`` (a ratio of the size), falling linearly to 0 at the borders"""
+    score_map = np.ones(map_size, np.float64)
+    h, w = map_size
+    y, x = int(h * center[0]), int(w * center[1])
+    score_map[:, x:w] = np.linspace(0, 1, w - x)[np.newaxis, ...]**2
+    score_map[:, 0:x] = np.linspace(1, 0, x)[np.newaxis, ...]**2
+    score_map[y:h] += np.linspace(0, 1, h - y)[..., np.newaxis]**2
+    score_map[0:y] += np.linspace(1, 0, y)[..., np.newaxis]**2
+    score_map = np.sqrt(score_map)
+    score_map = (score_map.max() - score_map) / score_map.max()
+    return score_map
+
+
+def build_score_map(h, w, config):
+    """reference maskprocess.py:181-189."""
+    centers = config['objectremoval']['score_map_center']
+    return get_score_map((h, w), centers['landscape'] if w > h else centers['portrait'])
+
+
+_SCORE_MAPS = {}
+
+
+def _score_map_dev(h, w, cfg, device):
+    centers = cfg['objectremoval']['score_map_center']
+    center = tuple(centers['landscape'] if w > h else centers['portrait'])
+    key = (h, w, center, str(device))
+    if key not in _SCORE_MAPS:
+        _SCORE_MAPS[key] = torch.from_numpy(get_score_map((h, w), center)).to(device)
+    return _SCORE_MAPS[key]
+
+
+def remove_invalid_objects(cfg, alpha, segmask=None, saliency_thr=0.001, consensus_thr=0.5, score_map=None,
+                           score_map_center=(3. / 5, 1. / 2), max_objects=16384):
+    """reference maskprocess.py:77-152: clear every object (contour of cv2.findContours) whose saliency or consensus score
+    fails.  As in the reference the thresholds and the score map come from ``cfg['objectremoval']`` (the keyword arguments
+    of the same name are ignored there too).  ``alpha`` may be [H,W] or a clip [N,H,W]; it is not modified.  Frames with
+    more than ``max_objects`` contours are redone with a larger table."""
+    saliency_thr = cfg['objectremoval']['saliency_thr']
+    consensus_thr = cfg['objectremoval']['consensus_thr']
+    a, as_np = to_dev(alpha)
+    s = a if segmask is None else to_dev(segmask)[0]
+    h, w = a.shape[-2:]
+    sm = _score_map_dev(h, w, cfg, a.device)
+    while True:
+        out, status = ops.remove_invalid_objects(a, s, sm, saliency_thr, consensus_thr, max_objects)
+        worst = int(status.max().item())
+        if worst <= max_objects:
+            break
+        if worst > h * w + 1:          # nested deeper than the tree kernel handles
+            raise RuntimeError("remove_invalid_objects: objects nested deeper than 65 levels")
+        max_objects = worst
+    return back(out, as_np)
