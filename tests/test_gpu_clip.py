@@ -251,3 +251,35 @@ def test_fused_green_chunk_equals_staged(env, tag, h, w, L):
     tri = env.ops.trimap_bits_packed(mb, fzb, flags, h, w, th, tw, 5)
     assert torch.equal(tri, env.ops.trimap_bits(want_a, th, tw, 5, fz, flags))
     assert torch.equal(env.ops.trimap_bits_packed(mb, None, None, h, w, th, tw, 3), env.ops.trimap_bits(want_a, th, tw, 3))
+
+
+def test_green_clip_with_object_removal(env):
+    """green.py:99-126 with remove_invalid_objects (:106-109) between colour filtering and the trimap, all on the device:
+    every frame against the oracle chain"""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import OBJ_CFGS
+    n, h, w, L = 5, 108, 192, 96
+    frames, segs = synth.green_clip(n, h, w, seed=31)
+    rng = np.random.default_rng(2)
+    for i in range(n):          # clutter for the removal to work on: small person-coloured patches away from the person
+        for _ in range(6):
+            y, x, s = rng.integers(0, h - 14), rng.integers(0, w - 14), rng.integers(3, 14)
+            frames[i, y:y + s, x:x + s] = np.array(synth.PERSON, np.uint8)
+    lb, lf, bgh = env.tables["x2"]
+    cf = env.CF(input_long_side=L)
+    cf.set_tables(lb, lf, bgh)
+    ta = env.TA(input_long_side=L)
+    cfg = OBJ_CFGS[0]
+    alpha, tri, fg, bgo = (t.cpu().numpy() for t in env.clip.green_clip(dev(frames), dev(segs), cf, ta, chunk=2, remove_objects=cfg))
+    col = cf.bg_color_bgr()
+    removed = 0
+    for i in range(n):
+        a_cf, _, _ = R.cf_forward_predict(frames[i], segs[i], lb, lf, bgh, L)
+        a_o = R.remove_invalid_objects(cfg, a_cf, segs[i])
+        removed += int((a_o != a_cf).sum())
+        assert np.array_equal(alpha[i], a_o), i
+        assert np.array_equal(tri[i], R.generate_trimap_withbg(a_o, frames[i], col, L)), i
+        patched = R.patch_bg(np.broadcast_to(col, frames[i].shape), frames[i], a_o, "lt128")
+        assert np.array_equal(bgo[i], patched) and np.array_equal(fg[i], R.get_fg(frames[i], a_o, patched)), i
+    assert removed > 0

@@ -747,3 +747,35 @@ def test_remove_invalid_objects_shapes(vu):
         x = (rng.random((72, 100)) < (0.35 + 0.08 * trial)).astype(np.uint8) * 255
         cfg = {'objectremoval': {'score_map_center': {'landscape': [0.5, 0.5], 'portrait': [0.6, 0.5]}, 'saliency_thr': 1e-7, 'consensus_thr': 0.1}}
         assert np.array_equal(vu.U.remove_invalid_objects(cfg, x, max_objects=256), R.remove_invalid_objects(cfg, x)), trial
+
+
+@pytest.mark.parametrize("h,w", [(33, 47), (5, 3), (1, 1), (35, 64)])
+def test_compositing_odd_sizes_and_views(vu, h, w):
+    """frames whose pixel count is not a multiple of 4, and unaligned views, go to the one-pixel-per-thread
+    kernels instead of raising; a background of the wrong shape raises instead of wrapping around"""
+    rng = np.random.default_rng(h * 100 + w)
+    fr = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    bg = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    al = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    al[rng.random((h, w)) < 0.3] = 0
+    assert np.array_equal(vu.U.get_fg(fr, al, bg), R.get_fg(fr, al, bg))
+    assert np.array_equal(vu.U.get_fg(fr, al, bg, patch="eq0"), R.get_fg(fr, al, R.patch_bg(bg, fr, al, "eq0")))
+    assert np.array_equal(vu.U.get_bg(al, bg), R.get_bg(al, bg))
+    assert np.array_equal(vu.U.get_fg_naive(fr, al), R.get_fg_naive(fr, al))
+    assert np.array_equal(vu.U.fuse_fgbg(fr, bg, al), R.fuse_fgbg(fr, bg, al))
+    assert np.array_equal(vu.U.replace_blend(fr, al, bg), R.replace_blend(fr, al, bg))
+    assert np.array_equal(vu.U.replace_blend(fr, np.stack([al] * 3, -1), bg), R.replace_blend(fr, al, bg))
+    assert np.array_equal(vu.U.composite_fgbg(fr, al, bg), R.composite_fgbg(fr, al, bg))
+    assert np.array_equal(vu.U.fuse_bg(fr, bg, 0.1), R.fuse_bg(fr, bg, 0.1))
+    assert np.array_equal(vu.U.bgdiff_gate(fr, bg, al, 25), R.bgdiff_gate(fr, bg, al, 25))
+    # an unaligned view: one byte into a larger buffer
+    buf = torch.zeros(h * w * 3 + 8, dtype=torch.uint8, device="cuda")
+    view = buf[1:1 + h * w * 3].view(h, w, 3)
+    view.copy_(dev(fr))
+    got = vu.ops.get_fg(view, dev(al), dev(bg))
+    assert np.array_equal(host(got), R.get_fg(fr, al, bg))
+    if h > 1:
+        with pytest.raises(ValueError):
+            vu.ops.get_fg(dev(fr), dev(al), dev(bg[: h - 1]))
+        with pytest.raises(ValueError):
+            vu.ops.blend(3, dev(fr), dev(al), dev(bg[:, : w - 1].copy()) if w > 1 else dev(bg[: h - 1]))

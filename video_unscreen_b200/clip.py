@@ -277,10 +277,14 @@ def color_correct_clip(frames, alpha, bg_color, target_long_side=960, mean_exp=0
     return out
 
 
-def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2, fused=True, out=None):
+def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None, bg_tile=None, color_correct=False, streams=2, fused=True, out=None,
+               remove_objects=None, max_objects=16384):
     """the green-screen loop of tools/unscreen/green.py:70-138 without its CNN
-    stages (alpha := colour-filter alpha): cf predict -> trimap with bg colour ->
-    [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.
+    stages (alpha := colour-filter alpha): cf predict -> [remove_invalid_objects, green.py:106-109, when
+    ``remove_objects`` = the script's cfg dict is given: the matte the trimap and get_fg see is the cleaned one; every
+    frame is scored against its segmentation mask, like the frames after the first in the script] -> trimap with bg
+    colour -> [color_correct, green.py:120, when asked for] -> bgimg[alpha<128] = frame[...] -> get_fg.  Everything
+    stays on the device; a frame with more than ``max_objects`` contours raises after the clip (one read-back).
     Returns alpha, trimap, fg, bg.
     ``bg_color`` ((3,) BGR, host) / ``bg_tile`` ([1,4,3] device) default to the agent's background colour; pass them
     in when the call is captured into a CUDA graph (fetching them synchronises)."""
@@ -297,9 +301,23 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None
         bg_color = cf_agent.bg_color_bgr()
     if bg_tile is None:
         bg_tile = torch.from_numpy(np.tile(bg_color, (1, 4, 1))).to(dev)     # constant background: a 4-pixel periodic image
-    use_fused = fused and _fused_green_supported(frames, segmasks, cf_agent, trimap_agent)
+    use_fused = fused and remove_objects is None and _fused_green_supported(frames, segmasks, cf_agent, trimap_agent)
+    statuses = []
+    if remove_objects is not None:
+        from .unscreen.utils.maskprocess import _score_map_dev
+        score_map = _score_map_dev(h, w, remove_objects, dev)
+        sal_thr, con_thr = remove_objects['objectremoval']['saliency_thr'], remove_objects['objectremoval']['consensus_thr']
     def body(s, e):
         # every stage writes straight into its slice of the clip-sized results
+        if remove_objects is not None:
+            a = cf_predict_clip(frames[s:e], segmasks[s:e], cf_agent, chunk=chunk)
+            a, st = ops.remove_invalid_objects(a, segmasks[s:e], score_map, sal_thr, con_thr, max_objects, out=alpha[s:e])
+            statuses.append(st)
+            trimap_clip(a, trimap_agent, frames[s:e], bg_color, chunk=chunk, out=tri[s:e])
+            if color_correct:
+                a = color_correct_clip(frames[s:e], a.clone(), bg_color, chunk=chunk, out=alpha[s:e])
+            ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True, out=fg[s:e], bg_out=bgo[s:e])
+            return
         if use_fused and not color_correct:      # get_fg rides along in the second pass (one BGR2HSV per pixel for both)
             _fused_green_chunk(frames[s:e], segmasks[s:e], cf_agent, trimap_agent, bg_color, alpha[s:e], tri[s:e], fg[s:e], bgo[s:e])
             return
@@ -314,6 +332,8 @@ def green_clip(frames, segmasks, cf_agent, trimap_agent, chunk=24, bg_color=None
         ops.get_fg(frames[s:e], a, bg_tile, _lib.PATCH_ALPHA_LT128, want_bg=True, out=fg[s:e], bg_out=bgo[s:e])
     cf_agent.tables_dev(), cf_agent.lut3d_dev()      # built (once) on the current stream, not on a side stream
     _overlap_chunks(n, chunk, body, streams)
+    if statuses and int(torch.cat(statuses).max().item()) > max_objects:
+        raise RuntimeError(f"green_clip: a frame has more than max_objects = {max_objects} contours; call again with a larger table")
     return alpha, tri, fg, bgo
 
 

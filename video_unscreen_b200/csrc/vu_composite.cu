@@ -7,6 +7,8 @@
 // reference's operation order, so the stages before cv2's HSV2BGR are
 // bit-exact; HSV2BGR itself is the truncating whole-image variant (+-1 LSB
 // against cv2 by cv2's own inconsistency).
+#include <initializer_list>
+
 #include "vu_common.cuh"
 
 namespace vu {
@@ -374,31 +376,125 @@ __global__ void __launch_bounds__(THREADS) bgdiff_gray_kernel(const uint8_t* __r
   }
 }
 
+// ---- one pixel per thread, byte accesses: frames whose pixel count is not a multiple of 4 (odd x odd sizes) or whose
+// buffers are not 4-byte aligned (views into larger arrays).  Same arithmetic as the vector kernels above. ----
+template <int PATCH, bool WRITE_BG>
+__global__ void __launch_bounds__(THREADS) get_fg_px_kernel(const uint8_t* __restrict__ frame, const uint8_t* __restrict__ alpha,
+                                                            const uint8_t* __restrict__ bg, int64_t npix, int64_t bg_npix,
+                                                            uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = alpha[i];
+    const uint8_t* f = frame + 3 * i;
+    const uint8_t* b = bg + 3 * (i % bg_npix);
+    const bool patch = (PATCH == VU_PATCH_ALPHA_LT128) ? (a < 128) : (PATCH == VU_PATCH_ALPHA_EQ0 ? (a == 0) : false);
+    const int c0 = f[0], c1 = f[1], c2 = f[2];
+    const int q0 = patch ? c0 : b[0], q1 = patch ? c1 : b[1], q2 = patch ? c2 : b[2];
+    int ih, is, iv, bh, bs, bv, o0, o1, o2;
+    bgr2hsv_px(c0, c1, c2, tab, ih, is, iv);
+    bgr2hsv_px(q0, q1, q2, tab, bh, bs, bv);
+    const float k = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
+    hsv2bgr_px(trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh)))), trunc_clamp255(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs)))),
+               trunc_clamp255(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bv)))), tab, o0, o1, o2);
+    fg_out[3 * i] = (uint8_t)o0; fg_out[3 * i + 1] = (uint8_t)o1; fg_out[3 * i + 2] = (uint8_t)o2;
+    if (WRITE_BG) { bg_out[3 * i] = (uint8_t)q0; bg_out[3 * i + 1] = (uint8_t)q1; bg_out[3 * i + 2] = (uint8_t)q2; }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) get_bg_px_kernel(const uint8_t* __restrict__ alpha, const uint8_t* __restrict__ bg, int64_t npix,
+                                                            uint8_t* __restrict__ out) {
+  __shared__ HsvTab tab;
+  hsv_tab_init(tab);
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    int bh, bs, bv, o0, o1, o2;
+    bgr2hsv_px(bg[3 * i], bg[3 * i + 1], bg[3 * i + 2], tab, bh, bs, bv);
+    const float k = __fsub_rn(1.f, __fdiv_rn((float)alpha[i], 255.f));
+    hsv2bgr_px(trunc_clamp255(__fmul_rn(k, u8_to_f32(bh))), trunc_clamp255(__fmul_rn(k, u8_to_f32(bs))), trunc_clamp255(__fmul_rn(k, u8_to_f32(bv))),
+               tab, o0, o1, o2);
+    out[3 * i] = (uint8_t)o0; out[3 * i + 1] = (uint8_t)o1; out[3 * i + 2] = (uint8_t)o2;
+  }
+}
+
+template <int MODE, int AC>
+__global__ void __launch_bounds__(THREADS) blend_px_kernel(const uint8_t* __restrict__ fg, const uint8_t* __restrict__ alpha,
+                                                           const uint8_t* __restrict__ bg, int64_t npix, int64_t bg_npix, uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      const double c = (double)fg[3 * i + ch];
+      const double q = MODE == VU_BLEND_NAIVE ? 0.0 : (double)bg[3 * (i % bg_npix) + ch];
+      double m = __ddiv_rn((double)(AC == 3 ? alpha[3 * i + ch] : alpha[i]), 255.0);
+      double r;
+      if (MODE == VU_BLEND_NAIVE) {
+        r = __dmul_rn(c, m);
+      } else if (MODE == VU_BLEND_COMPOSITE) {
+        if (m > 0.9) m = 1.0;
+        r = fmin(fmax(__dadd_rn(c, __dmul_rn(q, __dsub_rn(1.0, m))), 0.0), 255.0);
+      } else if (MODE == VU_BLEND_FUSE) {
+        r = __dadd_rn(__dmul_rn(m, c), __dmul_rn(__dsub_rn(1.0, m), q));
+      } else {
+        r = __dadd_rn(__dmul_rn(c, m), __dmul_rn(q, __dsub_rn(1.0, m)));
+      }
+      out[3 * i + ch] = (uint8_t)(int)r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(THREADS) fuse_bg_px_kernel(const uint8_t* __restrict__ bg, const uint8_t* __restrict__ always, int64_t nbytes,
+                                                             int64_t always_bytes, float beta, float omb, uint8_t* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (uint8_t)((int)__fadd_rn(__fmul_rn((float)bg[i], beta), __fmul_rn(omb, (float)always[i % always_bytes])) & 255);
+}
+
+__global__ void __launch_bounds__(THREADS) bgdiff_gray_px_kernel(const uint8_t* __restrict__ frame, const uint8_t* __restrict__ bg, int64_t npix,
+                                                                 int64_t bg_npix, int thr, uint8_t* __restrict__ gray) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint8_t* f = frame + 3 * i;
+    const uint8_t* b = bg + 3 * (i % bg_npix);
+    int y = bgr2gray_px(abs((int)f[0] - (int)b[0]), abs((int)f[1] - (int)b[1]), abs((int)f[2] - (int)b[2]));
+    if (y > thr) y = 255;
+    gray[i] = (uint8_t)y;
+  }
+}
+
 inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
+// true when the 4-pixel vector kernels cannot take the call: the byte kernels above do
+inline bool needs_px(int64_t npix, int64_t other_npix, std::initializer_list<const void*> ptrs) {
+  if (npix % 4 != 0 || (other_npix > 0 && other_npix % 4 != 0)) return true;
+  for (const void* p : ptrs)
+    if (p && !al4(p)) return true;
+  return false;
+}
 
 }  // namespace
 }  // namespace vu
 
 using namespace vu;
 
-// The vector kernels need 4-byte aligned pointers and pixel counts that are
-// multiples of 4 (true for every even-sized frame); anything else is refused
-// rather than silently taking a different code path.
-#define VU_REQUIRE_VEC(npix, ...)                                   \
-  do {                                                              \
-    const void* ptrs__[] = {__VA_ARGS__};                           \
-    for (const void* p__ : ptrs__)                                  \
-      if (p__ && !al4(p__)) return VU_ERR_UNSUPPORTED;              \
-    if ((npix) % 4 != 0) return VU_ERR_UNSUPPORTED;                 \
-  } while (0)
+// The vector kernels need 4-byte aligned pointers and pixel counts that are multiples of 4 (true for every even-sized
+// frame); anything else (odd x odd frames, unaligned views) goes to the one-pixel-per-thread kernels: same results.
 
 extern "C" int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8_t* bg, int64_t npix, int64_t bg_npix, int patch_mode,
                          uint8_t* fg_out, uint8_t* bg_out, vu_stream_t stream) {
   VU_REQUIRE(frame && alpha && bg && fg_out && npix >= 0 && bg_npix > 0);
   VU_REQUIRE(patch_mode >= VU_PATCH_NONE && patch_mode <= VU_PATCH_ALPHA_EQ0);
-  VU_REQUIRE_VEC(npix, frame, alpha, bg, fg_out, bg_out);
-  if (bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
   if (npix == 0) return VU_OK;
+  if (needs_px(npix, bg_npix == 1 ? 0 : bg_npix, {frame, alpha, bg, fg_out, bg_out}) || bg_npix == 1) {
+    const int g = grid_for(npix, THREADS, 8);
+#define VU_PX(P)                                                                                                   \
+  do {                                                                                                             \
+    if (bg_out) get_fg_px_kernel<P, true><<<g, THREADS, 0, S(stream)>>>(frame, alpha, bg, npix, bg_npix, fg_out, bg_out); \
+    else get_fg_px_kernel<P, false><<<g, THREADS, 0, S(stream)>>>(frame, alpha, bg, npix, bg_npix, fg_out, bg_out);       \
+  } while (0)
+    if (patch_mode == VU_PATCH_NONE) VU_PX(VU_PATCH_NONE);
+    else if (patch_mode == VU_PATCH_ALPHA_LT128) VU_PX(VU_PATCH_ALPHA_LT128);
+    else VU_PX(VU_PATCH_ALPHA_EQ0);
+#undef VU_PX
+    VU_RETURN_LAUNCH();
+  }
   const int64_t ng = npix / 4, bgg = bg_npix / 4;
   int mode = 3;
   dim3 grid(grid_for(ng, THREADS, 8));
@@ -459,8 +555,11 @@ extern "C" int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8
 
 extern "C" int vu_get_bg(const uint8_t* alpha, const uint8_t* bg, int64_t npix, uint8_t* out, vu_stream_t stream) {
   VU_REQUIRE(alpha && bg && out && npix >= 0);
-  VU_REQUIRE_VEC(npix, alpha, bg, out);
   if (npix == 0) return VU_OK;
+  if (needs_px(npix, 0, {alpha, bg, out})) {
+    get_bg_px_kernel<<<grid_for(npix, THREADS, 8), THREADS, 0, S(stream)>>>(alpha, bg, npix, out);
+    VU_RETURN_LAUNCH();
+  }
   get_bg_kernel<<<grid_for(npix / 4, THREADS, 8), THREADS, 0, S(stream)>>>(alpha, bg, npix / 4, out);
   VU_RETURN_LAUNCH();
 }
@@ -471,9 +570,24 @@ extern "C" int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int a
   VU_REQUIRE(mode >= VU_BLEND_NAIVE && mode <= VU_BLEND_REPLACE);
   VU_REQUIRE(alpha_channels == 1 || alpha_channels == 3);
   VU_REQUIRE(mode == VU_BLEND_NAIVE || (bg && bg_npix > 0));
-  VU_REQUIRE_VEC(npix, fg, alpha, bg, out);
-  if (mode != VU_BLEND_NAIVE && bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
   if (npix == 0) return VU_OK;
+  if (needs_px(npix, mode == VU_BLEND_NAIVE ? 0 : bg_npix, {fg, alpha, bg, out})) {
+    const int g = grid_for(npix, THREADS, 8);
+    const int64_t bn = mode == VU_BLEND_NAIVE ? 1 : bg_npix;
+#define VU_PX(M)                                                                                              \
+  do {                                                                                                        \
+    if (alpha_channels == 1) blend_px_kernel<M, 1><<<g, THREADS, 0, S(stream)>>>(fg, alpha, bg, npix, bn, out); \
+    else blend_px_kernel<M, 3><<<g, THREADS, 0, S(stream)>>>(fg, alpha, bg, npix, bn, out);                  \
+  } while (0)
+    switch (mode) {
+      case VU_BLEND_NAIVE: VU_PX(VU_BLEND_NAIVE); break;
+      case VU_BLEND_FUSE: VU_PX(VU_BLEND_FUSE); break;
+      case VU_BLEND_COMPOSITE: VU_PX(VU_BLEND_COMPOSITE); break;
+      default: VU_PX(VU_BLEND_REPLACE); break;
+    }
+#undef VU_PX
+    VU_RETURN_LAUNCH();
+  }
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const bool wide = npix % 16 == 0 && (mode == VU_BLEND_NAIVE || bg_npix % 16 == 0) && al16(fg) && al16(alpha) && al16(out) && (!bg || al16(bg));
   if (wide) {
@@ -516,9 +630,11 @@ extern "C" int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int a
 extern "C" int vu_fuse_bg(const uint8_t* bg, const uint8_t* bg_always, int64_t npix, int64_t always_npix, float beta, float one_minus_beta,
                           uint8_t* out, vu_stream_t stream) {
   VU_REQUIRE(bg && bg_always && out && npix >= 0 && always_npix > 0);
-  VU_REQUIRE_VEC(npix, bg, bg_always, out);
-  if (always_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
   if (npix == 0) return VU_OK;
+  if (needs_px(npix, always_npix, {bg, bg_always, out})) {
+    fuse_bg_px_kernel<<<grid_for(npix * 3, THREADS, 8), THREADS, 0, S(stream)>>>(bg, bg_always, npix * 3, always_npix * 3, beta, one_minus_beta, out);
+    VU_RETURN_LAUNCH();
+  }
   const int64_t nwords = npix * 3 / 4, aw = always_npix * 3 / 4;
   fuse_bg_kernel<<<grid_for(nwords, THREADS, 8), THREADS, 0, S(stream)>>>(reinterpret_cast<const unsigned*>(bg), reinterpret_cast<const unsigned*>(bg_always),
                                                                            nwords, aw, beta, one_minus_beta, reinterpret_cast<unsigned*>(out));
@@ -528,9 +644,11 @@ extern "C" int vu_fuse_bg(const uint8_t* bg, const uint8_t* bg_always, int64_t n
 extern "C" int vu_bgdiff_gray(const uint8_t* frame, const uint8_t* bg, int64_t npix, int64_t bg_npix, int thr, uint8_t* gray,
                               vu_stream_t stream) {
   VU_REQUIRE(frame && bg && gray && npix >= 0 && bg_npix > 0);
-  VU_REQUIRE_VEC(npix, frame, bg, gray);
-  if (bg_npix % 4 != 0) return VU_ERR_UNSUPPORTED;
   if (npix == 0) return VU_OK;
+  if (needs_px(npix, bg_npix, {frame, bg, gray})) {
+    bgdiff_gray_px_kernel<<<grid_for(npix, THREADS, 8), THREADS, 0, S(stream)>>>(frame, bg, npix, bg_npix, thr, gray);
+    VU_RETURN_LAUNCH();
+  }
   bgdiff_gray_kernel<<<grid_for(npix / 4, THREADS, 8), THREADS, 0, S(stream)>>>(frame, bg, npix / 4, bg_npix / 4, thr, gray);
   VU_RETURN_LAUNCH();
 }

@@ -513,10 +513,21 @@ def cf_threshold(alpha, mask, thr_ratio=0.8):
 
 # ---- compositing ----------------------------------------------------------------
 
+def _check_bg(bg, img, what):
+    """a background the kernels index correctly: the image's own shape, one [H,W,3] image under a clip, or the constant
+    tile ([1,4,3] / [1,1,3]: the caller's four pixels are one colour).  Anything else would wrap around silently."""
+    if tuple(bg.shape) == tuple(img.shape) or (img.ndim == 4 and tuple(bg.shape) == tuple(img.shape[1:])):
+        return
+    if bg.ndim == 3 and bg.shape[0] == 1 and bg.shape[1] in (1, 4) and img.shape[-3:-1] != (1, 4):
+        return
+    raise ValueError(f"{what}: background {tuple(bg.shape)} does not match the image {tuple(img.shape)}")
+
+
 def get_fg(frame, alpha, bg, patch=_lib.PATCH_NONE, want_bg=False, out=None, bg_out=None):
     frame, alpha, bg = _img(frame), _mask(alpha), _img(bg)
     if alpha.shape != frame.shape[:-1]:
         raise ValueError("alpha must have the frame's [N,]H,W")
+    _check_bg(bg, frame, "get_fg")
     fg = _out(out, frame.shape, frame.device)
     bgo = _out(bg_out, frame.shape, frame.device) if want_bg else None
     check(lib().vu_get_fg(_p(frame), _p(alpha), _p(bg), frame.numel() // 3, bg.numel() // 3, patch, _p(fg), _p(bgo), _stream()))
@@ -537,6 +548,7 @@ def blend(mode, fg, alpha, bg=None, out=None):
         raise ValueError("alpha must be [N,]H,W or the image's shape")
     if bg is not None:
         bg = _img(bg)
+        _check_bg(bg, fg, "blend")
     out = _out(out, fg.shape, fg.device)
     check(lib().vu_blend(mode, _p(fg), _p(alpha), ac, _p(bg), fg.numel() // 3, (bg.numel() // 3) if bg is not None else 0, _p(out), _stream()))
     return out
