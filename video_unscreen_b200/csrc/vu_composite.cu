@@ -292,18 +292,34 @@ __global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restric
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
     uint4 f[3], q[3], av[3], o[3];
+    if (AC == 3) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) av[k] = ldg_stream16(alpha + 3 * g + k);
+    } else {
+      av[0] = ldg_stream16(alpha + g);
+    }
+    if (MODE == VU_BLEND_REPLACE && AC == 1) {
+      // mattes are mostly 0 or 255: m = 1 gives fl(c * 1) + fl(q * 0) = c and m = 0 gives q, exactly: sixteen such pixels are
+      // a copy of one of the two images, and the other one is not even read
+      const unsigned all1 = av[0].x & av[0].y & av[0].z & av[0].w, any = av[0].x | av[0].y | av[0].z | av[0].w;
+      if (all1 == 0xFFFFFFFFu) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, ldg_stream16(fg + 3 * g + k));
+        continue;
+      }
+      if (any == 0u) {
+        const int64_t gb = g % bg_groups;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k));
+        continue;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < 3; ++k) f[k] = ldg_stream16(fg + 3 * g + k);
     if (MODE != VU_BLEND_NAIVE) {
       const int64_t gb = g % bg_groups;
 #pragma unroll
       for (int k = 0; k < 3; ++k) q[k] = (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k);
-    }
-    if (AC == 3) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) av[k] = ldg_stream16(alpha + 3 * g + k);
-    } else {
-      av[0] = ldg_stream16(alpha + g);
     }
     const unsigned* fw = reinterpret_cast<const unsigned*>(f);
     const unsigned* qw = reinterpret_cast<const unsigned*>(q);

@@ -161,8 +161,12 @@ __global__ void __launch_bounds__(OT) obj_flatten_kernel(const uint8_t* __restri
   const ObjWs ws = ws_of(wsbase, blockIdx.y, npix, cap);
   for (int64_t i = (int64_t)blockIdx.x * OT + threadIdx.x; i < npix; i += (int64_t)gridDim.x * OT) {
     const int me = (int)i + 1;
-    const int r = uf_find(ws.P, me);
-    ws.P[me] = r;     // safe: r is a root, and a root's entry never changes any more
+    // read-only walk: a path-halving find here would let another thread overwrite my final label with a mere ancestor
+    // (it writes into the nodes it passes); every entry only ever moves towards the root, so reading while others write
+    // their roots is safe
+    int r = me;
+    for (int p = ws.P[r]; p != r; p = ws.P[r]) r = p;
+    ws.P[me] = r;
     if (r == me) {
       const int k = atomicAdd(ws.nroots, 1);
       if (k < cap) {
