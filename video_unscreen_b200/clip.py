@@ -126,17 +126,20 @@ def streamed(host_inputs, host_outputs, body, chunk, depth=2):
         st.synchronize()
 
 
-def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None, streams=2):
+def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None, streams=2, return_flags=False):
     """ColorFilteringAgent.forward(frame, mask, iters=0) for every frame of
     frames[N,H,W,3] / segmasks[N,H,W] with the agent's current mixtures
     (reference colorfiltering/agent.py:285-354, predict-only branch :319-321).
-    Returns alpha[N,H,W]; the constant background image is ``agent.bg_color_bgr()``."""
+    Returns alpha[N,H,W]; the constant background image is ``agent.bg_color_bgr()``.
+    ``return_flags``: also the per-frame early-out flags [N] uint8 (1: no foreground, 2: no background: alpha is the
+    mask itself, agent.py:303-307; 0: evaluated)."""
     n, h, w, _ = frames.shape
     th, tw = get_target_size(h, w, agent.input_long_side)
     luts = agent.tables_dev()
     lut3d = agent.lut3d_dev()
     alpha = out if out is not None else torch.empty((n, h, w), dtype=torch.uint8, device=frames.device)
     fg_min, bg_min = max(agent.fg_ncomp) * 5, max(agent.bg_ncomp) * 5
+    all_flags = torch.empty(n, dtype=torch.uint8, device=frames.device) if return_flags else None
 
     def body(s, e):
         fr, sm = frames[s:e], segmasks[s:e]
@@ -156,8 +159,10 @@ def cf_predict_clip(frames, segmasks, agent, chunk=64, out=None, streams=2):
             a_lo = ops.cf_postprocess(ops.cf_alpha_lut3d(hsv_lo, lut3d), ops.resize_linear_mask(sm, th, tw), 0.8)
         # degenerate masks are returned as they came (agent.py:303-307): alt_src / alt_flags
         ops.resize_up(a_lo, h, w, alt_src=sm, alt_flags=flags, out=alpha[s:e])
+        if return_flags:
+            all_flags[s:e].copy_(flags)
     _overlap_chunks(n, chunk, body, streams)
-    return alpha
+    return (alpha, all_flags) if return_flags else alpha
 
 
 def _trimap_tail(masks, agent, fuzzy=None, flags=None, out=None, work_size=None):

@@ -127,8 +127,11 @@ class ColorFilteringAgent():
     def bg_color_bgr(self):
         """the constant background colour of forward()'s bg_img as a (3,) uint8 BGR array"""
         self.tables_dev()
-        px = torch.from_numpy(np.tile(self._bg_hsv, (1, 4, 1))).cuda()
-        return ops.hsv2bgr(px)[0, 0].cpu().numpy()
+        key = bytes(np.asarray(self._bg_hsv, np.uint8))
+        if getattr(self, "_bg_bgr_key", None) != key:     # one conversion per fit, not per frame
+            px = torch.from_numpy(np.tile(self._bg_hsv, (1, 4, 1))).cuda()
+            self._bg_bgr, self._bg_bgr_key = ops.hsv2bgr(px)[0, 0].cpu().numpy(), key
+        return self._bg_bgr.copy()
 
     def _sample(self, channel, mask):
         samples = channel[mask].astype(float)
@@ -231,6 +234,22 @@ class ColorFilteringAgent():
         """agent.py:285-354 -> (alpha HxW, bg_img HxWx3, confidence)."""
         img_t, as_np = to_dev(img)
         mask_t, _ = to_dev(mask)
+        if iters == 0:
+            # predict only (the per-frame call of green.py:99 between refits): the batched path with the early-outs decided
+            # on the device - no host round trip before the kernels, one read-back (flag + matte) after them
+            from ... import clip
+            alpha_d, flags = clip.cf_predict_clip(img_t[None], mask_t[None], self, chunk=1, streams=1, return_flags=True)
+            flag = int(flags.cpu()[0])
+            if flag == 1:
+                return mask, img, 1.0
+            if flag == 2:
+                return mask, (np.zeros_like(img) if as_np else torch.zeros_like(img_t)), 1.0
+            col = self.bg_color_bgr()
+            if as_np:
+                bg_img = np.empty(tuple(img_t.shape), np.uint8)
+                bg_img[:] = col
+                return alpha_d[0].cpu().numpy(), bg_img, None
+            return alpha_d[0], torch.from_numpy(col).to(img_t.device).expand(tuple(img_t.shape)).contiguous(), None
         no_fg, no_bg = self._degenerate(mask_t)
         if no_fg:
             return mask, img, 1.0

@@ -42,6 +42,11 @@ class TrimapAgent():
             bg = bgimg.cpu().numpy() if isinstance(bgimg, torch.Tensor) else np.asarray(bgimg)
         else:
             bg, _ = to_dev(bgimg)
+        if m.ndim == 2 and f.ndim == 3 and m.numel() % 4 == 0:
+            # the batched path: the ratio test of :92-96 is decided on the device (no host round trip between the kernels); an
+            # empty mask comes back as it went in (all zeros)
+            from ... import clip
+            return back(clip.trimap_clip(m[None], self, f[None], bg, chunk=1, streams=1)[0], as_np)
         bgmask = _inrange_dev(f, bg, self.color_winsize)
         fuzzy_n, pos_n = (int(v) for v in ops.count_and(m, bgmask)[0].tolist())
         if pos_n == 0:
