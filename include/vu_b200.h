@@ -318,6 +318,17 @@ int vu_masked_temporal_mean(const uint8_t* frames, const uint8_t* masks, int n, 
 int vu_masked_temporal_mean_dilate32(const uint8_t* frames, const uint8_t* masks, int n, int h, int w, int min_count,
                                      uint8_t* bg_out, uint8_t* mask_always_out, vu_stream_t stream);
 
+/* One pass per frame of the bg_step live loop, tools/unscreen/bg_offline.py:154-160 + :171-172 (== bg.py:85-92, :99-100):
+ * alpha = mask * (dilate_mask(g, 4, 2) // 255) with g = thresholded BGR2GRAY(|frame - bg|) (the difference gate of
+ * vu_bgdiff_gate), fg = get_fg(frame, alpha, bgimg) with bgimg[alpha == 0] = frame[alpha == 0] (vu_get_fg with
+ * VU_PATCH_ALPHA_EQ0), and - mask_bits != NULL, scale = 2 or 4 - the bits alpha[scale*y][scale*x] >= 128 that
+ * vu_trimap_bits_packed turns into the trimap of :166.  frames [n][h][w][3], bg [bg_frames][h][w][3] (1 or n), masks /
+ * alpha [n][h][w], fg [n][h][w][3], mask_bits [n][h/scale][w/scale/8].  The frame and the background are fetched
+ * once, as TMA tiles with halo.  w % 16 == 0 and 16-byte aligned buffers, else VU_ERR_UNSUPPORTED (use the two
+ * separate entry points). */
+int vu_bgstep_frames(const uint8_t* frames, const uint8_t* bg, const uint8_t* masks, int n, int h, int w, int bg_frames,
+                     int thr, uint8_t* alpha, uint8_t* fg, uint8_t* mask_bits, int scale, vu_stream_t stream);
+
 /* ---- BackgroundAgent (unscreen/bgmodel/agent.py), methods 'mean' and 'pcov' ---- */
 /* get_fgbox (utils/maskprocess.py:37-53): out4 = {min row, max row, min column, max column} of mask > 0
  * ({INT_MAX, -1, INT_MAX, -1} for an empty mask) */

@@ -283,3 +283,32 @@ def test_green_clip_with_object_removal(env):
         patched = R.patch_bg(np.broadcast_to(col, frames[i].shape), frames[i], a_o, "lt128")
         assert np.array_equal(bgo[i], patched) and np.array_equal(fg[i], R.get_fg(frames[i], a_o, patched)), i
     assert removed > 0
+
+
+@pytest.mark.parametrize("h,w,L,thr", [(96, 160, 80, 25), (384, 640, 160, 10), (100, 240, 60, 254), (64, 48, 32, 25), (150, 464, 116, 25)])
+def test_bgstep_frames_fused_equals_staged(env, h, w, L, thr):
+    """vu_bgstep_frames (TMA tiles with halo: gate + get_fg + trimap bits in one pass) against the separate kernels and the
+    oracle: tile seams at 224 columns / 48 rows, image borders, thresholds, per-frame and shared backgrounds, working
+    resolutions that are 2x, 4x and no exact fraction of the frame"""
+    n = 5
+    frames, masks, _ = synth.bgstep_clip(n, h, w, seed=h + w)
+    rng = np.random.default_rng(7)
+    masks[1] = rng.integers(0, 256, (h, w), dtype=np.uint8)          # grey-valued mask, differences everywhere
+    frames[2, :3] = 255 - frames[2, :3]                               # differences on the image's top rows
+    frames[3, :, -2:] = 0
+    f_d, m_d = dev(frames), dev(masks)
+    ta = env.TA(input_long_side=L)
+    got = env.clip.bgstep_clip(f_d, m_d, ta, thr=thr, chunk=2, fused=True)
+    want = env.clip.bgstep_clip(f_d, m_d, ta, thr=thr, chunk=2, fused=False)
+    for g, wv, name in zip(got, want, ("bg", "alpha", "trimap", "fg")):
+        assert torch.equal(g, wv), name
+    bg_o = R.temporal_median(frames)
+    for i in range(n):
+        a_o = R.bgdiff_gate(frames[i], bg_o, masks[i], thr)
+        assert np.array_equal(got[1][i].cpu().numpy(), a_o), i
+        assert np.array_equal(got[3][i].cpu().numpy(), R.get_fg(frames[i], a_o, R.patch_bg(bg_o, frames[i], a_o, "eq0"))), i
+    # a background per frame
+    bgs = dev(np.stack([np.roll(bg_o, k, axis=1) for k in range(n)]))
+    a1, f1, _ = env.ops.bgstep_frames(f_d, bgs, m_d, thr)
+    a0 = env.ops.bgdiff_gate(f_d, bgs, m_d, thr)
+    assert torch.equal(a1, a0) and torch.equal(f1, env.ops.get_fg(f_d, a0, bgs, 2))

@@ -87,6 +87,7 @@ SIGNATURES = {
     "vu_bgdiff_gray": (_i, [_p, _p, _i64, _i64, _i, _p, _p]),
     "vu_gate": (_i, [_p, _p, _i64, _p, _p]),
     "vu_bgdiff_gate": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "vu_bgstep_frames": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "vu_binarise": (_i, [_p, _i64, _i, _p, _p]),
     "vu_sub_wrap_u8": (_i, [_p, _p, _i64, _p, _p]),
     "vu_temporal_median_u8": (_i, [_p, _i, _i64, _p, _p]),

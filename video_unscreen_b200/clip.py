@@ -357,7 +357,7 @@ def replace_clip(fg, alpha, bg, dx=None, dy=None, scale=None, out=None):
     return ops.blend(_lib.BLEND_REPLACE, fg, alpha, bg, out=out)
 
 
-def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_size=None, out=None):
+def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_size=None, out=None, fused=True):
     """bg_step: exact temporal-median background, then per frame the difference
     gate (bg_offline.py:154-160), mask-only trimap (:166) and get_fg with the
     alpha==0 patch (:171-172), CNN stage skipped (alpha := gated mask).
@@ -373,8 +373,19 @@ def bgstep_clip(frames, masks, trimap_agent, thr=25, chunk=24, streams=2, work_s
         alpha = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
         tri = torch.empty((n, h, w), dtype=torch.uint8, device=dev)
         fg = torch.empty_like(frames)
+    th, tw = work_size if work_size is not None else get_target_size(h, w, trimap_agent.input_long_side)
+    scale = 2 if (h == 2 * th and w == 2 * tw) else (4 if (h == 4 * th and w == 4 * tw) else 0)
+    bits_ok = scale != 0 and tw % 16 == 0 and trimap_agent.kernelsize == 3 and 0 <= trimap_agent.iters <= 12
     def body(s, e):
         # every stage writes straight into its slice of the clip-sized results
+        if fused and ops.bgstep_frames_supported(frames[s:e], bg, masks[s:e]) and alpha[s:e].data_ptr() % 16 == 0 and tri[s:e].data_ptr() % 16 == 0:
+            # one pass over TMA tiles: gate, matte, get_fg and the trimap's source bits; the trimap from the bits
+            a, _, mb = ops.bgstep_frames(frames[s:e], bg, masks[s:e], thr, scale if bits_ok else 0, out_alpha=alpha[s:e], out_fg=fg[s:e])
+            if bits_ok:
+                ops.trimap_bits_packed(mb, None, None, h, w, th, tw, trimap_agent.iters, out=tri[s:e])
+            else:
+                trimap_clip(a, trimap_agent, chunk=chunk, out=tri[s:e], work_size=work_size)
+            return
         if ops.bgdiff_gate_supported(frames[s:e], bg, masks[s:e]):
             a = ops.bgdiff_gate(frames[s:e], bg, masks[s:e], thr, out=alpha[s:e])
         else:

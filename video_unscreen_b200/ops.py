@@ -443,6 +443,24 @@ def bgdiff_gate(frames, bg, masks, thr, out=None):
     return out
 
 
+def bgstep_frames_supported(frames, bg, masks):
+    return frames.shape[-2] % 16 == 0 and all(t.data_ptr() % 16 == 0 for t in (frames, bg, masks))
+
+
+def bgstep_frames(frames, bg, masks, thr, scale=0, out_alpha=None, out_fg=None):
+    """difference gate + get_fg(patch alpha == 0) (+ the trimap's source bits for an exact ``scale`` = 2 / 4) in one pass over
+    TMA tiles (vu_bgstep_frames; bg_offline.py:154-160, :171-172).  -> alpha, fg, mask_bits (None when scale == 0)."""
+    frames, bg, masks = _img(frames), _img(bg), _dev(masks)
+    h, w = frames.shape[-3], frames.shape[-2]
+    n = frames.numel() // (h * w * 3)
+    nb = bg.numel() // (h * w * 3)
+    alpha = _out(out_alpha, masks.shape, masks.device)
+    fg = _out(out_fg, frames.shape, frames.device)
+    mb = torch.empty((n, h // scale, w // scale // 8), dtype=u8, device=frames.device) if scale else None
+    check(lib().vu_bgstep_frames(_p(frames), _p(bg), _p(masks), n, h, w, nb, int(thr), _p(alpha), _p(fg), _p(mb), int(scale), _stream()))
+    return alpha, fg, mb
+
+
 def sub_wrap(a, b):
     a, b = _dev(a), _dev(b)
     out = torch.empty_like(a)
