@@ -7,13 +7,13 @@
 //     B     = nearest-down(alpha) >= 128                                          what the trimap of :166 needs (bits)
 //
 // vu_bgdiff_gate + vu_get_fg read the frame twice (and the gate's 4-byte loads are bound by instruction issue, not by
-// HBM).  Here a CTA owns a 224 x 48 output tile: the TMA unit fetches the tile plus its halo (4 rows above, 2 below for the
+// HBM).  Here a CTA owns a 224 x 32 output tile: the TMA unit fetches the tile plus its halo (4 rows above, 2 below for the
 // two 4x4-ellipse dilations; 16 columns either side: the unit wants 16-byte aligned box rows, and 16 pixels are 48
-// bytes) of the frame AND of the background into shared memory as two boxes of 54 rows x 768 bytes - coordinates
+// bytes) of the frame AND of the background into shared memory as two boxes of 38 rows x 768 bytes - coordinates
 // outside the image are zero-filled by the unit, which is exactly "no difference" for the gate - and everything else
 // happens on chip: the binary difference map (VABSDIFF4 + two IDP.4A per pixel, REDUX.OR to 32-pixel words), both
 // dilations on the words, the gated matte, and get_fg for the pixels the gate let through, with the frame and
-// background pixels taken from the staged tile.  Per frame: frame 3P (x 1.29 for the halo) + mask P in, alpha P +
+// background pixels taken from the staged tile.  Per frame: frame 3P (x 1.36 for the halo) + mask P in, alpha P +
 // fg 3P out; the background stays in L2.
 #include "vu_common.cuh"
 #include "vu_tma.cuh"
@@ -22,7 +22,7 @@ namespace vu {
 namespace {
 
 constexpr int BS_THREADS = 256;
-constexpr int BS_TW = 224, BS_TH = 48;          // output tile
+constexpr int BS_TW = 224, BS_TH = 32;          // output tile: 67 KB of shared memory per CTA, three CTAs per SM
 constexpr int BS_SW = 256;                      // staged pixels per row: 16 + 224 + 16
 constexpr int BS_ROWS = BS_TH + 6;              // staged rows: 4 above, 2 below
 constexpr int BS_ROWB = BS_SW * 3;              // bytes per staged row
@@ -62,6 +62,19 @@ __global__ void __launch_bounds__(BS_THREADS) bgstep_frame_kernel(const __grid_c
     const int c0 = ((X0 - 16) * 3) / 4;
     tma::load_3d((unsigned)__cvta_generic_to_shared(ft), &fmap, c0, Y0 - 4, n, mbar);
     tma::load_3d((unsigned)__cvta_generic_to_shared(bt), &bmap, c0, Y0 - 4, bg_per_frame ? n : 0, mbar);
+  }
+  // the masks of this thread's output items: requested now, needed after the dilations
+  constexpr int GPR = BS_TW / 16;                                          // 14 items of 16 pixels per tile row
+  constexpr int ITEMS = BS_TH * GPR, IPT = (ITEMS + BS_THREADS - 1) / BS_THREADS;
+  const int64_t fpix = (int64_t)n * h * w;
+  const uint8_t* mk = masks + fpix;
+  uint4 mreg[IPT];
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const int i = threadIdx.x + k * BS_THREADS;
+    const int ty = i / GPR, tg = i - ty * GPR;
+    const int gy = Y0 + ty, gx = X0 + 16 * tg;
+    mreg[k] = (i < ITEMS && gy < h && gx < w) ? ldg_stream16(mk + (int64_t)gy * w + gx) : make_uint4(0u, 0u, 0u, 0u);
   }
   hsv_tab_init(tab);
   for (int a = threadIdx.x; a < 256; a += BS_THREADS) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
@@ -123,21 +136,19 @@ __global__ void __launch_bounds__(BS_THREADS) bgstep_frame_kernel(const __grid_c
   // ---- output: 16 pixels per item.  alpha = mask where the dilated bit is set; fg = get_fg(frame, alpha, bg patched where
   //      alpha == 0): black where the gate closed (the patched background is the pixel itself), the HSV arithmetic of
   //      utils/fgfuncs.py:84-110 elsewhere, frame and background pixels from the staged tiles ----
-  const int64_t fpix = (int64_t)n * h * w;
-  const uint8_t* mk = masks + fpix;
   uint8_t* ao = alpha_out + fpix;
   uint8_t* fo = fg_out + fpix * 3;
-  constexpr int GPR = BS_TW / 16;   // 14 items per tile row
-  for (int i = threadIdx.x; i < ((BS_TH * GPR + 31) & ~31); i += BS_THREADS) {   // whole warps: the shuffle below
+#pragma unroll
+  for (int kk = 0; kk < IPT; ++kk) {   // every thread runs every round: the shuffle below wants whole warps
+    const int i = threadIdx.x + kk * BS_THREADS;
     const int ty = i / GPR, tg = i - ty * GPR;
     const int gy = Y0 + ty, gx = X0 + 16 * tg;
-    const bool act = i < BS_TH * GPR && gy < h && gx < w;
+    const bool act = i < ITEMS && gy < h && gx < w;
     unsigned aw[4] = {0u, 0u, 0u, 0u};
     if (act) {
       const int sx = 16 + 16 * tg;   // staged pixel index of gx: bits sx .. sx+15 = one half of a word
       const unsigned bits = (D[ty + 4][sx >> 5] >> (sx & 31)) & 0xFFFFu;
-      const uint4 m = ldg_stream16(mk + (int64_t)gy * w + gx);
-      const unsigned mw[4] = {m.x, m.y, m.z, m.w};
+      const unsigned mw[4] = {mreg[kk].x, mreg[kk].y, mreg[kk].z, mreg[kk].w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const unsigned nb = (bits >> (4 * k)) & 15u;

@@ -195,21 +195,26 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
   const int tpr = w / (4 * NG);   // threads per row
   const int64_t psz = (int64_t)nframes * th * wpr;   // words per plane
   constexpr int CPG = 4 / SC;                        // working-resolution columns per group: 1 (4x) or 2 (2x)
-  // a warp = 8 thread-groups x 4 rows (a compact footprint: the flat test below diverges per warp, and a warp that
-  // covers 4 * NG * 8 columns of 4 rows straddles the unknown band far less often than one that covers 32 groups of one
-  // row); warp tiles in a grid-stride loop, one 32-bit division per tile
+  // a thread owns 4 * NG columns of the SC output rows of ONE working-resolution row: the eight plane words (and the index
+  // arithmetic - the kernel is bound by instruction issue) are fetched once for SC stores; a warp = 8 such column groups x 4
+  // working rows: a compact footprint, because the flat test below diverges per warp and a compact warp straddles the
+  // unknown band far less often than 32 groups of one row.  Warp tiles in a grid-stride loop, one 32-bit division each.
   const int lane = threadIdx.x & 31;
-  const int tiles_x = (tpr + 7) >> 3, tiles = tiles_x * ((h + 3) >> 2);
+  const int tiles_x = (tpr + 7) >> 3, tiles = tiles_x * ((th + 3) >> 2);
   for (int tile = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * (TB_THREADS / 32)) {
     const int tyy = tile / tiles_x, txx = tile - tyy * tiles_x;
-    const int y = tyy * 4 + (lane >> 3), t = txx * 8 + (lane & 7);
-    if (y >= h || t >= tpr) continue;
-    const int r = y / SC, below = (y % SC) >= SC / 2;
+    const int r = tyy * 4 + (lane >> 3), t = txx * 8 + (lane & 7);
+    if (r >= th || t >= tpr) continue;
     const unsigned* row = planes + ((int64_t)n * th + r) * wpr;
     const int c0 = t * NG * CPG;                     // first working-resolution column of the thread: NG * CPG <= 8 bits, one word
     const int j = c0 >> 5, b = c0 & 31;
-    const unsigned zl = __ldg(row + (0 + below) * psz + j) >> b, zr = __ldg(row + (2 + below) * psz + j) >> b;
-    const unsigned fl = __ldg(row + (4 + below) * psz + j) >> b, fr = __ldg(row + (6 + below) * psz + j) >> b;
+    unsigned pw[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) pw[q] = __ldg(row + q * psz + j) >> b;
+#pragma unroll
+    for (int yi = 0; yi < SC; ++yi) {
+    const int y = SC * r + yi, below = yi >= SC / 2;
+    const unsigned zl = pw[0 + below], zr = pw[2 + below], fl = pw[4 + below], fr = pw[6 + below];
     const int64_t o = ((int64_t)n * h + y) * w + (int64_t)t * 4 * NG;
     unsigned fz[NG];
     if (ens && PACKED) {
@@ -270,6 +275,7 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
     }
     if (NG == 4) stg_stream16(out + o, make_uint4(words[0], words[1 % NG], words[2 % NG], words[3 % NG]));
     else *reinterpret_cast<unsigned*>(out + o) = words[0];
+    }
   }
 }
 

@@ -234,7 +234,7 @@ class ColorFilteringAgent():
         """agent.py:285-354 -> (alpha HxW, bg_img HxWx3, confidence)."""
         img_t, as_np = to_dev(img)
         mask_t, _ = to_dev(mask)
-        if iters == 0:
+        if iters == 0 and (self._luts_dev is not None or self._is_trained):
             # predict only (the per-frame call of green.py:99 between refits): the batched path with the early-outs decided
             # on the device - no host round trip before the kernels, one read-back (flag + matte) after them
             from ... import clip
@@ -246,9 +246,12 @@ class ColorFilteringAgent():
                 return mask, (np.zeros_like(img) if as_np else torch.zeros_like(img_t)), 1.0
             col = self.bg_color_bgr()
             if as_np:
-                bg_img = np.empty(tuple(img_t.shape), np.uint8)
-                bg_img[:] = col
-                return alpha_d[0].cpu().numpy(), bg_img, None
+                # a fresh constant image per call (callers write into it, green.py:125): a copy of a cached one (a numpy
+                # broadcast fill of 3-byte pixels takes longer than all the kernels together)
+                key = (tuple(img_t.shape), bytes(col))
+                if getattr(self, "_bg_img_key", None) != key:
+                    self._bg_img, self._bg_img_key = np.ascontiguousarray(np.broadcast_to(col, tuple(img_t.shape))), key
+                return alpha_d[0].cpu().numpy(), self._bg_img.copy(), None
             return alpha_d[0], torch.from_numpy(col).to(img_t.device).expand(tuple(img_t.shape)).contiguous(), None
         no_fg, no_bg = self._degenerate(mask_t)
         if no_fg:
