@@ -116,22 +116,18 @@ __global__ void __launch_bounds__(BS_THREADS) bgstep_frame_kernel(const __grid_c
     return m_hi & ~((1u << lo) - 1u);
   };
   // MORPH_ELLIPSE(4,4) = rows 0010 / 1111 / 1111 / 1111, anchor (2,2): dst(y,x) = src(y-2,x) | OR_{dy -1..1, dx -2..1} src(y+dy,x+dx)
-  for (int it = 0; it < 2; ++it) {
-    for (int i = threadIdx.x; i < BS_ROWS * BS_WORDS; i += BS_THREADS) H[i >> 3][i & 7] = hor_or8(B[i >> 3], i & 7);
-    __syncthreads();
+  for (int it = 0; it < 2; ++it) {   // B -> H -> D: one sweep per iteration (the horizontal ORs of the three rows recomputed per cell)
+    const unsigned(*src)[BS_WORDS] = it == 0 ? B : H;
+    unsigned(*dst)[BS_WORDS] = it == 0 ? H : D;
     for (int i = threadIdx.x; i < BS_ROWS * BS_WORDS; i += BS_THREADS) {
       const int r = i >> 3, j = i & 7;
-      unsigned v = H[r][j];
-      if (r >= 1) v |= H[r - 1][j];
-      if (r + 1 < BS_ROWS) v |= H[r + 1][j];
-      if (r >= 2) v |= B[r - 2][j];
-      D[r][j] = v & inside(r, j);
+      unsigned v = hor_or8(src[r], j);
+      if (r >= 1) v |= hor_or8(src[r - 1], j);
+      if (r + 1 < BS_ROWS) v |= hor_or8(src[r + 1], j);
+      if (r >= 2) v |= src[r - 2][j];
+      dst[r][j] = v & inside(r, j);
     }
     __syncthreads();
-    if (it == 0) {
-      for (int i = threadIdx.x; i < BS_ROWS * BS_WORDS; i += BS_THREADS) B[i >> 3][i & 7] = D[i >> 3][i & 7];
-      __syncthreads();
-    }
   }
   // ---- output: 16 pixels per item.  alpha = mask where the dilated bit is set; fg = get_fg(frame, alpha, bg patched where
   //      alpha == 0): black where the gate closed (the patched background is the pixel itself), the HSV arithmetic of
