@@ -21,7 +21,7 @@
 namespace vu {
 namespace {
 
-constexpr int BS_THREADS = 256;
+constexpr int BS_THREADS = 512;   // three CTAs per SM by shared memory: 48 warps in flight
 constexpr int BS_TW = 224, BS_TH = 32;          // output tile: 67 KB of shared memory per CTA, three CTAs per SM
 constexpr int BS_SW = 256;                      // staged pixels per row: 16 + 224 + 16
 constexpr int BS_ROWS = BS_TH + 6;              // staged rows: 4 above, 2 below

@@ -53,7 +53,7 @@ __device__ __forceinline__ void block_add2(unsigned a, unsigned b, unsigned long
 }
 
 template <int SC, bool FG>
-__global__ void __launch_bounds__(UT) alpha_up_fuzzy_kernel(const uint8_t* __restrict__ alpha_lo, int th, int tw, const uint8_t* __restrict__ alt_src,
+__global__ void __launch_bounds__(UT, FG ? 4 : 5) alpha_up_fuzzy_kernel(const uint8_t* __restrict__ alpha_lo, int th, int tw, const uint8_t* __restrict__ alt_src,
                                                             const uint8_t* __restrict__ alt_flags, const uint8_t* __restrict__ frames, int lo0, int lo1,
                                                             int lo2, int hi0, int hi1, int hi2, uint8_t* __restrict__ alpha,
                                                             uint8_t* __restrict__ fzbits, uint8_t* __restrict__ mbits,
