@@ -779,3 +779,16 @@ def test_compositing_odd_sizes_and_views(vu, h, w):
             vu.ops.get_fg(dev(fr), dev(al), dev(bg[: h - 1]))
         with pytest.raises(ValueError):
             vu.ops.blend(3, dev(fr), dev(al), dev(bg[:, : w - 1].copy()) if w > 1 else dev(bg[: h - 1]))
+
+
+@pytest.mark.parametrize("k,n", [(9, 2), (11, 1), (15, 1), (7, 45), (5, 70), (4, 80)])
+def test_morphology_large(vu, k, n):
+    """structuring elements above 7x7 and iteration counts whose halo does not fit one launch's shared memory
+    (several launches through a scratch image) instead of VU_ERR_UNSUPPORTED"""
+    rng = np.random.default_rng(k * 100 + n)
+    m = rng.integers(0, 256, (2, 150, 170), dtype=np.uint8)
+    m[0, 40:110, 50:120] = 0
+    m[1, 10:60, 10:90] = 255
+    for op, ref in ((vu.ops.dilate, M.dilate), (vu.ops.erode, M.erode)):
+        got = host(op(dev(m), k, n))
+        assert np.array_equal(got, np.stack([ref(x, k, n) for x in m])), (k, n)

@@ -1013,9 +1013,16 @@ extern "C" int vu_resize_up_u8(const uint8_t* src, int n, int sh, int sw, uint8_
       VU_RETURN_LAUNCH();
     }
   }
-  dim3 grid((dw + RU_TW - 1) / RU_TW, (dh + RU_TH - 1) / RU_TH, n);
-  if (mode == 0) resize_up_kernel<0><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
-  else resize_up_kernel<1><<<grid, FT, 0, S(stream)>>>(src, sh, sw, dst, dh, dw, fuzzy, flags, alt_src, alt_flags);
+  for (int n0 = 0; n0 < n; n0 += 65535) {   // grid.z holds at most 65535 frames
+    const int nn = n - n0 < 65535 ? n - n0 : 65535;
+    dim3 grid((dw + RU_TW - 1) / RU_TW, (dh + RU_TH - 1) / RU_TH, nn);
+    const uint8_t* s0 = src + (int64_t)n0 * sh * sw;
+    uint8_t* d0 = dst + (int64_t)n0 * dh * dw;
+    const uint8_t* fz = fuzzy ? fuzzy + (int64_t)n0 * dh * dw : nullptr;
+    const uint8_t* as = alt_src ? alt_src + (int64_t)n0 * dh * dw : nullptr;
+    if (mode == 0) resize_up_kernel<0><<<grid, FT, 0, S(stream)>>>(s0, sh, sw, d0, dh, dw, fz, flags ? flags + n0 : nullptr, as, alt_flags ? alt_flags + n0 : nullptr);
+    else resize_up_kernel<1><<<grid, FT, 0, S(stream)>>>(s0, sh, sw, d0, dh, dw, fz, flags ? flags + n0 : nullptr, as, alt_flags ? alt_flags + n0 : nullptr);
+  }
   VU_RETURN_LAUNCH();
 }
 

@@ -12,7 +12,7 @@ namespace vu {
 namespace {
 
 constexpr int TW = 64, TH = 32, THREADS = 256;
-constexpr int MAXK = 7;
+constexpr int MAXK = 15;
 
 struct SE {
   int k, anchor;
@@ -94,33 +94,66 @@ __global__ void __launch_bounds__(THREADS) morph_kernel(const uint8_t* __restric
 
 using namespace vu;
 
-extern "C" size_t vu_morph_workspace_bytes(int, int, int, int, int) { return 0; }
+namespace {
+constexpr size_t SMEM_LIMIT = 200 * 1024;
+// iterations one launch can chain: the staged tile (output tile + a halo of iterations * reach) twice in shared memory
+int iters_per_launch(int ksize, int iters) {
+  const int a = ksize / 2, b = ksize - 1 - a;
+  int k = iters;
+  while (k > 1 && 2 * (size_t)(TW + k * (a + b)) * (TH + k * (a + b)) > SMEM_LIMIT) --k;
+  return k;
+}
+template <bool DILATE>
+int launch_morph(const uint8_t* src, uint8_t* dst, int n, int h, int w, const SE& se, int iters, cudaStream_t st) {
+  const int reach_lo = se.anchor, reach_hi = se.k - 1 - se.anchor;
+  const int halo_lo = iters * reach_lo, halo_hi = iters * reach_hi;
+  const size_t smem = 2 * (size_t)(TW + halo_lo + halo_hi) * (TH + halo_lo + halo_hi);
+  if (smem > SMEM_LIMIT) return VU_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    int e = record_cuda(cudaFuncSetAttribute(morph_kernel<DILATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (e) return e;
+  }
+  for (int n0 = 0; n0 < n; n0 += 65535) {   // grid.z
+    const int nn = n - n0 < 65535 ? n - n0 : 65535;
+    dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, nn);
+    morph_kernel<DILATE><<<grid, THREADS, smem, st>>>(src + (int64_t)n0 * h * w, dst + (int64_t)n0 * h * w, h, w, se, iters, halo_lo, halo_hi);
+  }
+  note_launch();
+  return record_cuda(cudaGetLastError());
+}
+}  // namespace
+
+// bytes of scratch vu_morph_u8 needs: none while all iterations fit one launch (every combination the reference uses),
+// else one image-sized buffer for the ping-pong between launches
+extern "C" size_t vu_morph_workspace_bytes(int n, int h, int w, int ksize, int iters) {
+  if (n <= 0 || h <= 0 || w <= 0 || ksize < 1 || ksize > MAXK || iters <= 0) return 0;
+  return iters_per_launch(ksize, iters) < iters ? (size_t)n * h * w : 0;
+}
 
 extern "C" int vu_morph_u8(const uint8_t* src, uint8_t* dst, int n, int h, int w, int ksize, int iters, int op,
-                           void*, size_t, vu_stream_t stream) {
+                           void* workspace, size_t workspace_bytes, vu_stream_t stream) {
   VU_REQUIRE(src && dst && n >= 0 && h > 0 && w > 0 && iters >= 0);
   VU_REQUIRE(op == VU_DILATE || op == VU_ERODE);
   if (ksize < 1 || ksize > MAXK) return VU_ERR_UNSUPPORTED;
   if (n == 0) return VU_OK;
   const SE se = make_se(ksize);
-  const int reach_lo = se.anchor, reach_hi = ksize - 1 - se.anchor;
-  const int halo_lo = iters * reach_lo, halo_hi = iters * reach_hi;
-  const int sw = TW + halo_lo + halo_hi, sh = TH + halo_lo + halo_hi;
-  const size_t smem = 2 * (size_t)sw * sh;
-  if (smem > 200 * 1024) return VU_ERR_UNSUPPORTED;
-  dim3 grid((w + TW - 1) / TW, (h + TH - 1) / TH, n);
-  if (op == VU_DILATE) {
-    if (smem > 48 * 1024) {
-      int e = record_cuda(cudaFuncSetAttribute(morph_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (e) return e;
-    }
-    morph_kernel<true><<<grid, THREADS, smem, S(stream)>>>(src, dst, h, w, se, iters, halo_lo, halo_hi);
-  } else {
-    if (smem > 48 * 1024) {
-      int e = record_cuda(cudaFuncSetAttribute(morph_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      if (e) return e;
-    }
-    morph_kernel<false><<<grid, THREADS, smem, S(stream)>>>(src, dst, h, w, se, iters, halo_lo, halo_hi);
+  cudaStream_t st = S(stream);
+  const int per = iters > 0 ? iters_per_launch(ksize, iters) : 0;
+  if (per >= iters) return op == VU_DILATE ? launch_morph<true>(src, dst, n, h, w, se, iters, st) : launch_morph<false>(src, dst, n, h, w, se, iters, st);
+  // more iterations than one launch can stage: several launches (iterated morphology composes exactly: cells outside the
+  // image are ignored by every pass either way), ping-ponging between dst and the workspace so that the last one lands in dst
+  if (!workspace || workspace_bytes < (size_t)n * h * w) return VU_ERR_WORKSPACE;
+  uint8_t* tmp = static_cast<uint8_t*>(workspace);
+  const int launches = (iters + per - 1) / per;
+  const uint8_t* in = src;
+  int left = iters;
+  for (int l = 0; l < launches; ++l) {
+    uint8_t* out = ((launches - 1 - l) % 2 == 0) ? dst : tmp;
+    const int k = left < per ? left : per;
+    const int e = op == VU_DILATE ? launch_morph<true>(in, out, n, h, w, se, k, st) : launch_morph<false>(in, out, n, h, w, se, k, st);
+    if (e) return e;
+    in = out;
+    left -= k;
   }
-  VU_RETURN_LAUNCH();
+  return VU_OK;
 }

@@ -100,7 +100,9 @@ def morph(x, ksize, iters, op):
     n = 1 if x.ndim == 2 else x.shape[0]
     h, w = x.shape[-2:]
     out = torch.empty_like(x)
-    check(lib().vu_morph_u8(_p(x), _p(out), n, h, w, int(ksize), int(iters), op, ctypes.c_void_p(0), 0, _stream()))
+    ws_bytes = int(lib().vu_morph_workspace_bytes(n, h, w, int(ksize), int(iters)))   # 0 unless the iterations need several launches
+    ws = torch.empty(ws_bytes, dtype=u8, device=x.device) if ws_bytes else None
+    check(lib().vu_morph_u8(_p(x), _p(out), n, h, w, int(ksize), int(iters), op, _p(ws), ws_bytes, _stream()))
     return out
 
 
