@@ -456,9 +456,9 @@ __global__ void __launch_bounds__(FT, 4) cf_lowres2_wide_kernel(const uint8_t* _
         for (int k = 0; k < 2; ++k) {
           const int q = 2 * o + k;   // pixel of the 16
           const int b0 = 3 * q, b1 = 3 * q + 1, b2 = 3 * q + 2;
-          const int B = byte_fma(fw[b0 >> 2], b0 & 3), G = byte_fma(fw[b1 >> 2], b1 & 3), R = byte_fma(fw[b2 >> 2], b2 & 3);
+          const int B = byte_fma4(fw[b0 >> 2], b0 & 3), G = byte_fma4(fw[b1 >> 2], b1 & 3), R = byte_fma4(fw[b2 >> 2], b2 & 3);
           int hh, ss, vv;
-          bgr2hsv_px(B, G, R, tab, hh, ss, vv);
+          bgr2hsv_px4(B, G, R, tab, hh, ss, vv);
           acc0 += hh; acc1 += ss; acc2 += vv;
           if (k == 0) macc = (int)__dp4a(mw[q >> 2], 0x0101u << (8 * (q & 3)), (unsigned)macc);   // both columns of the pair: one word
         }
@@ -528,9 +528,9 @@ __global__ void __launch_bounds__(FT) cf_lowres4_wide_kernel(const uint8_t* __re
         for (int k = 0; k < 2; ++k) {
           const int q = 4 * o + 1 + k;
           const int b0 = 3 * q, b1 = 3 * q + 1, b2 = 3 * q + 2;
-          const int B = byte_fma(fw[b0 >> 2], b0 & 3), G = byte_fma(fw[b1 >> 2], b1 & 3), R = byte_fma(fw[b2 >> 2], b2 & 3);
+          const int B = byte_fma4(fw[b0 >> 2], b0 & 3), G = byte_fma4(fw[b1 >> 2], b1 & 3), R = byte_fma4(fw[b2 >> 2], b2 & 3);
           int hh, ss, vv;
-          bgr2hsv_px(B, G, R, tab, hh, ss, vv);
+          bgr2hsv_px4(B, G, R, tab, hh, ss, vv);
           acc0 += hh; acc1 += ss; acc2 += vv;
         }
         macc = (int)__dp4a(mw[o], 0x00010100u, (unsigned)macc);   // bytes 1 and 2 of the block's mask word
