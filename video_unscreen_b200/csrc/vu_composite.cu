@@ -279,7 +279,7 @@ __device__ __forceinline__ double u8_to_f64(unsigned x) { return __dsub_rn(__hil
 __device__ __forceinline__ int f64_trunc_nonneg(double x) { return __double2loint(__dadd_rz(x, 4503599627370496.0)); }
 
 template <int MODE, int AC>
-__global__ void __launch_bounds__(THREADS, 6) blend16_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
+__global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
                                                           int64_t ngroups, int64_t bg_groups, uint4* __restrict__ out) {
   __shared__ double mtab[256], otab[256];
   for (int a = threadIdx.x; a < 256; a += THREADS) {

@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(FT, 4) cf_lowres2_wide_kernel(const uint8_t* _
 // rounded mean of the centre 2x2 of its 4x4 block (rows 4y+1, 4y+2, columns 4x+1, 4x+2: what cv2's bilinear comes to at
 // exactly 4x).  Only the two centre rows of the frame are read; with mcounts2 all four rows of the mask
 // are, for the early-out counts of agent.py:303-307.
-__global__ void __launch_bounds__(FT) cf_lowres4_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
+__global__ void __launch_bounds__(FT, 4) cf_lowres4_wide_kernel(const uint8_t* __restrict__ frames, const uint8_t* __restrict__ masks, int h, int w, int th,
                                                              int tw, const uint8_t* __restrict__ lut3d, uint8_t* __restrict__ alpha_lo,
                                                              unsigned long long* __restrict__ stats2, unsigned long long* __restrict__ mcounts2) {
   __shared__ HsvTab tab;
