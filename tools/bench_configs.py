@@ -425,9 +425,10 @@ def run_bgstep_4k(D, steps, warmup, peak, cpu=True, e2e_steps=1, frames=None):
     if keep:
         (fr, fr_win), (mk, mk_win) = fr, mk
     res, bufs = [None], [None]
+    chunk = 24 * D.world     # a row tile is 1 / world of a frame: chunks of the same number of pixels as 24 whole frames
 
     def step():      # the result buffers (tile plus halo) of the first call are reused: no allocation in the steady state
-        res[0] = clip.bgstep_clip_tile(fr, mk, ta, D.rank, D.world, thr=25, chunk=24, rows=(a0, a1, h), out=bufs[0])
+        res[0] = clip.bgstep_clip_tile(fr, mk, ta, D.rank, D.world, thr=25, chunk=chunk, rows=(a0, a1, h), out=bufs[0])
         if bufs[0] is None:
             bufs[0] = tuple(x._base if x._base is not None else x for x in res[0][1:])
     st = max(2, steps // 4)
@@ -469,7 +470,7 @@ def run_bgstep_4k(D, steps, warmup, peak, cpu=True, e2e_steps=1, frames=None):
     def e2e_step():
         nonlocal outs_p
         f_d, m_d = fr_p.to(D.dev, non_blocking=True), mk_p.to(D.dev, non_blocking=True)
-        _, bg_e, a_e, t_e, f_e = clip.bgstep_clip_tile(f_d, m_d, ta, D.rank, D.world, thr=25, chunk=24, rows=(a0, a1, h))
+        _, bg_e, a_e, t_e, f_e = clip.bgstep_clip_tile(f_d, m_d, ta, D.rank, D.world, thr=25, chunk=chunk, rows=(a0, a1, h))
         if outs_p is None:
             outs_p = [pinned_like(torch, x) for x in (bg_e, a_e, t_e, f_e)]
         for o, x in zip(outs_p, (bg_e, a_e, t_e, f_e)):
@@ -484,7 +485,7 @@ def run_bgstep_4k(D, steps, warmup, peak, cpu=True, e2e_steps=1, frames=None):
     algo = n * 12 * rows_alg * w + 6 * rows_alg * w
     return block(name, D, n, ms, st, launches, algo, peak, "strong", "row tiles of ONE clip (shard.row_tiles + shard.bgstep_halo: 28 / 24 halo rows "
                  "read from the rank's own rows, no exchange)", cpu_b, e2e, exact,
-                 {"frames": n, "rank_ms_min_max": [ms_lo / st, ms / st], "rows_per_gpu": rows_alg, "halo_rows": [ht, hb], "chunk": 24, "streams": 2,
+                 {"frames": n, "rank_ms_min_max": [ms_lo / st, ms / st], "rows_per_gpu": rows_alg, "halo_rows": [ht, hb], "chunk": chunk, "streams": 2,
                   "note": "the named config is 2000 frames on 8 GPUs (bench.py runs it as bgstep_4k_2000 when --gpus 8); 500 frames keep the "
                           "clip plus outputs within one GPU at N = 1"})
 
