@@ -171,8 +171,10 @@ __global__ void __launch_bounds__(THREADS) get_fg16_kernel(const uint4* __restri
           bh = patch ? ih : h0[i];
           bs = patch ? is : s0[i];
           bvv = patch ? iv : v0[i];
-        } else {
+        } else if (a != 255) {
           bgr2hsv_px(q[3 * i], q[3 * i + 1], q[3 * i + 2], tab, bh, bs, bvv);
+        } else {
+          bh = bs = bvv = 0;   // k = 1 - 255/255 = 0 exactly: the background's HSV is multiplied by it
         }
         const float k = ktab[a];   // 1 - alpha/255.
         const int fh = trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
