@@ -431,7 +431,7 @@ def run_bgstep_4k(D, steps, warmup, peak, cpu=True, e2e_steps=1, frames=None):
         res[0] = clip.bgstep_clip_tile(fr, mk, ta, D.rank, D.world, thr=25, chunk=chunk, rows=(a0, a1, h), out=bufs[0])
         if bufs[0] is None:
             bufs[0] = tuple(x._base if x._base is not None else x for x in res[0][1:])
-    st = max(2, steps // 4)
+    st = max(4, steps // 2)
     ms, ms_lo, launches = timed(D, step, st, 2)
     (_, _), bg_t, a_t, t_t, f_t = res[0]
     exact, cpu_b = True, None

@@ -40,7 +40,7 @@ __device__ __forceinline__ unsigned hor_or8(const unsigned* row, int j) {
 
 // SC: 0 = no trimap bits, 2 / 4 = frame size / working size (mbits [n][h/SC][w/SC/8])
 template <int SC>
-__global__ void __launch_bounds__(BS_THREADS) bgstep_frame_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap bmap,
+__global__ void __launch_bounds__(BS_THREADS, 3) bgstep_frame_kernel(const __grid_constant__ CUtensorMap fmap, const __grid_constant__ CUtensorMap bmap,
                                                                   int bg_per_frame, const uint8_t* __restrict__ masks, int h, int w, int thr,
                                                                   uint8_t* __restrict__ alpha_out, uint8_t* __restrict__ fg_out,
                                                                   uint8_t* __restrict__ mbits) {
