@@ -14,7 +14,7 @@
 // happens on chip: the binary difference map (VABSDIFF4 + two IDP.4A per pixel, REDUX.OR to 32-pixel words), both
 // dilations on the words, the gated matte, and get_fg for the pixels the gate let through, with the frame and
 // background pixels taken from the staged tile.  Per frame: frame 3P (x 1.36 for the halo) + mask P in, alpha P +
-// fg 3P out; the background stays in L2.
+// fg 3P out; the background stays in L2.  Tiles whose masks are all zero skip everything but the stores.
 #include "vu_common.cuh"
 #include "vu_tma.cuh"
 
@@ -54,6 +54,44 @@ __global__ void __launch_bounds__(BS_THREADS, 3) bgstep_frame_kernel(const __gri
   const int n = blockIdx.z;
   const int X0 = blockIdx.x * BS_TW, Y0 = blockIdx.y * BS_TH;
   const unsigned mbar = (unsigned)__cvta_generic_to_shared(&bar);
+  // the masks of this thread's output items come first: alpha = mask * gate, so a tile whose masks are all zero (most of
+  // a frame: the person covers a fraction of it) has alpha = 0, fg = black and no trimap bits whatever the frame holds,
+  // and neither the frame nor the background is fetched for it
+  constexpr int GPR = BS_TW / 16;                                          // 14 items of 16 pixels per tile row
+  constexpr int ITEMS = BS_TH * GPR, IPT = (ITEMS + BS_THREADS - 1) / BS_THREADS;
+  const int64_t fpix = (int64_t)n * h * w;
+  const uint8_t* mk = masks + fpix;
+  uint4 mreg[IPT];
+  unsigned anym = 0;
+#pragma unroll
+  for (int k = 0; k < IPT; ++k) {
+    const int i = threadIdx.x + k * BS_THREADS;
+    const int ty = i / GPR, tg = i - ty * GPR;
+    const int gy = Y0 + ty, gx = X0 + 16 * tg;
+    mreg[k] = (i < ITEMS && gy < h && gx < w) ? ldg_stream16(mk + (int64_t)gy * w + gx) : make_uint4(0u, 0u, 0u, 0u);
+    anym |= mreg[k].x | mreg[k].y | mreg[k].z | mreg[k].w;
+  }
+  if (!__syncthreads_or(anym != 0u)) {
+#pragma unroll
+    for (int k = 0; k < IPT; ++k) {
+      const int i = threadIdx.x + k * BS_THREADS;
+      const int ty = i / GPR, tg = i - ty * GPR;
+      const int gy = Y0 + ty, gx = X0 + 16 * tg;
+      if (i >= ITEMS || gy >= h || gx >= w) continue;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      stg_stream16(alpha_out + fpix + (int64_t)gy * w + gx, z);
+      uint8_t* o = fg_out + (fpix + (int64_t)gy * w + gx) * 3;
+      stg_stream16(o, z); stg_stream16(o + 16, z); stg_stream16(o + 32, z);
+      if constexpr (SC != 0) {
+        const int tw8 = (w / SC) >> 3;
+        if ((gy % SC) == 0) {
+          if (SC == 2) mbits[((int64_t)n * (h / SC) + gy / SC) * tw8 + (gx >> 4)] = 0;
+          else if (!(tg & 1)) mbits[((int64_t)n * (h / SC) + gy / SC) * tw8 + (gx >> 5)] = 0;
+        }
+      }
+    }
+    return;
+  }
   if (threadIdx.x == 0) {
     tma::mbar_init(mbar, 1);
     tma::mbar_fence_init();
@@ -62,19 +100,6 @@ __global__ void __launch_bounds__(BS_THREADS, 3) bgstep_frame_kernel(const __gri
     const int c0 = ((X0 - 16) * 3) / 4;
     tma::load_3d((unsigned)__cvta_generic_to_shared(ft), &fmap, c0, Y0 - 4, n, mbar);
     tma::load_3d((unsigned)__cvta_generic_to_shared(bt), &bmap, c0, Y0 - 4, bg_per_frame ? n : 0, mbar);
-  }
-  // the masks of this thread's output items: requested now, needed after the dilations
-  constexpr int GPR = BS_TW / 16;                                          // 14 items of 16 pixels per tile row
-  constexpr int ITEMS = BS_TH * GPR, IPT = (ITEMS + BS_THREADS - 1) / BS_THREADS;
-  const int64_t fpix = (int64_t)n * h * w;
-  const uint8_t* mk = masks + fpix;
-  uint4 mreg[IPT];
-#pragma unroll
-  for (int k = 0; k < IPT; ++k) {
-    const int i = threadIdx.x + k * BS_THREADS;
-    const int ty = i / GPR, tg = i - ty * GPR;
-    const int gy = Y0 + ty, gx = X0 + 16 * tg;
-    mreg[k] = (i < ITEMS && gy < h && gx < w) ? ldg_stream16(mk + (int64_t)gy * w + gx) : make_uint4(0u, 0u, 0u, 0u);
   }
   hsv_tab_init(tab);
   for (int a = threadIdx.x; a < 256; a += BS_THREADS) ktab[a] = __fsub_rn(1.f, __fdiv_rn((float)a, 255.f));
