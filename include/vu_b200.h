@@ -359,6 +359,28 @@ int vu_remove_invalid_objects(const uint8_t* alpha, const uint8_t* segmask, cons
                               double saliency_thr, double consensus_thr, uint8_t* out, int32_t* status, void* workspace,
                               size_t workspace_bytes, int max_objects, vu_stream_t stream);
 
+/* regionfill (unscreen/utils/region_fill.py:26-63; BackgroundAgent 'rf', bgmodel/agent.py:133-157; bg.py:79): the masked
+ * pixels of x [planes][h][w] (float64, in place; the planes share mask [h][w], > 0 = fill) become the solution of the
+ * discrete Laplace equation whose boundary data are the pixels outside the mask (every masked pixel = the mean of its
+ * in-image 4-neighbours).  The reference builds the sparse matrix and calls scipy's direct solver; this is conjugate
+ * gradients in float64, stopped at |r| <= tol |b| or after max_iters iterations: parity is a tolerance (tol 1e-10: ~1e-6
+ * grey levels on a 1080p person-sized hole).  HOST-SYNCHRONOUS on `stream` (the residuals are read every 64 iterations);
+ * iters_out / resid_out (host pointers, may be NULL) receive the iterations done and the final max |r| / |b|. */
+size_t vu_regionfill_workspace_bytes(int planes, int h, int w);
+int vu_regionfill_f64(double* x, const uint8_t* mask, int planes, int h, int w, double tol, int max_iters, void* workspace,
+                      size_t workspace_bytes, int32_t* iters_out, double* resid_out, vu_stream_t stream);
+/* cv2.resize of float64 planes with the default INTER_LINEAR (region_fill.py:10-15): scale_x / scale_y are the sampling
+ * steps (1 / fx for the `(0, 0), fx=` form, else src / dst size); exactly 2 in both axes = cv2's INTER_AREA shortcut.
+ * keep_mask [dh][dw] / keep_src [planes][dh][dw] (both or neither): where keep_mask == 0 the output is keep_src
+ * (region_fill.py:16). */
+int vu_resize_linear_f64(const double* src, int planes, int sh, int sw, double* dst, int dh, int dw, double scale_x, double scale_y,
+                         const uint8_t* keep_mask, const double* keep_src, vu_stream_t stream);
+
+/* ---- frame I/O glue (unscreen/utils/fileio.py:31-62): the JPEG codec itself is nvJPEG (library code); these convert
+ * between its planar RGB [3][npix] and the reference's interleaved BGR [npix][3] ---- */
+int vu_planar_rgb_to_bgr(const uint8_t* src, uint8_t* dst, int64_t npix, vu_stream_t stream);
+int vu_bgr_to_planar_rgb(const uint8_t* src, uint8_t* dst, int64_t npix, vu_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

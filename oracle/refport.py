@@ -533,9 +533,69 @@ def bg_by_pcov(img, mask, ksize=5):
     return bgimg
 
 
+def regionfill(I, mask, factor=1.0):
+    """unscreen/utils/region_fill.py:7-63: fill the masked pixels of the single-channel image I with the solution of the
+    discrete Laplace equation (every masked pixel = the mean of its in-image 4-neighbours; pixels outside the mask are
+    the boundary data), at ``factor`` x the resolution, resized back and pasted under the mask.  -> float64 [H,W].
+    The linear solve is scipy's ``spsolve``, like in the reference (scipy is the reference's dependency for this function);
+    the two cv2.resize calls on float64 data are cvmodel.resize_linear_f64."""
+    from scipy import sparse
+    from scipy.sparse.linalg import spsolve
+    I = np.asarray(I)
+    mask = np.asarray(mask)
+    if np.count_nonzero(mask) == 0:
+        return I.copy()
+    h0, w0 = I.shape
+    if factor == 1.0:
+        m, x = mask.astype(np.float64) > 0, I.astype(np.float64)
+    else:
+        dw, dh = cvm.scaled_size(w0, factor), cvm.scaled_size(h0, factor)
+        m = cvm.resize_linear_f64(mask.astype(np.float64), dw, dh, factor, factor) > 0
+        x = cvm.resize_linear_f64(I.astype(np.float64), dw, dh, factor, factor)
+    h, w = m.shape
+    ys, xs = np.nonzero(m)
+    idx = -np.ones((h + 2, w + 2), np.int64)
+    idx[ys + 1, xs + 1] = np.arange(ys.size)
+    data = np.where(m, 0.0, x)                               # boundary data: every pixel outside the mask
+    dpad = np.zeros((h + 2, w + 2))
+    dpad[1:-1, 1:-1] = data
+    nn = np.full((h, w), 4.0)
+    nn[[0, -1], :] -= 1
+    nn[:, [0, -1]] -= 1
+    rows, cols, vals = [np.arange(ys.size)], [np.arange(ys.size)], [nn[ys, xs]]
+    rhs = np.zeros(ys.size)
+    for dy, dx in ((-1, 0), (0, 1), (1, 0), (0, -1)):
+        nb = idx[ys + 1 + dy, xs + 1 + dx]
+        k = nb >= 0
+        rows.append(np.nonzero(k)[0])
+        cols.append(nb[k])
+        vals.append(-np.ones(int(k.sum())))
+        rhs += dpad[ys + 1 + dy, xs + 1 + dx]
+    D = sparse.coo_matrix((np.concatenate(vals), (np.concatenate(rows), np.concatenate(cols)))).tocsr()
+    x = x.copy()
+    x[ys, xs] = spsolve(D, rhs)
+    out = x if (h, w) == (h0, w0) else cvm.resize_linear_f64(x, w0, h0)
+    out = out.copy()
+    keep = mask == 0
+    out[keep] = I[keep]
+    return out
+
+
+def bg_by_regionfill(img_hsv, mask, boundary_ksize=7, boundary_iters=10):
+    """BackgroundAgent.get_bg_by_regionfill, unscreen/bgmodel/agent.py:133-157: V from regionfill at half resolution,
+    H and S from the boundary's mean colour."""
+    col = bg_mean_hsv(img_hsv, mask, boundary_ksize, boundary_iters)
+    out = img_hsv.copy()
+    v = regionfill(img_hsv[:, :, 2], mask > 0, 0.5).astype(np.uint8)
+    fgm = mask > 0
+    out[fgm] = col
+    out[:, :, 2][fgm] = v[fgm]
+    return out
+
+
 def background_forward(img, mask, method="rf", input_long_side=540, dilation_ksize=5, dilation_iters=3, boundary_ksize=7,
                        boundary_iters=10, pcov_ksize=5):
-    """BackgroundAgent.forward, unscreen/bgmodel/agent.py:159-208, methods 'mean' and 'pcov'."""
+    """BackgroundAgent.forward, unscreen/bgmodel/agent.py:159-208."""
     oh, ow = mask.shape
     if (mask == 0).sum() == 0:
         return np.zeros(img.shape)                         # float64 zeros, as the reference returns them (:178)
@@ -552,6 +612,8 @@ def background_forward(img, mask, method="rf", input_long_side=540, dilation_ksi
         bgimg = fuse_fgbg(cvm.hsv2bgr(bg_hsv), img, dil)
     elif method == "pcov":
         bgimg = fuse_fgbg(bg_by_pcov(img, dil, pcov_ksize), img, dil)
+    elif method == "rf":
+        bgimg = cvm.hsv2bgr(bg_by_regionfill(cvm.bgr2hsv(img), dil, boundary_ksize, boundary_iters))
     else:
         raise NameError(f"No such method for background inpainting: {method}")
     return cvm.resize_linear(bgimg, ow, oh)

@@ -298,6 +298,22 @@ def bgmodel(BA):
     np.savez_compressed(os.path.join(HERE, "bgmodel.npz"), **out)
 
 
+def regionfill(U, BA):
+    """regionfill (utils/region_fill.py) at both factors its callers use, and BackgroundAgent.forward(method='rf')
+    (SURVEY.md 8f rank 4).  `python make_golden.py regionfill`.  The comparison of the device results with
+    these is a tolerance (tests/test_gpu_parity.py)."""
+    out = {}
+    cases = [(108, 192, 96, 0), (150, 100, 75, 1), (135, 240, 270, 2), (200, 130, 90, 1), (121, 187, 187, 0)]
+    out["cases"] = np.array(cases)
+    for i, (h, w, L, kind) in enumerate(cases):
+        img, m = bgmodel_case(h, w, 300 + i, kind)
+        out[f"img_{i}"], out[f"mask_{i}"] = img, m
+        for f in (1.0, 0.5):
+            out[f"fill_{i}_{int(f * 10)}"] = U.regionfill(img[:, :, i % 3].copy(), m > 0, f)
+        out[f"rf_{i}"] = BA(input_long_side=L).forward(img.copy(), m.copy(), "rf")
+    np.savez_compressed(os.path.join(HERE, "regionfill.npz"), **out)
+
+
 OBJ_CFGS = [{'objectremoval': {'score_map_center': {'landscape': [0.5, 0.5], 'portrait': [0.6, 0.5]}, 'saliency_thr': t, 'consensus_thr': 0.5}}
             for t in (0.005, 0.00001, 0.001)]      # configs/green.json, configs/bg.json, the function's default
 
@@ -356,6 +372,10 @@ if __name__ == "__main__":
         write_manifest()
     elif sys.argv[1:] == ["objects"]:
         objects(load_reference()[0])
+        write_manifest()
+    elif sys.argv[1:] == ["regionfill"]:
+        ref = load_reference()
+        regionfill(ref[0], ref[3])
         write_manifest()
     elif sys.argv[1:] == ["bgmodel"]:
         bgmodel(load_reference()[3])

@@ -684,13 +684,47 @@ def test_background_agent_golden(vu, golden, i):
     assert z.dtype == np.float64 and z.shape == img.shape and not z.any()
     with pytest.raises(NameError):
         ag.forward(img, m, "telea")
-    with pytest.raises(NotImplementedError):
-        ag.forward(img, m, "rf")
     t = ag.forward(dev(img), dev(m), "pcov")
     assert t.is_cuda and np.array_equal(host(t), g[f"pcov_{i}"])
     ag3 = BackgroundAgent(input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3)
     assert np.array_equal(ag3.forward(img, m, "pcov"),
                           R.background_forward(img, m, "pcov", input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3))
+
+
+@pytest.mark.parametrize("i", range(5))
+def test_regionfill_golden(vu, golden, i):
+    """regionfill (utils/region_fill.py) and BackgroundAgent.forward(method='rf').  The reference solves
+    the Laplace system directly (scipy spsolve), the device by conjugate gradients to a relative residual of 1e-10: the
+    tolerance is |difference| <= 1e-5 grey levels on the float result; after the reference's truncation to uint8 that is
+    <= 1 LSB on at most 1e-4 of the pixels (values that sit on an integer).  'rf' then ends in HSV2BGR: <= 2 LSB after the
+    final resize against the reference (the scalar tail of cv2's HSV2BGR, as for 'mean'), near-exact against the oracle."""
+    from video_unscreen_b200.unscreen.bgmodel import BackgroundAgent
+    g = golden("regionfill")
+    h, w, L, kind = (int(v) for v in g["cases"][i])
+    img, m = g[f"img_{i}"], g[f"mask_{i}"]
+    plane = np.ascontiguousarray(img[:, :, i % 3])
+    for f in (1.0, 0.5):
+        want = g[f"fill_{i}_{int(f * 10)}"]
+        got = vu.U.regionfill(plane, m > 0, f)
+        assert got.dtype == np.float64 and got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-5, (f, np.abs(got - want).max())
+        flips = got.astype(np.uint8) != want.astype(np.uint8)
+        assert flips.mean() <= 1e-4 and maxdiff(got.astype(np.uint8), want.astype(np.uint8)) <= 1
+        assert np.array_equal(got[m == 0], plane[m == 0].astype(np.float64))
+    # uint8 0 / 255 mask (bg.py:79), three planes in one solve (CUDA tensors in -> CUDA tensor out), empty mask
+    planes = dev(np.ascontiguousarray(img.transpose(2, 0, 1)))
+    got3 = vu.U.regionfill(planes, dev(m), 1.0)
+    assert got3.is_cuda and got3.dtype == torch.float64
+    assert np.abs(host(got3)[i % 3] - g[f"fill_{i}_10"]).max() <= 1e-5
+    assert np.array_equal(vu.U.regionfill(plane, np.zeros_like(m)), plane)
+    # the agent
+    ag = BackgroundAgent(input_long_side=L)
+    got = ag.forward(img, m, "rf")
+    assert got.dtype == np.uint8 and got.shape == img.shape
+    assert maxdiff(got, g[f"rf_{i}"]) <= 2
+    orc = R.background_forward(img, m, "rf", input_long_side=L)
+    assert maxdiff(got, orc) <= 1 and (got != orc).mean() <= 1e-3, ((got != orc).mean(), maxdiff(got, orc))
+    assert BackgroundAgent().forward(img, m).shape == img.shape          # 'rf' is the default method (:159)
 
 
 @pytest.mark.parametrize("i", range(6))

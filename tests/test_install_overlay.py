@@ -74,16 +74,32 @@ assert ColorFilteringAgent is mine_cf.ColorFilteringAgent and TrimapAgent is min
 assert ref_mp.dilate_mask is mine.dilate_mask
 assert unscreen.utils.temporal_median is mine.temporal_median
 # ... and everything else is still the reference's
-for f in (parallel_read_img, save_img, save_video, regionfill, get_center, return_date):
+for f in (parallel_read_img, save_img, save_video, get_center, return_date):
     assert f.__module__.startswith("unscreen."), (f, f.__module__)
+assert regionfill is mine.regionfill
 assert VMattingAgent.__module__ == "unscreen.vmatting.agent" and STMAgent.__module__.startswith("unscreen.stm")
-import unscreen.bgmodel.agent as ref_bg
-assert issubclass(BackgroundAgent, ref_bg.BackgroundAgent.__mro__[1]) and BackgroundAgent._vu_b200_hybrid   # 'rf' stays the reference's
+import unscreen.bgmodel.agent as ref_bg, video_unscreen_b200.unscreen.bgmodel as mine_bg
+assert BackgroundAgent is mine_bg.BackgroundAgent and ref_bg.BackgroundAgent is BackgroundAgent
 assert BackgroundAgent(input_long_side=100).pcov_ksize == 5
 assert "unscreen.utils.fgfuncs.get_fg" in vu.installed_names()
 print("overlay ok", len(vu.installed_names()))
 """)
     assert "overlay ok" in out
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "unscreen")), reason="reference checkout not present")
+def test_overlay_io_is_opt_in():
+    out = _run((SHIM % ROOT) + f"""
+sys.path.insert(0, {REF!r})
+import video_unscreen_b200 as vu
+vu.install(io=True)
+from unscreen.utils import parallel_read_img, save_img, save_video
+import unscreen.utils.fileio as ref_io
+assert parallel_read_img.__module__ == "video_unscreen_b200.unscreen.utils.fileio" and ref_io.save_img is save_img
+assert save_video.__module__.startswith("unscreen.")          # mmcv / ffmpeg: the reference's
+print("io ok")
+""")
+    assert "io ok" in out
 
 
 def test_alias_mode_without_the_reference():

@@ -167,6 +167,22 @@ def test_background_agent_mean_pcov(golden, i):
         R.background_forward(img, m, "telea")
 
 
+@pytest.mark.parametrize("i", range(5))
+def test_regionfill(golden, i):
+    """regionfill (utils/region_fill.py:7-63) at factor 1 (bg.py:79) and 0.5 (bgmodel/agent.py:150): the same sparse
+    system handed to the same scipy solver, the float64 cv2.resize calls modelled (cvmodel.resize_linear_f64): equal to
+    1e-9.  BackgroundAgent 'rf' ends in HSV2BGR: <= 2 LSB after the final resize, as for 'mean'."""
+    g = golden("regionfill")
+    h, w, L, kind = (int(v) for v in g["cases"][i])
+    img, m = g[f"img_{i}"], g[f"mask_{i}"]
+    for f in (1.0, 0.5):
+        got = R.regionfill(img[:, :, i % 3], m > 0, f)
+        assert np.abs(got - g[f"fill_{i}_{int(f * 10)}"]).max() <= 1e-9, f
+    d = np.abs(R.background_forward(img, m, "rf", input_long_side=L).astype(int) - g[f"rf_{i}"].astype(int))
+    assert d.max() <= 2
+    assert R.regionfill(img[:, :, 0], np.zeros_like(m)).dtype == np.uint8        # :8-9: the input's copy
+
+
 @pytest.mark.parametrize("i", range(6))
 def test_remove_invalid_objects(golden, i):
     """the closed-form contour model (oracle/refport.py:contour_objects) against the reference's cv2.findContours /

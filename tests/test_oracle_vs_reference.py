@@ -144,6 +144,11 @@ def test_background_agent(h, w, L, kind):
     assert np.array_equal(R.background_forward(img, m, "pcov", input_long_side=L), ag.forward(img.copy(), m.copy(), "pcov"))
     d = np.abs(R.background_forward(img, m, "mean", input_long_side=L).astype(int) - ag.forward(img.copy(), m.copy(), "mean").astype(int))
     assert d.max() <= 2      # where: the hole pixels of the scalar-tail columns (image width mod the SIMD width)
+    d = np.abs(R.background_forward(img, m, "rf", input_long_side=L).astype(int) - ag.forward(img.copy(), m.copy(), "rf").astype(int))
+    assert d.max() <= 2      # the same HSV2BGR tail; the region fill itself agrees to 1e-9:
+    import unscreen.utils.region_fill as ref_rf
+    for f in (1.0, 0.5):
+        assert np.abs(R.regionfill(img[:, :, 1], m > 0, f) - ref_rf.regionfill(img[:, :, 1].copy(), m > 0, f)).max() <= 1e-9
     ag2 = BA(input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3)
     want = ag2.forward(img.copy(), m.copy(), "pcov")
     assert np.array_equal(R.background_forward(img, m, "pcov", input_long_side=L, dilation_ksize=3, dilation_iters=2, pcov_ksize=3), want)

@@ -483,9 +483,15 @@ def run_bgstep_4k(D, steps, warmup, peak, cpu=True, e2e_steps=1, frames=None):
                   "(the median needs every frame before the per-frame stages start: no overlap of copies and kernels)"}
     rows_alg = r1 - r0
     algo = n * 12 * rows_alg * w + 6 * rows_alg * w
+    # data-independent bound: every mask pixel set (the kernel's all-zero-mask tile shortcut never fires; the person masks
+    # above cover 17 % of the frame)
+    mk.fill_(255)
+    ms_d, _, _ = timed(D, step, st, 1)
+    dense = {"ms_per_step": ms_d / st, "value": n / (ms_d / st * 1e-3), "frac": algo / (ms_d / st * 1e-3) / 1e9 / peak,
+             "what": "the same step with every segmentation-mask pixel set: no tile takes the all-zero-mask shortcut"}
     return block(name, D, n, ms, st, launches, algo, peak, "strong", "row tiles of ONE clip (shard.row_tiles + shard.bgstep_halo: 28 / 24 halo rows "
                  "read from the rank's own rows, no exchange)", cpu_b, e2e, exact,
-                 {"frames": n, "rank_ms_min_max": [ms_lo / st, ms / st], "rows_per_gpu": rows_alg, "halo_rows": [ht, hb], "chunk": chunk, "streams": 2,
+                 {"frames": n, "rank_ms_min_max": [ms_lo / st, ms / st], "rows_per_gpu": rows_alg, "halo_rows": [ht, hb], "chunk": chunk, "streams": 2, "dense_masks": dense,
                   "note": "the named config is 2000 frames on 8 GPUs (bench.py runs it as bgstep_4k_2000 when --gpus 8); 500 frames keep the "
                           "clip plus outputs within one GPU at N = 1"})
 

@@ -12,16 +12,18 @@ import sys
 __version__ = "0.2.0"
 
 # reference module -> mirror module whose ``__all__`` is patched over it.  Only hot-path names are replaced: everything
-# else of the reference package (parallel_read_img, save_img, save_video, regionfill, get_center, return_date,
-# build_score_map, unscreen.binseg / stm / vmatting / iseg / harmonization ...) stays the reference's own.
+# else of the reference package (parallel_read_img, save_img, save_video, get_center, return_date,
+# unscreen.binseg / stm / vmatting / iseg / harmonization ...) stays the reference's own.
 _OVERLAY = {
     "utils.fgfuncs": "utils.fgfuncs",
     "utils.maskprocess": "utils.maskprocess",
     "utils.imgprocess": "utils.imgprocess",
     "utils.visualize": "utils.visualize",
+    "utils.region_fill": "utils.region_fill",
     "utils": "utils.temporal",            # no reference counterpart: the scripts' inline lines + the temporal median
     "colorfiltering.agent": "colorfiltering.agent",
     "trimap.agent": "trimap.agent",
+    "bgmodel.agent": "bgmodel.agent",
 }
 _AGENT_CLASSES = {"colorfiltering.agent": "ColorFilteringAgent", "trimap.agent": "TrimapAgent", "bgmodel.agent": "BackgroundAgent"}
 
@@ -37,20 +39,20 @@ def _reference_importable(name):
     return spec is not None
 
 
-def install(name="unscreen", overlay=None):
+def install(name="unscreen", overlay=None, io=False):
     """Put the B200 hot path behind the import name ``unscreen``.  Call before importing the reference's tools.
 
     * The reference package is importable (its checkout is on ``sys.path``) -> OVERLAY: the reference is imported as it
       is and the hot-path names of this mirror are patched over the reference's in ``unscreen.utils`` (and the
       sub-modules that define them, so the reference's internal callers pick them up too), ``unscreen.colorfiltering``
-      and ``unscreen.trimap``; ``unscreen.bgmodel.BackgroundAgent`` becomes a subclass of the reference's whose
-      'mean' and 'pcov' methods run on the device.  Everything else -- file I/O, region fill ('rf'), the CNN
-      agents -- stays the reference's, so ``tools/unscreen/green.py``, ``bg.py``, ``bg_offline.py`` and ``tools/replace/replace.py``
+      ``unscreen.trimap`` and ``unscreen.bgmodel``.  Everything else -- file I/O, the CNN agents -- stays the
+      reference's, so ``tools/unscreen/green.py``, ``bg.py``, ``bg_offline.py`` and ``tools/replace/replace.py``
       import and run unchanged.
     * No reference package around -> ALIAS: ``sys.modules['unscreen'...]`` point at the mirror (hot-path names only).
 
-    ``overlay`` forces one mode (True / False).  Returns ``sys.modules[name]``; ``installed_names(name)`` lists what was
-    patched."""
+    ``io=True`` also replaces ``parallel_read_img`` / ``save_img`` (utils/fileio.py) with the nvJPEG-based ones: JPEG
+    decoders are not bit-identical, so that one is opt-in.  ``overlay`` forces one mode (True / False).  Returns
+    ``sys.modules[name]``; ``installed_names(name)`` lists what was patched."""
     import importlib.util  # noqa: F401  (find_spec)
     base = __name__ + ".unscreen"
     if overlay is None:
@@ -65,7 +67,8 @@ def install(name="unscreen", overlay=None):
     if getattr(ref, "__name__", "").startswith(__name__):
         raise ImportError(f"install(overlay=True): '{name}' resolves to the B200 mirror itself, not to the reference package")
     patched = []
-    for ref_sub, mirror_sub in _OVERLAY.items():
+    overlay_map = dict(_OVERLAY, **({"utils.fileio": "utils.fileio"} if io else {}))
+    for ref_sub, mirror_sub in overlay_map.items():
         mirror = importlib.import_module(f"{base}.{mirror_sub}")
         target = importlib.import_module(f"{name}.{ref_sub}")
         names = getattr(mirror, "__all__", None) or [_AGENT_CLASSES[ref_sub]]
@@ -76,27 +79,6 @@ def install(name="unscreen", overlay=None):
             setattr(target, n, obj)
             setattr(parent, n, obj)
             patched.append(f"{name}.{ref_sub}.{n}")
-    # unscreen.bgmodel: 'mean' and 'pcov' run on the device, 'rf' (scipy region fill) stays the reference's
-    ref_bg = importlib.import_module(f"{name}.bgmodel.agent")
-    mine_bg = importlib.import_module(f"{base}.bgmodel.agent").BackgroundAgent
-    if not getattr(ref_bg.BackgroundAgent, "_vu_b200_hybrid", False):
-        ref_cls = ref_bg.BackgroundAgent
-
-        class BackgroundAgent(ref_cls):
-            __doc__ = ref_cls.__doc__
-            _vu_b200_hybrid = True
-
-            def forward(self, img, mask, method='rf'):
-                if method in ('mean', 'pcov'):
-                    return mine_bg.forward(self, img, mask, method)
-                return ref_cls.forward(self, img, mask, method)
-
-            _mean_color_hsv = mine_bg._mean_color_hsv
-            _pcov_dev = mine_bg._pcov_dev
-        BackgroundAgent.__module__ = mine_bg.__module__
-        ref_bg.BackgroundAgent = BackgroundAgent
-        importlib.import_module(f"{name}.bgmodel").BackgroundAgent = BackgroundAgent
-        patched.append(f"{name}.bgmodel.agent.BackgroundAgent[mean,pcov]")
     _PATCHED[name] = patched
     return ref
 

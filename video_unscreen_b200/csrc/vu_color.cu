@@ -165,3 +165,34 @@ extern "C" int vu_inrange_image(const uint8_t* bgr, const uint8_t* bgimg, int64_
   const bool vec = aligned4(bgr) && aligned4(bgimg) && aligned4(mask01) && (bg_npix % 4 == 0);
   return launch_px(f, npix, vec, stream);
 }
+
+// ---- frame I/O glue: nvJPEG hands out planar RGB, the reference's arrays are interleaved BGR ----
+namespace vu {
+namespace {
+// planes [3][npix] (R, G, B) -> pixels [npix][3] (B, G, R), or back
+template <bool TO_PLANAR>
+__global__ void __launch_bounds__(kThreads) planar_rgb_bgr_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int64_t npix) {
+  for (int64_t p = (int64_t)blockIdx.x * kThreads + threadIdx.x; p < npix; p += (int64_t)gridDim.x * kThreads) {
+    if (TO_PLANAR) {
+      dst[p] = src[3 * p + 2]; dst[npix + p] = src[3 * p + 1]; dst[2 * npix + p] = src[3 * p];
+    } else {
+      dst[3 * p] = src[2 * npix + p]; dst[3 * p + 1] = src[npix + p]; dst[3 * p + 2] = src[p];
+    }
+  }
+}
+}  // namespace
+}  // namespace vu
+
+extern "C" int vu_planar_rgb_to_bgr(const uint8_t* src, uint8_t* dst, int64_t npix, vu_stream_t stream) {
+  VU_REQUIRE(src && dst && npix >= 0);
+  if (npix == 0) return VU_OK;
+  vu::planar_rgb_bgr_kernel<false><<<vu::grid_for(npix, vu::kThreads, 8), vu::kThreads, 0, vu::S(stream)>>>(src, dst, npix);
+  VU_RETURN_LAUNCH();
+}
+
+extern "C" int vu_bgr_to_planar_rgb(const uint8_t* src, uint8_t* dst, int64_t npix, vu_stream_t stream) {
+  VU_REQUIRE(src && dst && npix >= 0);
+  if (npix == 0) return VU_OK;
+  vu::planar_rgb_bgr_kernel<true><<<vu::grid_for(npix, vu::kThreads, 8), vu::kThreads, 0, vu::S(stream)>>>(src, dst, npix);
+  VU_RETURN_LAUNCH();
+}

@@ -304,6 +304,11 @@ def resize_linear_image(x, dh, dw):
     return _resize(lib().vu_resize_linear_u8, x, dh, dw, 3)
 
 
+def resize_linear(x, dh, dw):
+    """cv2.resize(x, (dw, dh)) of an image [H,W,3] or a single-channel [H,W] array, any ratio"""
+    return _resize(lib().vu_resize_linear_u8, x, dh, dw, 3 if x.ndim == 3 else 1)
+
+
 def resize_nearest_mask(x, dh, dw):
     return _resize(lib().vu_resize_nearest_u8, x, dh, dw, 1)
 
@@ -752,6 +757,69 @@ def pcov_fill(img, hole_mask, box, ksize=5, max_rounds=100, batch=8):
     return bufs[done_after % 2]
 
 
+# ---- regionfill (utils/region_fill.py) -----------------------------------------------------------------
+
+def resize_linear_f64(x, dh, dw, fx=None, fy=None, keep_mask=None, keep_src=None):
+    """cv2.resize of float64 planes [C,H,W] (default INTER_LINEAR).  fx / fy: the ``(0, 0), fx=, fy=`` form (sampling step
+    1 / fx whatever the rounded size).  keep_mask / keep_src: where keep_mask == 0 the result is keep_src."""
+    x = _dev(x, torch.float64)
+    c, sh, sw = x.shape
+    out = torch.empty((c, dh, dw), dtype=torch.float64, device=x.device)
+    sx = 1.0 / fx if fx is not None else 1.0 / (float(dw) / sw)
+    sy = 1.0 / fy if fy is not None else 1.0 / (float(dh) / sh)
+    if keep_mask is not None:
+        keep_mask, keep_src = _mask(keep_mask), _dev(keep_src, torch.float64)
+        if tuple(keep_mask.shape) != (dh, dw) or tuple(keep_src.shape) != (c, dh, dw):
+            raise ValueError("keep_mask / keep_src must have the output's shape")
+    check(lib().vu_resize_linear_f64(_p(x), c, sh, sw, _p(out), int(dh), int(dw), sx, sy,
+                                     _p(keep_mask) if keep_mask is not None else None, _p(keep_src) if keep_src is not None else None, _stream()))
+    return out
+
+
+def laplace_fill(planes, mask, tol=1e-10, max_iters=50000):
+    """regionfillLaplace (utils/region_fill.py:26-63) for float64 planes [C,H,W] sharing mask [H,W] (> 0 = fill): solved on
+    the mask's bounding box (+ 1 pixel, so that only real image borders act as borders).  -> (filled planes, iterations).
+    Raises if the conjugate gradients did not reach ``tol`` (relative residual) within ``max_iters``."""
+    planes, mask = _dev(planes, torch.float64), _mask(mask)
+    c, h, w = planes.shape
+    if tuple(mask.shape) != (h, w):
+        raise ValueError("mask must be [H,W] of the planes")
+    box = mask_bbox(mask)
+    out = planes.clone()
+    if box is None:
+        return out, 0
+    r0, r1, c0, c1 = box
+    r0, r1, c0, c1 = max(r0 - 1, 0), min(r1 + 2, h), max(c0 - 1, 0), min(c1 + 2, w)
+    x = out[:, r0:r1, c0:c1].contiguous()
+    m = mask[r0:r1, c0:c1].contiguous()
+    rh, rw = r1 - r0, c1 - c0
+    nbytes = lib().vu_regionfill_workspace_bytes(c, rh, rw)
+    ws = torch.empty(nbytes, dtype=u8, device=planes.device)
+    iters, resid = ctypes.c_int32(0), ctypes.c_double(0.0)
+    check(lib().vu_regionfill_f64(_p(x), _p(m), c, rh, rw, float(tol), int(max_iters), _p(ws), nbytes, ctypes.byref(iters), ctypes.byref(resid), _stream()))
+    if not resid.value <= tol:
+        raise RuntimeError(f"regionfill: residual {resid.value:.3g} after {iters.value} iterations (tol {tol:g})")
+    out[:, r0:r1, c0:c1] = x
+    return out, iters.value
+
+
+def regionfill(planes, mask, factor=1.0, tol=1e-10):
+    """regionfill (utils/region_fill.py:7-17) for planes [C,H,W] (any real dtype; uint8 images as they are) sharing mask
+    [H,W] (bool / uint8, != 0 = fill).  -> float64 [C,H,W]."""
+    mask = _mask(mask)
+    if not (isinstance(planes, torch.Tensor) and planes.is_cuda and planes.ndim == 3):
+        raise TypeError("expected a CUDA tensor [C,H,W]")
+    src = planes.to(torch.float64).contiguous()
+    c, h, w = src.shape
+    if factor == 1.0:
+        return laplace_fill(src, mask, tol)[0]
+    dw, dh = int(np.rint(w * factor)), int(np.rint(h * factor))          # saturate_cast<int>: round half to even
+    m_lo = (resize_linear_f64(mask[None].to(torch.float64), dh, dw, factor, factor)[0] > 0).to(u8)
+    x_lo = resize_linear_f64(src, dh, dw, factor, factor)
+    x_lo = laplace_fill(x_lo, m_lo, tol)[0]
+    return resize_linear_f64(x_lo, h, w, keep_mask=mask, keep_src=src)
+
+
 # ---- remove_invalid_objects (utils/maskprocess.py:77-152) -----------------------------------------
 
 def remove_invalid_objects(alpha, segmask, score_map, saliency_thr, consensus_thr, max_objects=16384, out=None):
@@ -772,3 +840,23 @@ def remove_invalid_objects(alpha, segmask, score_map, saliency_thr, consensus_th
     check(lib().vu_remove_invalid_objects(_p(alpha), _p(segmask), _p(score_map), n, h, w, float(saliency_thr), float(consensus_thr), _p(out),
                                           _p(status), _p(ws), ws_bytes, int(max_objects), _stream()))
     return out, status
+
+
+# ---- frame I/O glue (utils/fileio.py) ----------------------------------------------------------------
+
+def planar_rgb_to_bgr(x):
+    """[3,H,W] planar RGB (what nvJPEG decodes to) -> [H,W,3] interleaved BGR"""
+    x = _dev(x)
+    h, w = x.shape[-2:]
+    out = torch.empty((h, w, 3), dtype=u8, device=x.device)
+    check(lib().vu_planar_rgb_to_bgr(_p(x), _p(out), h * w, _stream()))
+    return out
+
+
+def bgr_to_planar_rgb(x):
+    """[H,W,3] interleaved BGR -> [3,H,W] planar RGB (what nvJPEG encodes from)"""
+    x = _img(x)
+    h, w = x.shape[:2]
+    out = torch.empty((3, h, w), dtype=u8, device=x.device)
+    check(lib().vu_bgr_to_planar_rgb(_p(x), _p(out), h * w, _stream()))
+    return out

@@ -1,7 +1,7 @@
 """BackgroundAgent (reference: unscreen/bgmodel/agent.py:9-208): single-image background inpainting under a
-foreground mask.  SURVEY.md section 8 keeps its signature (row a25) and ranks its bodies as "next" row f-4: the 'mean'
-and 'pcov' methods run on the device here; 'rf' (region fill: a sparse Laplace solve with scipy, bgmodel/region_fill.py)
-is not a streaming per-pixel kernel and stays with the reference (``install()`` keeps the reference's own method)."""
+foreground mask.  SURVEY.md section 8 keeps its signature (row a25) and ranks its bodies as "next" row f-4.  All three
+methods run on the device: 'mean' and 'pcov' bit-exactly; 'rf' (region fill, utils/region_fill.py: a sparse Laplace
+solve with scipy in the reference) by conjugate gradients, i.e. to a tolerance (csrc/vu_regionfill.cu)."""
 import numpy as np
 import torch
 
@@ -55,14 +55,26 @@ class BackgroundAgent():
         m, _ = to_dev(mask)
         return back(self._pcov_dev(t, m), as_np)
 
+    def _regionfill_dev(self, img_hsv, mask):
+        """get_bg_by_regionfill (reference :133-157) on device tensors: V from the Laplace fill at half resolution, H and S
+        from the boundary's mean colour"""
+        col = self._mean_color_hsv(img_hsv, mask)
+        hole = mask > 0
+        v = ops.regionfill(img_hsv[:, :, 2][None], mask, 0.5)[0].clamp_(0, 255).to(torch.uint8)     # .astype(np.uint8): truncation
+        out = img_hsv.clone()
+        out[hole] = torch.from_numpy(col).to(out.device)
+        out[:, :, 2][hole] = v[hole]
+        return out
+
+    def get_bg_by_regionfill(self, img_hsv, mask):
+        t, as_np = to_dev(img_hsv)
+        m, _ = to_dev(mask)
+        return back(self._regionfill_dev(t, m), as_np)
+
     def forward(self, img, mask, method='rf'):
-        """reference :159-208.  'mean': boundary mean colour; 'pcov': iterated partial convolutions; 'rf': not here."""
+        """reference :159-208.  'mean': boundary mean colour; 'pcov': iterated partial convolutions; 'rf': region fill."""
         if method not in ('mean', 'pcov', 'rf'):
             raise NameError(f'No such method for background inpainting: {method}')
-        if method == 'rf':
-            raise NotImplementedError(
-                "BackgroundAgent.forward(method='rf') (region fill: scipy sparse solve, reference bgmodel/region_fill.py) "
-                "is outside the B200 hot path; use the reference's implementation (video_unscreen_b200.install() keeps it)")
         t, as_np = to_dev(img)
         m, _ = to_dev(mask)
         ori_h, ori_w = m.shape
@@ -79,7 +91,10 @@ class BackgroundAgent():
             col_hsv = self._mean_color_hsv(ops.bgr2hsv(img_lo), dil)
             col_bgr = ops.hsv2bgr(torch.from_numpy(np.tile(col_hsv, (1, 4, 1))).to(t.device))[0, 0].cpu().numpy()
             bgimg = torch.from_numpy(np.broadcast_to(col_bgr, (ih, iw, 3)).copy()).to(t.device)
-        else:
+        elif method == 'pcov':
             bgimg = self._pcov_dev(img_lo, dil)
-        bgimg = ops.blend(_lib.BLEND_FUSE, bgimg, dil, img_lo)       # fuse_fgbg(bgimg, img, dilated_mask), :194 / :197
+        if method == 'rf':
+            bgimg = ops.hsv2bgr(self._regionfill_dev(ops.bgr2hsv(img_lo), dil))      # :198-201, no fuse
+        else:
+            bgimg = ops.blend(_lib.BLEND_FUSE, bgimg, dil, img_lo)   # fuse_fgbg(bgimg, img, dilated_mask), :194 / :197
         return back(ops.resize_linear_image(bgimg, ori_h, ori_w), as_np)
