@@ -364,10 +364,12 @@ int vu_remove_invalid_objects(const uint8_t* alpha, const uint8_t* segmask, cons
  * discrete Laplace equation whose boundary data are the pixels outside the mask (every masked pixel = the mean of its
  * in-image 4-neighbours).  The reference builds the sparse matrix and calls scipy's direct solver; this is conjugate
  * gradients in float64, stopped at |r| <= tol |b| or after max_iters iterations: parity is a tolerance (tol 1e-10: ~1e-6
- * grey levels on a 1080p person-sized hole).  HOST-SYNCHRONOUS on `stream` (the residuals are read every 64 iterations);
+ * grey levels on a 1080p person-sized hole).  snap_eps > 0: filled values within snap_eps of an integer become that integer
+ * (the reference truncates the result to uint8, and exact-integer solutions -- isolated pixels, flat boundaries -- come out of
+ * the direct solver exactly; 1e-6 with tol 1e-10).  HOST-SYNCHRONOUS on `stream` (the residuals are read every 64 iterations);
  * iters_out / resid_out (host pointers, may be NULL) receive the iterations done and the final max |r| / |b|. */
 size_t vu_regionfill_workspace_bytes(int planes, int h, int w);
-int vu_regionfill_f64(double* x, const uint8_t* mask, int planes, int h, int w, double tol, int max_iters, void* workspace,
+int vu_regionfill_f64(double* x, const uint8_t* mask, int planes, int h, int w, double tol, int max_iters, double snap_eps, void* workspace,
                       size_t workspace_bytes, int32_t* iters_out, double* resid_out, vu_stream_t stream);
 /* cv2.resize of float64 planes with the default INTER_LINEAR (region_fill.py:10-15): scale_x / scale_y are the sampling
  * steps (1 / fx for the `(0, 0), fx=` form, else src / dst size); exactly 2 in both axes = cv2's INTER_AREA shortcut.

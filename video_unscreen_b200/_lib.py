@@ -81,7 +81,7 @@ SIGNATURES = {
     "vu_remove_objects_workspace_bytes": (ctypes.c_size_t, [_i, _i, _i, _i]),
     "vu_remove_invalid_objects": (_i, [_p, _p, _p, _i, _i, _i, _d, _d, _p, _p, _p, ctypes.c_size_t, _i, _p]),
     "vu_regionfill_workspace_bytes": (_sz, [_i, _i, _i]),
-    "vu_regionfill_f64": (_i, [_p, _p, _i, _i, _i, _d, _i, _p, _sz, _p, _p, _p]),
+    "vu_regionfill_f64": (_i, [_p, _p, _i, _i, _i, _d, _i, _d, _p, _sz, _p, _p, _p]),
     "vu_resize_linear_f64": (_i, [_p, _i, _i, _i, _p, _i, _i, _d, _d, _p, _p, _p]),
     "vu_planar_rgb_to_bgr": (_i, [_p, _p, _i64, _p]),
     "vu_bgr_to_planar_rgb": (_i, [_p, _p, _i64, _p]),

@@ -13,7 +13,8 @@
 // alpha / beta are formed on the device from the dot products (float64 atomics, three rotating slots), the host only reads
 // the residuals every CHECK iterations.  Several planes that share one mask (the B, G, R planes of bg.py:79) are solved
 // together.  Parity with the direct solver is a TOLERANCE: iteration stops at |r| <= tol |b| (default 1e-10: within ~1e-6
-// grey levels of spsolve on a 1080p person-sized hole), and the reference truncates the float result to uint8.
+// grey levels of spsolve on a 1080p person-sized hole), and the reference truncates the float result to uint8 (hence
+// rf_snap_kernel at the end).
 //
 //   vu_resize_linear_f64   the two cv2.resize calls on float64 data around the solve (region_fill.py:10-15)
 #include "vu_common.cuh"
@@ -171,6 +172,23 @@ __global__ void __launch_bounds__(RT) rf_step_kernel(double* __restrict__ x, con
   if (threadIdx.x == 0) atomicAdd(&sc[c].rr[(k + 1) % 3], rr);
 }
 
+// values within eps of an integer become that integer.  The reference truncates the fill to uint8: where the exact solution
+// IS an integer (an isolated masked pixel whose four neighbours sum to a multiple of 4, a flat boundary) the direct solver
+// returns it exactly, the iteration returns it -1e-7 half of the time, and the truncation would differ by a whole level.
+__global__ void __launch_bounds__(RT) rf_snap_kernel(double* __restrict__ x, const uint8_t* __restrict__ mask, int h, int w, double eps) {
+  const int c = blockIdx.z;
+  const int64_t plane = (int64_t)c * h * w;
+  const int px = blockIdx.x * 32 + (threadIdx.x & 31);
+  for (int j = 0; j < RROWS; ++j) {
+    const int py = (blockIdx.y * 8 + (threadIdx.x >> 5)) * RROWS + j;
+    if (px >= w || py >= h) continue;
+    const int64_t i = (int64_t)py * w + px;
+    if (!mask[i]) continue;
+    const double v = x[plane + i], n = rint(v);
+    if (fabs(v - n) <= eps) x[plane + i] = n;
+  }
+}
+
 // cv2.resize of CV_64F data (INTER_LINEAR, IPP: double weights); AREA: the exact-2x case, which cv2 turns into 2 x 2
 // means (the last row / column of an odd source averages what exists, in float32)
 template <bool AREA>
@@ -222,9 +240,9 @@ extern "C" size_t vu_regionfill_workspace_bytes(int planes, int h, int w) {
   return 4 * (size_t)planes * h * w * sizeof(double) + (size_t)planes * sizeof(RfScal);
 }
 
-extern "C" int vu_regionfill_f64(double* x, const uint8_t* mask, int planes, int h, int w, double tol, int max_iters, void* workspace,
+extern "C" int vu_regionfill_f64(double* x, const uint8_t* mask, int planes, int h, int w, double tol, int max_iters, double snap_eps, void* workspace,
                                  size_t workspace_bytes, int32_t* iters_out, double* resid_out, vu_stream_t stream) {
-  VU_REQUIRE(x && mask && planes > 0 && planes <= 16 && h > 0 && w > 0 && tol > 0.0 && max_iters >= 0);
+  VU_REQUIRE(x && mask && planes > 0 && planes <= 16 && h > 0 && w > 0 && tol > 0.0 && max_iters >= 0 && snap_eps >= 0.0);
   if (!workspace || workspace_bytes < vu_regionfill_workspace_bytes(planes, h, w)) return VU_ERR_WORKSPACE;
   cudaStream_t st = S(stream);
   const size_t n = (size_t)planes * h * w;
@@ -264,6 +282,12 @@ extern "C" int vu_regionfill_f64(double* x, const uint8_t* mask, int planes, int
       rf_dir_kernel<<<grid, RT, 0, st>>>(mask, h, w, r, p[k & 1], p[(k + 1) & 1], ap, sc, k);
       rf_step_kernel<<<grid, RT, 0, st>>>(x, mask, h, w, r, p[(k + 1) & 1], ap, sc, k);
     }
+    e = record_cuda(cudaGetLastError());
+    if (e) return e;
+  }
+  if (snap_eps > 0.0) {
+    rf_snap_kernel<<<grid, RT, 0, st>>>(x, mask, h, w, snap_eps);
+    note_launch();
     e = record_cuda(cudaGetLastError());
     if (e) return e;
   }

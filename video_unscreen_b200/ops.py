@@ -776,9 +776,10 @@ def resize_linear_f64(x, dh, dw, fx=None, fy=None, keep_mask=None, keep_src=None
     return out
 
 
-def laplace_fill(planes, mask, tol=1e-10, max_iters=50000):
+def laplace_fill(planes, mask, tol=1e-10, max_iters=50000, snap_eps=1e-6):
     """regionfillLaplace (utils/region_fill.py:26-63) for float64 planes [C,H,W] sharing mask [H,W] (> 0 = fill): solved on
     the mask's bounding box (+ 1 pixel, so that only real image borders act as borders).  -> (filled planes, iterations).
+    Filled values within ``snap_eps`` of an integer are set to it (the callers truncate to uint8; include/vu_b200.h).
     Raises if the conjugate gradients did not reach ``tol`` (relative residual) within ``max_iters``."""
     planes, mask = _dev(planes, torch.float64), _mask(mask)
     c, h, w = planes.shape
@@ -796,7 +797,7 @@ def laplace_fill(planes, mask, tol=1e-10, max_iters=50000):
     nbytes = lib().vu_regionfill_workspace_bytes(c, rh, rw)
     ws = torch.empty(nbytes, dtype=u8, device=planes.device)
     iters, resid = ctypes.c_int32(0), ctypes.c_double(0.0)
-    check(lib().vu_regionfill_f64(_p(x), _p(m), c, rh, rw, float(tol), int(max_iters), _p(ws), nbytes, ctypes.byref(iters), ctypes.byref(resid), _stream()))
+    check(lib().vu_regionfill_f64(_p(x), _p(m), c, rh, rw, float(tol), int(max_iters), float(snap_eps), _p(ws), nbytes, ctypes.byref(iters), ctypes.byref(resid), _stream()))
     if not resid.value <= tol:
         raise RuntimeError(f"regionfill: residual {resid.value:.3g} after {iters.value} iterations (tol {tol:g})")
     out[:, r0:r1, c0:c1] = x
