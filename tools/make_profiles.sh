@@ -8,7 +8,8 @@ K='regex:cf_lowres|alpha_up_fuzzy|cross_march|trimap_|bgstep_frame|median|blend|
 python bench.py --steps 20 --warmup 5 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
 python bench.py --impl reference --steps 20 --warmup 5 > $out/${tag}_bench_reference_arm.json 2>> $out/${tag}_bench.err
 for wl in cf_trimap_1080p green_4k replace_1080p bgstep_4k; do
-  ncu --metrics $M --clock-control none -k "$K" --csv --log-file $out/${tag}_${wl}_launches.csv python tools/bench_configs.py --only $wl --steps 1 --warmup 1 --no-cpu --no-e2e --frames 120 > $out/${tag}_ncu_${wl}.log 2>&1
+  C=""; [ $wl = bgstep_4k ] && C="-c 96"     # the 6 person-mask runs (16 launches each); the dense-mask runs that follow are left out
+  ncu --metrics $M --clock-control none -k "$K" $C --csv --log-file $out/${tag}_${wl}_launches.csv python tools/bench_configs.py --only $wl --steps 1 --warmup 1 --no-cpu --no-e2e --frames 120 > $out/${tag}_ncu_${wl}.log 2>&1
 done
 ncu --metrics $M --clock-control none -k "$K" --csv --log-file $out/${tag}_median_launches.csv python bench.py --steps 2 --warmup 3 --configs none --no-cpu > $out/${tag}_ncu_median.log 2>&1
 ls -la $out/${tag}_*
