@@ -52,6 +52,15 @@ __device__ __forceinline__ void block_add2(unsigned a, unsigned b, unsigned long
   }
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS): the FG variant prefetches the next row's frame bytes while it works
+// on this one, without holding them in registers
+__device__ __forceinline__ void cp_async16(void* smem, const void* gptr) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gptr));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int SC, bool FG>
 __global__ void __launch_bounds__(UT, FG ? 4 : 5) alpha_up_fuzzy_kernel(const uint8_t* __restrict__ alpha_lo, int th, int tw, const uint8_t* __restrict__ alt_src,
                                                             const uint8_t* __restrict__ alt_flags, const uint8_t* __restrict__ frames, int lo0, int lo1,
@@ -61,6 +70,7 @@ __global__ void __launch_bounds__(UT, FG ? 4 : 5) alpha_up_fuzzy_kernel(const ui
                                                             uint8_t* __restrict__ fg_out, uint8_t* __restrict__ bg_out) {
   __shared__ HsvTab tab;
   __shared__ float ktab[FG ? 256 : 1];   // 1 - alpha/255. for every alpha byte
+  __shared__ uint4 stage[FG ? 2 : 1][FG ? 3 : 1][FG ? UT : 1];   // FG: the frame bytes of this row and the next, [stage][16-byte piece][thread]
   if (FG) hsv_tab_init(tab);
   else hsv_tab_init_fwd(tab);
   if (FG)
@@ -80,21 +90,33 @@ __global__ void __launch_bounds__(UT, FG ? 4 : 5) alpha_up_fuzzy_kernel(const ui
   int h0v = 0, s0v = 0, v0v = 0;
   if (FG) bgr2hsv_px(bgB, bgG, bgR, tab, h0v, s0v, v0v);
   unsigned cnt_f = 0, cnt_p = 0;
+  auto row_of = [&](int it) { return ((blockIdx.y * UP_ROWS + it) * (UT / 32) + (threadIdx.x >> 5)) * 4 + (lane >> 3); };
+  // FG: the patched background needs the frame everywhere, so its 48 bytes per thread and row are fetched one row ahead with
+  // asynchronous copies (a thread only ever reads back its own pieces: no barrier).  The kernel waited on these loads with
+  // half of its issue slots empty when every row fetched its own.
+  auto prefetch = [&](int it) {
+    if (!FG) return;
+    const int y = row_of(it);
+    if (it < UP_ROWS && x0 < w && y < h) {
+      const uint8_t* src = frames + (((int64_t)n * h + y) * w + x0) * 3;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) cp_async16(&stage[it & 1][k][threadIdx.x], src + 16 * k);
+    }
+    cp_async_commit();
+  };
+  prefetch(0);
   // a warp takes one destination row at a time (UP_ROWS of them, interleaved with the CTA's other warps: the table set-up
   // above is paid once per UP_ROWS * 8 rows); the rows of a thread do not depend on each other
 #pragma unroll 1
   for (int it = 0; it < UP_ROWS; ++it) {
-  const int y = ((blockIdx.y * UP_ROWS + it) * (UT / 32) + (threadIdx.x >> 5)) * 4 + (lane >> 3);
+  const int y = row_of(it);
   if (y - (lane >> 3) >= h) break;   // warp-uniform
+  prefetch(it + 1);
   const bool act = x0 < w && y < h;
   const int r = y / SC, ph = y % SC;
   unsigned aw[4] = {0u, 0u, 0u, 0u};
   const int64_t fo = (((int64_t)n * h + y) * w + x0) * 3;
   uint4 fv[3];
-  if (FG && act) {   // the patched background needs the frame everywhere: fetch it before anything else
-#pragma unroll
-    for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frames + fo + 16 * k);
-  }
   if (act) {
     if (alt) {
       const uint4 v = ldg_stream16(alt_src + ((int64_t)n * h + y) * w + x0);
@@ -166,7 +188,11 @@ __global__ void __launch_bounds__(UT, FG ? 4 : 5) alpha_up_fuzzy_kernel(const ui
   if (act) {
     const unsigned any = aw[0] | aw[1] | aw[2] | aw[3];
     unsigned fz = 0;
-    if (!FG && any) {
+    if (FG) {
+      cp_async_wait<1>();   // everything but the row just requested has landed
+#pragma unroll
+      for (int k = 0; k < 3; ++k) fv[k] = stage[it & 1][k][threadIdx.x];
+    } else if (any) {
 #pragma unroll
       for (int k = 0; k < 3; ++k) fv[k] = ldg_stream16(frames + fo + 16 * k);
     }
@@ -236,6 +262,7 @@ __global__ void __launch_bounds__(UT, FG ? 4 : 5) alpha_up_fuzzy_kernel(const ui
     *reinterpret_cast<unsigned short*>(fzbits + (((int64_t)n * h + y) * w + x0) / 8) = (unsigned short)fz;
   }
   }
+  if (FG) cp_async_wait<0>();
   block_add2(cnt_f, cnt_p, counts2 + 2 * n);
 }
 
