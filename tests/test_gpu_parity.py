@@ -309,6 +309,31 @@ def test_blend_all_alpha_values(vu):
     assert np.array_equal(U.get_fg(fg, al, bg), R.get_fg(fg, al, bg))
 
 
+def test_replace_blend_every_triple_on_every_lane(vu):
+    """The integer replace / fuse blend (blend16_int_kernel) against the float64 expression of replace.py:74-76 on ALL 2^24
+    (alpha, fg, bg) byte triples, shifted so that every triple passes through each of the twelve byte positions of the
+    kernel's four-pixel pattern (pairs, singles, both accumulators of the fix-up bits)."""
+    n = 1 << 24
+    p = np.arange(n, dtype=np.uint32)
+    a, c, q = (p >> 16).astype(np.uint8), ((p >> 8) & 255).astype(np.uint8), (p & 255).astype(np.uint8)
+    m = a.astype(np.float64) / 255
+    want = (c.astype(np.float64) * m + q.astype(np.float64) * (1 - m)).astype(np.uint8)
+    assert np.array_equal(want[:300000:4097], R.replace_blend(c[:300000:4097, None, None].repeat(3, 2), a[:300000:4097, None],
+                                                              q[:300000:4097, None, None].repeat(3, 2))[:, 0, 0])
+    U = vu.U
+    for shift in range(4):
+        ar, cr, qr, wr = (np.roll(x, shift) for x in (a, c, q, want))
+        fg = dev(np.repeat(cr[:, None], 3, 1).reshape(4096, 4096, 3))
+        bg = dev(np.repeat(qr[:, None], 3, 1).reshape(4096, 4096, 3))
+        al = dev(ar.reshape(4096, 4096))
+        got = host(U.replace_blend(fg, al, bg)).reshape(n, 3)
+        for ch in range(3):
+            bad = np.flatnonzero(got[:, ch] != wr)
+            assert bad.size == 0, (shift, ch, bad[:5], got[bad[:5], ch], wr[bad[:5]])
+        if shift == 0:
+            assert np.array_equal(host(U.fuse_fgbg(fg, bg, al)).reshape(n, 3), got)
+
+
 @pytest.mark.parametrize("shape,thr", [((70, 128), 25), ((64, 120), 25), ((131, 244), 10), ((9, 12), 25), ((200, 500), 254), ((200, 500), 255),
                                        ((65, 124), 0)])
 def test_bgdiff_gate_fused(vu, shape, thr):

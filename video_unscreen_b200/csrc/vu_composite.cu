@@ -7,6 +7,7 @@
 // reference's operation order, so the stages before cv2's HSV2BGR are
 // bit-exact; HSV2BGR itself is the truncating whole-image variant (+-1 LSB
 // against cv2 by cv2's own inconsistency).
+#include <cstdlib>
 #include <initializer_list>
 
 #include "vu_common.cuh"
@@ -358,6 +359,120 @@ __global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restric
   }
 }
 
+// REPLACE / FUSE with one alpha per pixel, in integers.  The float64 sequence trunc(fl(fl(c m) + fl(q fl(1 - m)))), m = fl(a / 255),
+// equals floor(t / 255), t = c a + q (255 - a), whenever 255 does not divide t: its rounding errors (~1e-13) cannot cross an
+// integer that lies at least 1 / 255 away.  Where 255 | t the exact value IS an integer K and the float64 result is K or a hair
+// below it (truncated: K - 1): 12 397 of the 2^24 (a, c, q) triples, with no closed form.
+//   main path: two channels of a pixel that lie in one word share an IMAD pair as 16-bit lanes ([c0, c1] * a + [q0, q1] * (255 - a)
+//   cannot carry: <= 65025), the third one is an IDP.4A; t / 255 = (t + 1 + (t >> 8)) >> 8 on both lanes at once, and the LOW
+//   byte of that sum is zero exactly when 255 | t and t > 0 - the candidates.  Candidate bytes of soft pixels (a not 0 / 255: those
+//   two are exact copies) are collected as bits, by position;
+//   fix-up: a thread with candidates (1.9 % of the bytes on random data) parks its 112 input bytes in shared memory - registers
+//   cannot be indexed by a run-time position -, walks the bits, evaluates the float64 sequence of blend_kernel for those bytes and
+//   stores the byte again where it differs.  (A first version looked the triples up in a 2 MB bit table and re-read the bytes
+//   from global memory: two dependent L2 round trips per candidate made it latency-bound, 1.44 ms against 1.17 ms for the
+//   float64 kernel on 300 x 1080p.)
+// s = t + 1 + (t >> 8) on two 16-bit lanes: byte 1 / 3 = floor(t / 255), byte 0 / 2 = 0 iff 255 | t and t > 0
+__device__ __forceinline__ unsigned div255_lanes(unsigned t) { return t + __byte_perm(t, 0u, 0x4341) + 0x00010001u; }
+
+__global__ void __launch_bounds__(THREADS) blend16_int_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
+                                                              int64_t ngroups, int64_t bg_groups, uint4* __restrict__ out) {
+  __shared__ double mtab[256];
+  __shared__ uint4 park[7][THREADS];   // fg 0..2, bg 3..5, alpha 6 of the thread's group
+  mtab[threadIdx.x] = __ddiv_rn((double)threadIdx.x, 255.0);   // THREADS == 256
+  __syncthreads();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
+    const uint4 av = ldg_stream16(alpha + g);
+    const unsigned all1 = av.x & av.y & av.z & av.w, any = av.x | av.y | av.z | av.w;
+    if (all1 == 0xFFFFFFFFu) {       // sixteen pixels of the foreground: the background is not read (as in blend16_kernel)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, ldg_stream16(fg + 3 * g + k));
+      continue;
+    }
+    const int64_t gb = g % bg_groups;
+    if (any == 0u) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k));
+      continue;
+    }
+    uint4 f[3], q[3], o[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) f[k] = ldg_stream16(fg + 3 * g + k);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) q[k] = (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k);
+    const unsigned* fw = reinterpret_cast<const unsigned*>(f);
+    const unsigned* qw = reinterpret_cast<const unsigned*>(q);
+    const unsigned aw[4] = {av.x, av.y, av.z, av.w};
+    unsigned* ow = reinterpret_cast<unsigned*>(o);
+    unsigned accA = 0u, accB = 0u;   // candidate bits: byte b of output word w at bit 8 b + w (w < 8) / 8 b + w - 4 (w >= 8)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {    // four pixels = three words: B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+      const unsigned a4 = aw[j];
+      // bit 7 of byte p: pixel p is soft (a differs from its own sign byte, 0x00 / 0xFF)
+      unsigned sg;                                                      // every byte's sign spread over the byte
+      asm("prmt.b32 %0, %1, %1, 0xBA98;" : "=r"(sg) : "r"(a4));
+      const unsigned ax = a4 ^ sg;
+      const unsigned soft = (((ax & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | ax) & 0x80808080u;
+      unsigned m[4], om[4], mw[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        m[p] = __byte_perm(a4, 0u, 0x4440 | p);
+        om[p] = 255u - m[p];
+        mw[p] = om[p] * 256u + m[p];                                  // IDP.4A weights [a, 255 - a, 0, 0]
+      }
+      const unsigned f0 = fw[3 * j], f1 = fw[3 * j + 1], f2 = fw[3 * j + 2];
+      const unsigned q0 = qw[3 * j], q1 = qw[3 * j + 1], q2 = qw[3 * j + 2];
+      // pairs (two channels of one pixel, one word): lanes [x, 0, y, 0]
+      const unsigned tP0 = __byte_perm(f0, 0u, 0x4140) * m[0] + __byte_perm(q0, 0u, 0x4140) * om[0];   // B0 G0
+      const unsigned tP1 = __byte_perm(f1, 0u, 0x4140) * m[1] + __byte_perm(q1, 0u, 0x4140) * om[1];   // G1 R1
+      const unsigned tP2 = __byte_perm(f1, 0u, 0x4342) * m[2] + __byte_perm(q1, 0u, 0x4342) * om[2];   // B2 G2
+      const unsigned tP3 = __byte_perm(f2, 0u, 0x4241) * m[3] + __byte_perm(q2, 0u, 0x4241) * om[3];   // B3 G3
+      // singles: [c, q, *, *] . [a, 255 - a, 0, 0]
+      const unsigned tS0 = __dp4a(__byte_perm(f0, q0, 0x2262), mw[0], 0u);                              // R0
+      const unsigned tS1 = __dp4a(__byte_perm(f0, q0, 0x3373), mw[1], 0u);                              // B1
+      const unsigned tS2 = __dp4a(__byte_perm(f2, q2, 0x0040), mw[2], 0u);                              // R2
+      const unsigned tS3 = __dp4a(__byte_perm(f2, q2, 0x3373), mw[3], 0u);                              // R3
+      const unsigned sP0 = div255_lanes(tP0), sP1 = div255_lanes(tP1), sP2 = div255_lanes(tP2), sP3 = div255_lanes(tP3);
+      const unsigned sS01 = div255_lanes(tS1 * 65536u + tS0), sS23 = div255_lanes(tS3 * 65536u + tS2);
+      ow[3 * j] = __byte_perm(sP0, sS01, 0x7531);
+      ow[3 * j + 1] = __byte_perm(sP1, sP2, 0x7531);
+      ow[3 * j + 2] = __byte_perm(sS23, sP3, 0x3751);
+      // the low bytes in the same order, zero bytes of soft pixels -> bit 7 (a borrow can flag the byte above a zero byte as
+      // well: a needless evaluation, never a wrong one)
+      const unsigned l0 = __byte_perm(sP0, sS01, 0x6420), l1 = __byte_perm(sP1, sP2, 0x6420), l2 = __byte_perm(sS23, sP3, 0x2640);
+      const unsigned z0 = (l0 - 0x01010101u) & ~l0 & __byte_perm(soft, 0u, 0x1000);
+      const unsigned z1 = (l1 - 0x01010101u) & ~l1 & __byte_perm(soft, 0u, 0x2211);
+      const unsigned z2 = (l2 - 0x01010101u) & ~l2 & __byte_perm(soft, 0u, 0x3332);
+      if (3 * j < 8) accA = (accA >> 1) + z0; else accB = (accB >> 1) + z0;
+      if (3 * j + 1 < 8) accA = (accA >> 1) + z1; else accB = (accB >> 1) + z1;
+      if (3 * j + 2 < 8) accA = (accA >> 1) + z2; else accB = (accB >> 1) + z2;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, o[k]);
+    if (accA | accB) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { park[k][threadIdx.x] = f[k]; park[3 + k][threadIdx.x] = q[k]; }
+      park[6][threadIdx.x] = av;
+      const uint8_t* pk = reinterpret_cast<const uint8_t*>(&park[0][threadIdx.x]);   // the thread's own bytes: no barrier
+      uint8_t* o8 = reinterpret_cast<uint8_t*>(out + 3 * g);
+      do {
+        unsigned n, w0;
+        if (accA) { n = __ffs(accA) - 1; accA &= accA - 1; w0 = 0; }
+        else { n = __ffs(accB) - 1; accB &= accB - 1; w0 = 4; }
+        const unsigned i = 4 * ((n & 7) + w0) + (n >> 3);              // byte of the 48
+        const unsigned pi = (i * 171u) >> 9;                           // its pixel, i / 3
+        const unsigned c = pk[(i >> 4) * (THREADS * 16) + (i & 15)], b = pk[(3 + (i >> 4)) * (THREADS * 16) + (i & 15)];
+        const unsigned a = pk[6 * (THREADS * 16) + pi];
+        const double md = mtab[a];
+        const int v = f64_trunc_nonneg(__dadd_rn(__dmul_rn(u8_to_f64(c), md), __dmul_rn(u8_to_f64(b), __dsub_rn(1.0, md))));
+        const int k = (int)(((c * a + b * (255u - a)) * 0x8081u) >> 23);
+        if (v != k) o8[i] = (uint8_t)v;
+      } while (accA | accB);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) fuse_bg_kernel(const unsigned* __restrict__ bg, const unsigned* __restrict__ always, int64_t nwords,
                                                           int64_t always_words, float beta, float omb, unsigned* __restrict__ out) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -480,6 +595,17 @@ __global__ void __launch_bounds__(THREADS) bgdiff_gray_px_kernel(const uint8_t* 
 
 inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3) == 0; }
 // true when the 4-pixel vector kernels cannot take the call: the byte kernels above do
+inline bool overlaps(const void* a, int64_t na, const void* b, int64_t nb) {
+  const uintptr_t x = reinterpret_cast<uintptr_t>(a), y = reinterpret_cast<uintptr_t>(b);
+  return x < y + (uintptr_t)nb && y < x + (uintptr_t)na;
+}
+
+// VU_BLEND_FP64=1 keeps the float64 kernel for the replace / fuse blend (A/B measurements)
+inline bool blend_fp64_forced() {
+  static const bool forced = [] { const char* e = getenv("VU_BLEND_FP64"); return e && e[0] == '1'; }();
+  return forced;
+}
+
 inline bool needs_px(int64_t npix, int64_t other_npix, std::initializer_list<const void*> ptrs) {
   if (npix % 4 != 0 || (other_npix > 0 && other_npix % 4 != 0)) return true;
   for (const void* p : ptrs)
@@ -611,6 +737,12 @@ extern "C" int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int a
   if (wide) {
     const int64_t ng = npix / 16, bgg = (mode == VU_BLEND_NAIVE) ? 1 : bg_npix / 16;
     const int grid = grid_for(ng, THREADS, 8);
+    if ((mode == VU_BLEND_REPLACE || mode == VU_BLEND_FUSE) && alpha_channels == 1 && !blend_fp64_forced() &&
+        !overlaps(out, npix * 3, fg, npix * 3) && !overlaps(out, npix * 3, bg, bg_npix * 3) && !overlaps(out, npix * 3, alpha, npix)) {
+      blend16_int_kernel<<<grid, THREADS, 0, S(stream)>>>(reinterpret_cast<const uint4*>(fg), reinterpret_cast<const uint4*>(alpha),
+                                                          reinterpret_cast<const uint4*>(bg), ng, bgg, reinterpret_cast<uint4*>(out));
+      VU_RETURN_LAUNCH();
+    }
 #define LAUNCH16(M)                                                                                                          \
   do {                                                                                                                       \
     if (alpha_channels == 1)                                                                                                 \

@@ -19,6 +19,8 @@
 // image reset to the identity after every pass), then the four quadrant ANDs of Z = "t == 0" and F = "t == 255":
 // eight bit planes of th x ceil(tw/32) words per frame.  Kernel B: one pass over the output: four plane words per 4
 // pixels, the fuzzy override, one store.  The working-resolution trimap never exists as bytes.
+#include <cstdlib>
+
 #include "vu_common.cuh"
 
 namespace vu {
@@ -181,6 +183,111 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_bits_kernel(const uint8_t* 
   }
 }
 
+// The same planes by MARCHING (packed inputs, P passes, tw % 32 == 0 and at most 32 words per row: every working resolution
+// of input_long_side <= 1024): one warp owns a band of rows over the whole width, lane = word column, so the horizontal
+// neighbours are the neighbouring lanes' words (two shuffles per row and pass, no halo columns) and the P passes are a
+// systolic pipeline down the rows held in registers: when input row t arrives, pass p + 1 of row t - p - 1 is complete.
+// No shared memory, no barrier, and ~6x fewer instructions than the tile kernel above, which spends them on indices,
+// bounds and barriers for one word per thread and pass.
+constexpr int TM_WARPS = 4;      // bands per CTA
+template <int SC, int P>
+__global__ void __launch_bounds__(32 * TM_WARPS) trimap_bits_march_kernel(const uint8_t* __restrict__ mask_bits, const uint8_t* __restrict__ fuzzy_bits,
+                                                                          const uint8_t* __restrict__ flags, int h, int w, int th, int tw,
+                                                                          unsigned* __restrict__ planes, int nframes, int wpr, int band_rows) {
+  constexpr unsigned FULL = 0xFFFFFFFFu;
+  const int n = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int y0 = (blockIdx.x * TM_WARPS + (threadIdx.x >> 5)) * band_rows;
+  if (y0 >= th) return;                      // warp-uniform; nothing below synchronises the CTA
+  const int y1 = min(y0 + band_rows, th);
+  const bool ens = fuzzy_bits && flags && flags[n] == 0;
+  const bool col = lane < wpr;
+  const unsigned inw = col ? FULL : 0u;      // tw % 32 == 0: whole words
+  const unsigned* mb = reinterpret_cast<const unsigned*>(mask_bits + (int64_t)n * th * (tw >> 3));
+  const uint8_t* fb = fuzzy_bits + (int64_t)n * h * (w >> 3);
+  const int fstride = SC * (w >> 3);         // bytes between the fuzzy rows of consecutive working rows
+  auto load_row = [&](int y) -> unsigned {   // B = (nearest-sampled alpha >= 128) & ~fuzzy of working row y; 0 outside the image
+    if (!col || y < 0 || y >= th) return 0u;
+    unsigned b = __ldg(mb + (int64_t)y * wpr + lane);
+    if (ens) {
+      const uint8_t* f = fb + (int64_t)y * fstride;
+      unsigned fz;
+      if (SC == 2) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(f) + lane);
+        fz = compress2(v.x) | (compress2(v.y) << 16);
+      } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(f) + lane);
+        fz = compress4(v.x) | (compress4(v.y) << 8) | (compress4(v.z) << 16) | (compress4(v.w) << 24);
+      }
+      b &= ~fz;
+    }
+    return b;
+  };
+  // x | pixel x-1 | pixel x+1 (dilation; nothing beyond lanes 0 / 31) and x & x-1 & x+1 (erosion; ones beyond: lanes past the
+  // last column hold the erosion's identity anyway)
+  auto hor_or = [&](unsigned x) {
+    unsigned l = __shfl_up_sync(FULL, x, 1), r = __shfl_down_sync(FULL, x, 1);
+    if (lane == 0) l = 0u;
+    if (lane == 31) r = 0u;
+    return x | __funnelshift_l(l, x, 1) | __funnelshift_r(x, r, 1);
+  };
+  auto hor_and = [&](unsigned x) {
+    unsigned l = __shfl_up_sync(FULL, x, 1), r = __shfl_down_sync(FULL, x, 1);
+    if (lane == 0) l = FULL;
+    if (lane == 31) r = FULL;
+    return x & __funnelshift_l(l, x, 1) & __funnelshift_r(x, r, 1);
+  };
+  // in-image masks of the pixels left / right of every pixel of this lane's word
+  const unsigned inl = __funnelshift_l(lane > 0 ? inw : 0u, inw, 1);                              // the previous lane is a column whenever this one is
+  const unsigned inr = __funnelshift_r(inw, (lane + 1 < wpr) ? FULL : 0u, 1);
+  unsigned aD[P], bD[P], hD[P], aE[P], bE[P], hE[P];     // rows tp-2, tp-1 of X_p and the horizontal combination of row tp-1
+#pragma unroll
+  for (int p = 0; p < P; ++p) { aD[p] = bD[p] = hD[p] = 0u; aE[p] = bE[p] = hE[p] = FULL; }
+  unsigned above[4] = {0u, 0u, 0u, 0u}, cur[4] = {0u, 0u, 0u, 0u};   // ZL, ZR, FL, FR of rows y-1 and y
+  const int t0 = y0 - (P + 1), t1 = y1 + P;              // input rows t0 .. t1 inclusive
+  unsigned nextB = load_row(t0);
+#pragma unroll 1
+  for (int t = t0; t <= t1; ++t) {
+    const unsigned B = nextB;
+    nextB = load_row(t + 1);                             // one row ahead of the arithmetic
+    const unsigned in_t = ((unsigned)t < (unsigned)th) ? inw : 0u;
+    unsigned cD = B, cE = B | ~in_t;                     // X_0(t)
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      // X_(p+1)(tp - 1) from X_p(tp - 2), X_p(tp - 1), X_p(tp), tp = t - p; rows outside the image are reset to the identity
+      const unsigned in_o = ((unsigned)(t - p - 1) < (unsigned)th) ? inw : 0u;
+      const unsigned oD = (hD[p] | aD[p] | cD) & in_o;
+      const unsigned oE = (hE[p] & aE[p] & cE) | ~in_o;
+      aD[p] = bD[p]; bD[p] = cD; hD[p] = hor_or(cD);
+      aE[p] = bE[p]; bE[p] = cE; hE[p] = hor_and(cE);
+      cD = oD; cE = oE;
+    }
+    // cD / cE = X_P(yP), yP = t - P: Z = no dilated bit, F = eroded bit, ANDed with the pixel on the left / right
+    // (replicated at the image border: the pixel itself)
+    unsigned nw[4];
+    {
+      const unsigned z = ~cD, f = cE;
+      unsigned zl = __shfl_up_sync(FULL, z, 1), zr = __shfl_down_sync(FULL, z, 1), fl = __shfl_up_sync(FULL, f, 1), fr = __shfl_down_sync(FULL, f, 1);
+      if (lane == 0) { zl = 0u; fl = 0u; }
+      if (lane == 31) { zr = 0u; fr = 0u; }
+      nw[0] = z & (__funnelshift_l(zl, z, 1) | ~inl);
+      nw[1] = z & (__funnelshift_r(z, zr, 1) | ~inr);
+      nw[2] = f & (__funnelshift_l(fl, f, 1) | ~inl);
+      nw[3] = f & (__funnelshift_r(f, fr, 1) | ~inr);
+    }
+    const int y = t - P - 1;                             // the row whose three X_P rows are now known
+    if (y >= y0 && col) {                                // y < y1 by the loop bound
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        planes[(((int64_t)(2 * k) * nframes + n) * th + y) * wpr + lane] = cur[k] & (y > 0 ? above[k] : cur[k]);
+        planes[(((int64_t)(2 * k + 1) * nframes + n) * th + y) * wpr + lane] = cur[k] & (y + 1 < th ? nw[k] : cur[k]);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { above[k] = cur[k]; cur[k] = nw[k]; }
+  }
+}
+
 // plane index: (Z left, Z right, F left, F right) x (pair with the row above, pair with the row below) -> 2 * k + below.
 // NG groups of 4 output pixels per thread (4: 128-bit fuzzy loads and stores - a streaming kernel needs the bytes in
 // flight; 1: widths that are not a multiple of 16).  The NG groups of a thread read the same four plane words.
@@ -286,6 +393,18 @@ inline int tile_rows(int passes) {
   return oh >= 32 ? oh : TB_OH;
 }
 
+// rows per band of the marching kernel: a band re-computes 12 rows of halo, so bands are as tall as the machine allows -
+// about 12 warps per SM over the whole launch, never shorter than 12 rows (2x redundancy), never taller than 64
+inline int march_band_rows(int n, int th) {
+  static const int per_sm = [] { const char* e = getenv("VU_TM_WARPS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 12; }();   // sweep switch
+  const int64_t warps = (int64_t)device_sms() * per_sm;
+  int bands = (int)((warps + n - 1) / n);
+  if (bands < 1) bands = 1;
+  int rows = (th + bands - 1) / bands;
+  rows = rows < 12 ? 12 : (rows > 64 ? 64 : rows);
+  return rows;
+}
+
 }  // namespace
 }  // namespace vu
 
@@ -352,11 +471,19 @@ extern "C" int vu_trimap_bits_packed(const uint8_t* mask_bits, const uint8_t* fu
   const int64_t cap = ((int64_t)device_sms() * 8 + n - 1) / n;
   if (bx > cap) bx = cap;
   dim3 gb((unsigned)(bx < 1 ? 1 : bx), n);
+  // the reference's 5 passes at a working resolution of whole 32-pixel words: the marching kernel
+  static const bool march_off = [] { const char* e = getenv("VU_TRIMAP_MARCH"); return e && e[0] == '0'; }();   // A/B switch
+  const bool march = !march_off && iters == 5 && tw % 32 == 0 && wpr <= 32 && (reinterpret_cast<uintptr_t>(mask_bits) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(fuzzy_bits) & 15) == 0;
+  const int band = march_band_rows(n, th);
+  dim3 gm(((th + band - 1) / band + TM_WARPS - 1) / TM_WARPS, n);
   if (sc == 2) {
-    trimap_bits_kernel<2, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr, oh);
+    if (march) trimap_bits_march_kernel<2, 5><<<gm, 32 * TM_WARPS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, planes, n, wpr, band);
+    else trimap_bits_kernel<2, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr, oh);
     trimap_up_bits_kernel<2, 4, true><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy_bits, flags, out);
   } else {
-    trimap_bits_kernel<4, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr, oh);
+    if (march) trimap_bits_march_kernel<4, 5><<<gm, 32 * TM_WARPS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, planes, n, wpr, band);
+    else trimap_bits_kernel<4, true><<<ga, TB_THREADS, 0, S(stream)>>>(mask_bits, fuzzy_bits, flags, h, w, th, tw, iters, planes, n, wpr, oh);
     trimap_up_bits_kernel<4, 4, true><<<gb, TB_THREADS, 0, S(stream)>>>(planes, n, th, tw, wpr, fuzzy_bits, flags, out);
   }
   note_launch();
