@@ -375,34 +375,53 @@ __global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restric
 // s = t + 1 + (t >> 8) on two 16-bit lanes: byte 1 / 3 = floor(t / 255), byte 0 / 2 = 0 iff 255 | t and t > 0
 __device__ __forceinline__ unsigned div255_lanes(unsigned t) { return t + __byte_perm(t, 0u, 0x4341) + 0x00010001u; }
 
-__global__ void __launch_bounds__(THREADS) blend16_int_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
+// 78 registers, three CTAs per SM: capping them at 64 for a fourth CTA was no faster (0.954 against 0.948 ms)
+__global__ void __launch_bounds__(THREADS, 3) blend16_int_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
                                                               int64_t ngroups, int64_t bg_groups, uint4* __restrict__ out) {
   __shared__ double mtab[256];
   __shared__ uint4 park[7][THREADS];   // fg 0..2, bg 3..5, alpha 6 of the thread's group
   mtab[threadIdx.x] = __ddiv_rn((double)threadIdx.x, 255.0);   // THREADS == 256
   __syncthreads();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += stride) {
-    const uint4 av = ldg_stream16(alpha + g);
-    const unsigned all1 = av.x & av.y & av.z & av.w, any = av.x | av.y | av.z | av.w;
-    if (all1 == 0xFFFFFFFFu) {       // sixteen pixels of the foreground: the background is not read (as in blend16_kernel)
-#pragma unroll
-      for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, ldg_stream16(fg + 3 * g + k));
+  const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+  // what a group reads follows from its alphas: 0 = all 255 (sixteen pixels of the foreground: the background is not read),
+  // 1 = all 0 (the background alone), 2 = both
+  auto kind_of = [](const uint4& a) { return (a.x & a.y & a.z & a.w) == 0xFFFFFFFFu ? 0 : ((a.x | a.y | a.z | a.w) == 0u ? 1 : 2); };
+  uint4 f0, f1, f2, q0, q1, q2;   // scalars, not arrays: with arrays behind a lambda the compiler kept them on the stack
+#define VU_FETCH(gg, kind)                                                                   \
+  do {                                                                                       \
+    if ((kind) != 1) {                                                                       \
+      f0 = ldg_stream16(fg + 3 * (gg)); f1 = ldg_stream16(fg + 3 * (gg) + 1); f2 = ldg_stream16(fg + 3 * (gg) + 2); \
+    }                                                                                        \
+    if ((kind) != 0) {                                                                       \
+      const uint4* bp = bg + 3 * ((gg) % bg_groups);                                         \
+      if (bg_groups == ngroups) { q0 = ldg_stream16(bp); q1 = ldg_stream16(bp + 1); q2 = ldg_stream16(bp + 2); } \
+      else { q0 = __ldg(bp); q1 = __ldg(bp + 1); q2 = __ldg(bp + 2); }                       \
+    }                                                                                        \
+  } while (0)
+  // software pipeline over the thread's groups: the alphas run two groups ahead and the pixels one group ahead of the
+  // arithmetic, so that the next group's pixels are in flight while this group's candidates are walked and no group waits
+  // for its alphas before it can ask for its pixels
+  const int64_t g0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g0 >= ngroups) return;
+  uint4 av = ldg_stream16(alpha + g0);
+  uint4 av1 = g0 + stride < ngroups ? ldg_stream16(alpha + g0 + stride) : zero4;
+  VU_FETCH(g0, kind_of(av));
+  for (int64_t g = g0; g < ngroups; g += stride) {
+    const int64_t g1 = g + stride, g2 = g1 + stride;
+    const uint4 av2 = g2 < ngroups ? ldg_stream16(alpha + g2) : zero4;
+    const int kind = kind_of(av);
+    if (kind != 2) {
+      stg_stream16(out + 3 * g, kind == 0 ? f0 : q0);
+      stg_stream16(out + 3 * g + 1, kind == 0 ? f1 : q1);
+      stg_stream16(out + 3 * g + 2, kind == 0 ? f2 : q2);
+      if (g1 < ngroups) VU_FETCH(g1, kind_of(av1));
+      av = av1; av1 = av2;
       continue;
     }
-    const int64_t gb = g % bg_groups;
-    if (any == 0u) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k));
-      continue;
-    }
-    uint4 f[3], q[3], o[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) f[k] = ldg_stream16(fg + 3 * g + k);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) q[k] = (bg_groups == ngroups) ? ldg_stream16(bg + 3 * gb + k) : __ldg(bg + 3 * gb + k);
-    const unsigned* fw = reinterpret_cast<const unsigned*>(f);
-    const unsigned* qw = reinterpret_cast<const unsigned*>(q);
+    uint4 o[3];
+    const unsigned fw[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+    const unsigned qw[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
     const unsigned aw[4] = {av.x, av.y, av.z, av.w};
     unsigned* ow = reinterpret_cast<unsigned*>(o);
     unsigned accA = 0u, accB = 0u;   // candidate bits: byte b of output word w at bit 8 b + w (w < 8) / 8 b + w - 4 (w >= 8)
@@ -450,10 +469,17 @@ __global__ void __launch_bounds__(THREADS) blend16_int_kernel(const uint4* __res
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) stg_stream16(out + 3 * g + k, o[k]);
-    if (accA | accB) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { park[k][threadIdx.x] = f[k]; park[3 + k][threadIdx.x] = q[k]; }
+    const bool cand = (accA | accB) != 0u;
+    if (cand) {
+      // parked only now: parking every group up front (registers die early, 40 instead of 58, six CTAs per SM) was slower,
+      // 1.14 against 1.07 ms
+      park[0][threadIdx.x] = f0; park[1][threadIdx.x] = f1; park[2][threadIdx.x] = f2;
+      park[3][threadIdx.x] = q0; park[4][threadIdx.x] = q1; park[5][threadIdx.x] = q2;
       park[6][threadIdx.x] = av;
+    }
+    if (g1 < ngroups) VU_FETCH(g1, kind_of(av1));   // the registers are free: the next group's pixels travel during the walk below
+    av = av1; av1 = av2;
+    if (cand) {
       const uint8_t* pk = reinterpret_cast<const uint8_t*>(&park[0][threadIdx.x]);   // the thread's own bytes: no barrier
       uint8_t* o8 = reinterpret_cast<uint8_t*>(out + 3 * g);
       do {
@@ -472,6 +498,8 @@ __global__ void __launch_bounds__(THREADS) blend16_int_kernel(const uint4* __res
     }
   }
 }
+
+#undef VU_FETCH
 
 __global__ void __launch_bounds__(THREADS) fuse_bg_kernel(const unsigned* __restrict__ bg, const unsigned* __restrict__ always, int64_t nwords,
                                                           int64_t always_words, float beta, float omb, unsigned* __restrict__ out) {
