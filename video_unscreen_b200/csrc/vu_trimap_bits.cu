@@ -308,16 +308,38 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
   // unknown band far less often than 32 groups of one row.  Warp tiles in a grid-stride loop, one 32-bit division each.
   const int lane = threadIdx.x & 31;
   const int tiles_x = (tpr + 7) >> 3, tiles = tiles_x * ((th + 3) >> 2);
-  for (int tile = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5); tile < tiles; tile += gridDim.x * (TB_THREADS / 32)) {
+  // The tile loop is a software pipeline: the plane words (and the packed fuzzy bits) of the warp's NEXT tile are requested
+  // before this tile is worked on - a tile is ~60 instructions behind an L2 round trip, and with the loads inside the
+  // iteration the warps spent most of it waiting (ncu: long-scoreboard stalls 7 per issued instruction, 62 % of the issue slots)
+  const int tstep = gridDim.x * (TB_THREADS / 32);
+  unsigned nxt[8], nfz[PACKED ? SC : 1];
+  auto request = [&](int tile) {
     const int tyy = tile / tiles_x, txx = tile - tyy * tiles_x;
     const int r = tyy * 4 + (lane >> 3), t = txx * 8 + (lane & 7);
-    if (r >= th || t >= tpr) continue;
-    const unsigned* row = planes + ((int64_t)n * th + r) * wpr;
-    const int c0 = t * NG * CPG;                     // first working-resolution column of the thread: NG * CPG <= 8 bits, one word
-    const int j = c0 >> 5, b = c0 & 31;
-    unsigned pw[8];
+    if (tile >= tiles || r >= th || t >= tpr) return;
+    const unsigned* row = planes + ((int64_t)n * th + r) * wpr + ((t * NG * CPG) >> 5);
 #pragma unroll
-    for (int q = 0; q < 8; ++q) pw[q] = __ldg(row + q * psz + j) >> b;
+    for (int q = 0; q < 8; ++q) nxt[q] = __ldg(row + q * psz);
+    if (PACKED && ens) {
+#pragma unroll
+      for (int yi = 0; yi < SC; ++yi)
+        nfz[yi] = __ldg(reinterpret_cast<const unsigned short*>(fuzzy + ((((int64_t)n * h + SC * r + yi) * w + (int64_t)t * 4 * NG) >> 3)));
+    }
+  };
+  int tile = blockIdx.x * (TB_THREADS / 32) + (threadIdx.x >> 5);
+  request(tile);
+  for (; tile < tiles; tile += tstep) {
+    const int tyy = tile / tiles_x, txx = tile - tyy * tiles_x;
+    const int r = tyy * 4 + (lane >> 3), t = txx * 8 + (lane & 7);
+    const int c0 = t * NG * CPG;                     // first working-resolution column of the thread: NG * CPG <= 8 bits, one word
+    const int b = c0 & 31;
+    unsigned pw[8], fzb[PACKED ? SC : 1];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) pw[q] = nxt[q] >> b;
+#pragma unroll
+    for (int yi = 0; yi < (PACKED ? SC : 1); ++yi) fzb[yi] = nfz[yi];
+    request(tile + tstep);
+    if (r >= th || t >= tpr) continue;
 #pragma unroll
     for (int yi = 0; yi < SC; ++yi) {
     const int y = SC * r + yi, below = yi >= SC / 2;
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__(TB_THREADS) trimap_up_bits_kernel(const unsign
     const int64_t o = ((int64_t)n * h + y) * w + (int64_t)t * 4 * NG;
     unsigned fz[NG];
     if (ens && PACKED) {
-      const unsigned bits = __ldg(reinterpret_cast<const unsigned short*>(fuzzy + (o >> 3)));
+      const unsigned bits = fzb[yi];
 #pragma unroll
       for (int k = 0; k < NG; ++k) {
         const unsigned nib = (bits >> (4 * k)) & 15u;
