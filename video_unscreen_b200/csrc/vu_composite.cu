@@ -388,13 +388,13 @@ __global__ void __launch_bounds__(THREADS, 3) blend16_int_kernel(const uint4* __
   // 1 = all 0 (the background alone), 2 = both
   auto kind_of = [](const uint4& a) { return (a.x & a.y & a.z & a.w) == 0xFFFFFFFFu ? 0 : ((a.x | a.y | a.z | a.w) == 0u ? 1 : 2); };
   uint4 f0, f1, f2, q0, q1, q2;   // scalars, not arrays: with arrays behind a lambda the compiler kept them on the stack
-#define VU_FETCH(gg, kind)                                                                   \
+#define VU_FETCH(gg, gbb, kind)                                                              \
   do {                                                                                       \
     if ((kind) != 1) {                                                                       \
       f0 = ldg_stream16(fg + 3 * (gg)); f1 = ldg_stream16(fg + 3 * (gg) + 1); f2 = ldg_stream16(fg + 3 * (gg) + 2); \
     }                                                                                        \
     if ((kind) != 0) {                                                                       \
-      const uint4* bp = bg + 3 * ((gg) % bg_groups);                                         \
+      const uint4* bp = bg + 3 * (gbb);                                                      \
       if (bg_groups == ngroups) { q0 = ldg_stream16(bp); q1 = ldg_stream16(bp + 1); q2 = ldg_stream16(bp + 2); } \
       else { q0 = __ldg(bp); q1 = __ldg(bp + 1); q2 = __ldg(bp + 2); }                       \
     }                                                                                        \
@@ -406,16 +406,21 @@ __global__ void __launch_bounds__(THREADS, 3) blend16_int_kernel(const uint4* __
   if (g0 >= ngroups) return;
   uint4 av = ldg_stream16(alpha + g0);
   uint4 av1 = g0 + stride < ngroups ? ldg_stream16(alpha + g0 + stride) : zero4;
-  VU_FETCH(g0, kind_of(av));
+  // the background's group index, g mod bg_groups, advances with the loop: one 64-bit modulo per thread, not one per group
+  const int64_t sb = stride % bg_groups;
+  int64_t gb1 = g0 % bg_groups;
+  VU_FETCH(g0, gb1, kind_of(av));
   for (int64_t g = g0; g < ngroups; g += stride) {
     const int64_t g1 = g + stride, g2 = g1 + stride;
+    gb1 += sb;
+    if (gb1 >= bg_groups) gb1 -= bg_groups;
     const uint4 av2 = g2 < ngroups ? ldg_stream16(alpha + g2) : zero4;
     const int kind = kind_of(av);
     if (kind != 2) {
       stg_stream16(out + 3 * g, kind == 0 ? f0 : q0);
       stg_stream16(out + 3 * g + 1, kind == 0 ? f1 : q1);
       stg_stream16(out + 3 * g + 2, kind == 0 ? f2 : q2);
-      if (g1 < ngroups) VU_FETCH(g1, kind_of(av1));
+      if (g1 < ngroups) VU_FETCH(g1, gb1, kind_of(av1));
       av = av1; av1 = av2;
       continue;
     }
@@ -477,7 +482,7 @@ __global__ void __launch_bounds__(THREADS, 3) blend16_int_kernel(const uint4* __
       park[3][threadIdx.x] = q0; park[4][threadIdx.x] = q1; park[5][threadIdx.x] = q2;
       park[6][threadIdx.x] = av;
     }
-    if (g1 < ngroups) VU_FETCH(g1, kind_of(av1));   // the registers are free: the next group's pixels travel during the walk below
+    if (g1 < ngroups) VU_FETCH(g1, gb1, kind_of(av1));   // the registers are free: the next group's pixels travel during the walk below
     av = av1; av1 = av2;
     if (cand) {
       const uint8_t* pk = reinterpret_cast<const uint8_t*>(&park[0][threadIdx.x]);   // the thread's own bytes: no barrier
