@@ -516,6 +516,48 @@ def test_trimap_bits_tail(vu, sc, th, tw, iters):
     assert np.array_equal(got2, np.stack(want2))
 
 
+@pytest.mark.parametrize("sc,th,tw", [(2, 1, 32), (2, 7, 64), (4, 13, 32), (2, 40, 1024), (4, 200, 96), (2, 150, 160), (4, 11, 992), (2, 97, 960)])
+def test_trimap_bits_marching(vu, sc, th, tw):
+    """vu_trimap_bits_packed at working widths of whole 32-pixel words and the reference's 5 passes: the marching kernel
+    (trimap_bits_march_kernel: one warp per band of rows, 1 .. 32 word columns, bands shorter than their halo, one-row
+    images, several frames) against the oracle's generate_trimap and the ensemble branch of generate_trimap_withbg."""
+    h, w = sc * th, sc * tw
+    rng = np.random.default_rng(sc * 7919 + th * 31 + tw)
+    n = 3
+    masks = np.zeros((n, h, w), np.uint8)
+    yy, xx = np.mgrid[0:h, 0:w]
+    for i in range(n):
+        blob = (((xx - w * (0.25 + 0.25 * i)) / (w * 0.2)) ** 2 + ((yy - h * 0.5) / (h * 0.4)) ** 2) <= 1
+        masks[i][blob] = rng.integers(100, 256, int(blob.sum()))
+        masks[i][rng.random((h, w)) < 0.01] = 255
+        masks[i][rng.random((h, w)) < 0.01] = 0
+    masks[0, :, : 2 * sc] = 255; masks[0, : 2 * sc, :] = 255              # touching the borders (word 0 / the last word)
+    masks[1, -sc:, :] = 255; masks[1, :, -sc:] = 200
+    masks[2, :, w // 2 - sc: w // 2 + sc] = 255                           # a bar across a word seam
+    fuzzy = ((rng.random((n, h, w)) < 0.05) & (masks > 0)).astype(np.uint8)
+    flags = np.array([0, 1, 0], np.uint8)
+    long_side = max(th, tw)
+    want, want_plain = [], []
+    for i in range(n):
+        plain = R.generate_trimap(masks[i], long_side, 3, 5)
+        want_plain.append(plain)
+        if flags[i] == 0:
+            m = masks[i].copy()
+            m[fuzzy[i] > 0] = 0
+            t = R.generate_trimap(m, long_side, 3, 5)
+            t[fuzzy[i] > 0] = 128
+        else:
+            t = plain
+        want.append(t)
+    mb = np.packbits((masks[:, ::sc, ::sc] >= 128).astype(np.uint8), axis=-1, bitorder="little")
+    fzb = np.packbits(fuzzy, axis=-1, bitorder="little")
+    ops = vu.ops
+    got_plain = ops.trimap_bits_packed(torch.from_numpy(mb).cuda(), None, None, h, w, th, tw, 5).cpu().numpy()
+    assert np.array_equal(got_plain, np.stack(want_plain))
+    got = ops.trimap_bits_packed(torch.from_numpy(mb).cuda(), torch.from_numpy(fzb).cuda(), torch.from_numpy(flags).cuda(), h, w, th, tw, 5).cpu().numpy()
+    assert np.array_equal(got, np.stack(want))
+
+
 @pytest.mark.parametrize("sc,sh,sw", [(2, 135, 240), (4, 90, 160), (2, 7, 12), (4, 5, 6), (2, 33, 100), (4, 67, 34)])
 def test_resize_up_exact_scales(vu, sc, sh, sw):
     """vu_resize_up_u8 on exact 2x / 4x scales (the constant-weight kernel) against the cv2 model: random grey maps (every
