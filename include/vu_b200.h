@@ -183,7 +183,9 @@ int vu_trimap_bits(const uint8_t* mask, const uint8_t* fuzzy, const uint8_t* fla
 
 /* The same tail from bit planes (no full-resolution byte map is read): mask_bits [n][th][tw/8] = (nearest-sampled
  * mask >= 128) at the working resolution, fuzzy_bits [n][h][w/8] = one bit per full-resolution pixel (bit i of byte j =
- * pixel 8j + i), as vu_cf_alpha_up_fuzzy writes them; fuzzy_bits / flags may both be NULL.  tw % 16 == 0. */
+ * pixel 8j + i), as vu_cf_alpha_up_fuzzy writes them; fuzzy_bits / flags may both be NULL.  tw % 16 == 0.  The
+ * reference's iters == 5 at tw % 32 == 0, tw <= 1024 (every input_long_side of the agents) runs the marching kernel, one
+ * warp per band of rows; VU_TRIMAP_MARCH=0 in the environment keeps the tile kernel (same bytes). */
 int vu_trimap_bits_packed(const uint8_t* mask_bits, const uint8_t* fuzzy_bits, const uint8_t* flags, int n, int h, int w,
                           int th, int tw, int iters, uint8_t* out, void* workspace, size_t workspace_bytes,
                           vu_stream_t stream);
@@ -275,7 +277,12 @@ int vu_get_fg(const uint8_t* frame, const uint8_t* alpha, const uint8_t* bg, int
 int vu_get_bg(const uint8_t* alpha, const uint8_t* bg, int64_t npix, uint8_t* out, vu_stream_t stream);
 /* float64 blends (see vu_blend_mode).  alpha_channels is 1 (HW mask) or 3
  * (HWC mask, replace.py).  bg repeats every bg_npix pixels; may be NULL for
- * VU_BLEND_NAIVE. */
+ * VU_BLEND_NAIVE.  out may be fg (in place).  The bytes are those of the
+ * reference's float64 expression in every case; FUSE / REPLACE with one
+ * alpha channel, 16-byte aligned buffers, npix % 16 == 0 and an out that
+ * overlaps no input take the integer kernel (float64 only where the
+ * quotient is exact); VU_BLEND_FP64=1 in the environment keeps the float64
+ * kernel for them too. */
 int vu_blend(int mode, const uint8_t* fg, const uint8_t* alpha, int alpha_channels, const uint8_t* bg,
              int64_t npix, int64_t bg_npix, uint8_t* out, vu_stream_t stream);
 /* bg_offline.py:150-151: u8(f32(bg)*beta + (1-beta)*f32(bg_always)) */
