@@ -223,10 +223,16 @@ __global__ void __launch_bounds__(BS_THREADS, 3) bgstep_frame_kernel(const __gri
         bgr2hsv_px(c[3 * p], c[3 * p + 1], c[3 * p + 2], tab, ih, is, iv);
         // a == 255 (almost every pixel the gate lets through: the masks are binary): k = 1 - 255/255 = 0 exactly, the
         // background's HSV is multiplied by it: no need to compute it
-        if (a != 255) bgr2hsv_px(patch ? c[3 * p] : q[3 * p], patch ? c[3 * p + 1] : q[3 * p + 1], patch ? c[3 * p + 2] : q[3 * p + 2], tab, bh, bs, bv);
-        const float k = ktab[a];
-        hsv2bgr_px(trunc_clamp255b(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh)))), trunc_clamp255b(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs)))),
-                   trunc_clamp255b(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bv)))), tab, oo[3 * p], oo[3 * p + 1], oo[3 * p + 2]);
+        // ... nor the float arithmetic: trunc(clamp(x - 0 * y)) = x
+        int fh = ih, fs = is, fv = iv;
+        if (a != 255) {
+          bgr2hsv_px(patch ? c[3 * p] : q[3 * p], patch ? c[3 * p + 1] : q[3 * p + 1], patch ? c[3 * p + 2] : q[3 * p + 2], tab, bh, bs, bv);
+          const float k = ktab[a];
+          fh = trunc_clamp255b(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
+          fs = trunc_clamp255b(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
+          fv = trunc_clamp255b(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bv))));
+        }
+        hsv2bgr_px(fh, fs, fv, tab, oo[3 * p], oo[3 * p + 1], oo[3 * p + 2]);
       }
       pack12(oo, ow[3 * g], ow[3 * g + 1], ow[3 * g + 2]);
     }

@@ -177,10 +177,13 @@ __global__ void __launch_bounds__(THREADS) get_fg16_kernel(const uint4* __restri
         } else {
           bh = bs = bvv = 0;   // k = 1 - 255/255 = 0 exactly: the background's HSV is multiplied by it
         }
-        const float k = ktab[a];   // 1 - alpha/255.
-        const int fh = trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
-        const int fs = trunc_clamp255(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
-        const int fv2 = trunc_clamp255(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bvv))));
+        int fh = ih, fs = is, fv2 = iv;   // alpha == 255 (the inside of a matte): k = 0 exactly and trunc(clamp(x - 0 * y)) = x
+        if (a != 255) {
+          const float k = ktab[a];   // 1 - alpha/255.
+          fh = trunc_clamp255(__fsub_rn(u8_to_f32(ih), __fmul_rn(k, u8_to_f32(bh))));
+          fs = trunc_clamp255(__fsub_rn(u8_to_f32(is), __fmul_rn(k, u8_to_f32(bs))));
+          fv2 = trunc_clamp255(__fsub_rn(u8_to_f32(iv), __fmul_rn(k, u8_to_f32(bvv))));
+        }
         hsv2bgr_px(fh, fs, fv2, tab, o[3 * i], o[3 * i + 1], o[3 * i + 2]);
       }
       pack12(o, ow[3 * s4], ow[3 * s4 + 1], ow[3 * s4 + 2]);
