@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(THREADS) blend_kernel(const uint8_t* __restric
 // float64 pipe operations per output byte and nothing on the slow conversion unit.  (Tried: the blends in integers -
 // PRMT + IDP.4A + two IMAD per byte - with the float64 sequence only for the bytes whose quotient is exact, the only
 // ones where truncation can differ: bit-exact as well, but ~19 instructions per byte and a fix-up loop made it slower,
-// 1.33 ms against 1.15 ms per 300 1080p frames.)
+// 1.33 ms against 1.15 ms per 300 1080p frames.  blend16_int_kernel below is the integer variant that IS faster; it takes
+// the replace / fuse blends with one alpha channel, this kernel the rest.)
 __device__ __forceinline__ double u8_to_f64(unsigned x) { return __dsub_rn(__hiloint2double(0x43300000, (int)x), 4503599627370496.0); }
 __device__ __forceinline__ int f64_trunc_nonneg(double x) { return __double2loint(__dadd_rz(x, 4503599627370496.0)); }
 
@@ -378,7 +379,7 @@ __global__ void __launch_bounds__(THREADS) blend16_kernel(const uint4* __restric
 // s = t + 1 + (t >> 8) on two 16-bit lanes: byte 1 / 3 = floor(t / 255), byte 0 / 2 = 0 iff 255 | t and t > 0
 __device__ __forceinline__ unsigned div255_lanes(unsigned t) { return t + __byte_perm(t, 0u, 0x4341) + 0x00010001u; }
 
-// 78 registers, three CTAs per SM: capping them at 64 for a fourth CTA was no faster (0.954 against 0.948 ms)
+// 80 registers, three CTAs per SM: capping them at 64 for a fourth CTA was no faster (0.954 against 0.948 ms)
 __global__ void __launch_bounds__(THREADS, 3) blend16_int_kernel(const uint4* __restrict__ fg, const uint4* __restrict__ alpha, const uint4* __restrict__ bg,
                                                               int64_t ngroups, int64_t bg_groups, uint4* __restrict__ out) {
   __shared__ double mtab[256];
@@ -448,18 +449,18 @@ __global__ void __launch_bounds__(THREADS, 3) blend16_int_kernel(const uint4* __
         om[p] = 255u - m[p];
         mw[p] = om[p] * 256u + m[p];                                  // IDP.4A weights [a, 255 - a, 0, 0]
       }
-      const unsigned f0 = fw[3 * j], f1 = fw[3 * j + 1], f2 = fw[3 * j + 2];
-      const unsigned q0 = qw[3 * j], q1 = qw[3 * j + 1], q2 = qw[3 * j + 2];
+      const unsigned fa = fw[3 * j], fb = fw[3 * j + 1], fc = fw[3 * j + 2];   // the three words of the four pixels
+      const unsigned qa = qw[3 * j], qb = qw[3 * j + 1], qc = qw[3 * j + 2];
       // pairs (two channels of one pixel, one word): lanes [x, 0, y, 0]
-      const unsigned tP0 = __byte_perm(f0, 0u, 0x4140) * m[0] + __byte_perm(q0, 0u, 0x4140) * om[0];   // B0 G0
-      const unsigned tP1 = __byte_perm(f1, 0u, 0x4140) * m[1] + __byte_perm(q1, 0u, 0x4140) * om[1];   // G1 R1
-      const unsigned tP2 = __byte_perm(f1, 0u, 0x4342) * m[2] + __byte_perm(q1, 0u, 0x4342) * om[2];   // B2 G2
-      const unsigned tP3 = __byte_perm(f2, 0u, 0x4241) * m[3] + __byte_perm(q2, 0u, 0x4241) * om[3];   // B3 G3
+      const unsigned tP0 = __byte_perm(fa, 0u, 0x4140) * m[0] + __byte_perm(qa, 0u, 0x4140) * om[0];   // B0 G0
+      const unsigned tP1 = __byte_perm(fb, 0u, 0x4140) * m[1] + __byte_perm(qb, 0u, 0x4140) * om[1];   // G1 R1
+      const unsigned tP2 = __byte_perm(fb, 0u, 0x4342) * m[2] + __byte_perm(qb, 0u, 0x4342) * om[2];   // B2 G2
+      const unsigned tP3 = __byte_perm(fc, 0u, 0x4241) * m[3] + __byte_perm(qc, 0u, 0x4241) * om[3];   // B3 G3
       // singles: [c, q, *, *] . [a, 255 - a, 0, 0]
-      const unsigned tS0 = __dp4a(__byte_perm(f0, q0, 0x2262), mw[0], 0u);                              // R0
-      const unsigned tS1 = __dp4a(__byte_perm(f0, q0, 0x3373), mw[1], 0u);                              // B1
-      const unsigned tS2 = __dp4a(__byte_perm(f2, q2, 0x0040), mw[2], 0u);                              // R2
-      const unsigned tS3 = __dp4a(__byte_perm(f2, q2, 0x3373), mw[3], 0u);                              // R3
+      const unsigned tS0 = __dp4a(__byte_perm(fa, qa, 0x2262), mw[0], 0u);                              // R0
+      const unsigned tS1 = __dp4a(__byte_perm(fa, qa, 0x3373), mw[1], 0u);                              // B1
+      const unsigned tS2 = __dp4a(__byte_perm(fc, qc, 0x0040), mw[2], 0u);                              // R2
+      const unsigned tS3 = __dp4a(__byte_perm(fc, qc, 0x3373), mw[3], 0u);                              // R3
       const unsigned sP0 = div255_lanes(tP0), sP1 = div255_lanes(tP1), sP2 = div255_lanes(tP2), sP3 = div255_lanes(tP3);
       const unsigned sS01 = div255_lanes(tS1 * 65536u + tS0), sS23 = div255_lanes(tS3 * 65536u + tS2);
       ow[3 * j] = __byte_perm(sP0, sS01, 0x7531);
