@@ -30,6 +30,41 @@ def test_row_tiles_cover_with_halo():
             assert 0 <= r0 - ht and r1 + hb <= h
 
 
+def test_row_tiles_weighted_balance_the_cost():
+    """content-aware tile heights: same cover / alignment / halo rules as row_tiles, and never a larger maximum cost than
+    the equal-height partition (the job takes the slowest rank)."""
+    rng = np.random.default_rng(4)
+
+    def cost_of(tiles, cost):
+        h = len(cost)
+        return [float(cost[max(0, a - ht): min(h, b + hb)].sum()) for a, b, ht, hb in tiles]
+
+    cases = [(2160, 8, (28, 24), 4), (2160, 4, (28, 24), 4), (1080, 8, (16, 14), 2), (1080, 3, 0, 1), (96, 5, (8, 8), 4), (37, 4, 2, 1)]
+    for h, world, halo, align in cases:
+        y = np.arange(h)
+        person = 1.0 + 6.0 * np.exp(-((y - 0.5 * h) / (0.16 * h)) ** 2)          # the person stands in the middle rows
+        for cost in (person, np.ones(h), rng.random(h) + 0.01, np.where(y < h // 3, 10.0, 0.0)):
+            ts = shard.row_tiles_weighted(cost, world, halo, align)
+            assert len(ts) == world and ts[0][0] == 0 and ts[-1][1] == h
+            for (a0, a1, _, _), (b0, b1, _, _) in zip(ts, ts[1:]):
+                assert a1 == b0 and a0 < a1
+            for r0, r1, ht, hb in ts:
+                assert 0 <= r0 - ht and r1 + hb <= h and (r0 % align == 0) and (r1 % align == 0 or r1 == h)
+            top, bottom = (halo, halo) if isinstance(halo, int) else halo
+            for r0, r1, ht, hb in ts:
+                assert ht == min(top, r0) and hb == min(bottom, h - r1)
+            even = shard.row_tiles(h, world, halo, align)
+            assert max(cost_of(ts, cost)) <= max(cost_of(even, cost)) * (1 + 1e-9)
+    # the middle tiles of a person-shaped cost are the short ones
+    ts = shard.row_tiles_weighted(1.0 + 6.0 * np.exp(-((np.arange(2160) - 1080) / 350.0) ** 2), 8, (28, 24), 4)
+    heights = [b - a for a, b, _, _ in ts]
+    assert min(heights) == min(heights[3:5]) and max(heights) in (heights[0], heights[-1])
+    # fewer units than ranks: the equal partition's answer (empty tiles at the end)
+    assert shard.row_tiles_weighted(np.ones(5), 8, 0, 1) == shard.row_tiles(5, 8, 0, 1)
+    with pytest.raises(ValueError):
+        shard.row_tiles_weighted([1.0, -1.0], 2)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))

@@ -62,6 +62,68 @@ def row_tiles(height, world, halo=0, align=1):
     return out
 
 
+def row_tiles_weighted(row_cost, world, halo=0, align=1):
+    """``row_tiles`` with content-aware heights: contiguous tiles whose interior boundaries are multiples of ``align`` and
+    whose MAXIMUM cost is as small as such a partition allows, for a per-row cost estimate ``row_cost`` (length = image
+    height; e.g. for the bg_step stages a constant per row plus a term per segmentation-mask pixel of the row, summed over
+    the clip: where the person stands, get_fg and the trimap's unknown band cost more, and the job takes the slowest rank).
+    A tile's cost counts its halo rows too (they are recomputed).  Every rank gets at least one ``align`` unit when the
+    image has that many.  Same return format as ``row_tiles``; equal costs give the same heights up to one unit.
+
+    Host-side arithmetic only: the masks (1 byte per pixel) can be reduced to row sums before the frames (3 bytes per
+    pixel) are placed, so the tiles can be chosen before a rank loads its rows."""
+    top, bottom = (halo, halo) if isinstance(halo, int) else halo
+    cost = [float(c) for c in row_cost]
+    height = len(cost)
+    if world < 1 or top < 0 or bottom < 0 or align < 1 or any(c < 0 for c in cost):
+        raise ValueError("bad arguments")
+    units = -(-height // align)
+    if units <= world:                       # nothing to balance: one unit per rank, the rest empty
+        return row_tiles(height, world, halo, align)
+    pre = [0.0]
+    for c in cost:
+        pre.append(pre[-1] + c)
+
+    def tile_cost(u0, u1):                   # units [u0, u1) plus the halo rows around them
+        a, b = u0 * align, min(height, u1 * align)
+        return pre[min(height, b + bottom)] - pre[max(0, a - top)]
+
+    def cuts_for(limit):
+        """greedy: every tile as long as its cost stays within ``limit`` while leaving one unit for every later rank; None if
+        ``world`` tiles cannot cover the image that way"""
+        cuts, u = [0], 0
+        for r in range(world):
+            left = world - r - 1
+            end = u + 1
+            if tile_cost(u, end) > limit:
+                return None
+            while end < units - left and tile_cost(u, end + 1) <= limit:
+                end += 1
+            if left == 0 and end < units:
+                return None
+            u = end
+            cuts.append(u)
+        return cuts
+
+    lo = max(tile_cost(u, u + 1) for u in range(units))
+    hi = tile_cost(0, units)
+    best = cuts_for(hi)
+    for _ in range(60):                      # bisection on the admissible maximum
+        mid = 0.5 * (lo + hi)
+        got = cuts_for(mid)
+        if got is None:
+            lo = mid
+        else:
+            hi, best = mid, got
+        if hi - lo <= 1e-9 * max(hi, 1.0):
+            break
+    out = []
+    for r in range(world):
+        start, stop = best[r] * align, min(height, best[r + 1] * align)
+        out.append((start, stop, min(top, start), min(bottom, height - stop)))
+    return out
+
+
 def my_frame_range(n_frames, rank, world, align=1):
     return frame_ranges(n_frames, world, align)[rank]
 
